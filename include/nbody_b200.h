@@ -1,0 +1,186 @@
+/*
+ * nbody_b200.h -- C ABI of libnbody_b200.so: the B200-native replacement of the acceleration
+ * hot path of SciML/NBodySimulator.jl (reference v1.15.0).
+ *
+ * The reference is pure Julia and has no FFI of its own; every entry point below states the
+ * reference interface (file:line under /root/reference) whose work it takes over, i.e. what a
+ * Julia `ccall` shim binds (INTEGRATION.md shows the shim).
+ *
+ * Conventions
+ *   - Every function returns NBX_OK (0) or a negative nbx_status; the message of the last
+ *     failure of a context is returned by nbx_last_error().  Nothing throws, nothing exits.
+ *   - Host arrays `u`, `v`, `dv` are Julia `Matrix{Float64}` bytes: 3 x ncols, column-major
+ *     (x1 y1 z1 x2 y2 z2 ...).  They are caller-owned and only read/written during the call.
+ *     ncols == n, except with the Nose-Hoover thermostat where ncols == n + 1
+ *     (src/nbody_to_ode.jl:6-8).  Indices are 0-based everywhere in this ABI.
+ *   - One context == one simulation on one GPU.  Calls on a context are blocking and must
+ *     not be issued concurrently (the reference's RHS is called from one Julia task).
+ *   - There is NO CPU fallback: without a CUDA device nbx_create fails with NBX_ERR_CUDA.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NBX_API __attribute__((visibility("default")))
+#else
+#define NBX_API
+#endif
+
+typedef struct nbx_ctx nbx_ctx;
+
+typedef enum {
+    NBX_OK = 0,
+    NBX_ERR_INVALID = -1,     /* bad argument / call order                                    */
+    NBX_ERR_CUDA = -2,        /* CUDA runtime error (message holds cudaGetErrorString)        */
+    NBX_ERR_NONFINITE = -3,   /* NaN/Inf coordinate (the reference's wrap loop would hang)    */
+    NBX_ERR_UNSUPPORTED = -4, /* combination the reference itself cannot express              */
+    NBX_ERR_CAPACITY = -5     /* caller buffer too small (nbx_neighbors)                      */
+} nbx_status;
+
+/* boundary kinds: src/boundary_conditions.jl:68-72 (InfiniteBox), :101-103 (Cubic, b[0]=L),
+ * :25-29 (Periodic, b[0..5] = xlo xhi ylo yhi zlo zhi; NOT a minimum image, kept as is). */
+enum { NBX_BC_INFINITE = 0, NBX_BC_CUBIC = 1, NBX_BC_PERIODIC = 2 };
+
+/* thermostat kinds: src/thermostats.jl (Berendsen :60-83, Nose-Hoover :93-128, Andersen and
+ * Langevin structs) -- Andersen/Langevin act in the stepper (nbx_step_*), not in the RHS. */
+enum { NBX_THERMO_NONE = 0, NBX_THERMO_BERENDSEN = 1, NBX_THERMO_NOSEHOOVER = 2,
+       NBX_THERMO_ANDERSEN = 3, NBX_THERMO_LANGEVIN = 4 };
+
+/* timing phases for nbx_timing_get */
+enum { NBX_T_PAIR_ALLPAIRS = 0,  /* tiled all-pairs kernel (gravity / Coulomb / dipole / PBC)   */
+       NBX_T_CELL_BUILD = 1,     /* wrap -> cell id -> count -> scan -> scatter                 */
+       NBX_T_PAIR_CELLS = 2,     /* cutoff pair kernel over the cell list                       */
+       NBX_T_BONDED = 3,         /* SPC/Fw bonds + angle                                        */
+       NBX_T_INTEGRATE = 4,      /* fused velocity-Verlet / thermostat update kernels           */
+       NBX_T_TRANSPOSE = 5,      /* AoS <-> SoA at the boundary                                 */
+       NBX_T_COUNT = 6 };
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* One context per NBodySimulation (src/nbody_simulation.jl:42-54).  `device` is the CUDA
+ * ordinal.  Fails loudly (NBX_ERR_CUDA) when no sm_100 device is present. */
+NBX_API int nbx_create(nbx_ctx **out, int device);
+NBX_API int nbx_destroy(nbx_ctx *ctx);
+/* Message of the last failing call on ctx (ctx == NULL: of the last failing nbx_create). */
+NBX_API const char *nbx_last_error(const nbx_ctx *ctx);
+/* Library/ABI version (major*10000 + minor*100 + patch). */
+NBX_API int nbx_version(void);
+
+/* ---- system description (what the reference's closures capture) ----------------------- */
+/* Per-particle tables built once at problem construction by obtain_data_for_*:
+ * masses (src/nbody_to_ode.jl:290-300, src/nbody_simulation_result.jl:121-139), charges
+ * (:316-351), magnetic moments 3 x n (src/bodies.jl:102-107).  q and mm may be NULL.
+ * water != 0: the n columns are (O, H1, H2) triples (src/nbody_to_ode.jl:46): LJ acts on the
+ * oxygen columns only (:302-314) and Coulomb excludes the own molecule (:331-351). */
+NBX_API int nbx_system(nbx_ctx *ctx, int64_t n, const double *m, const double *q,
+                       const double *mm, int water);
+/* Boundary conditions used by get_interparticle_distance (src/boundary_conditions.jl:111-172). */
+NBX_API int nbx_boundary(nbx_ctx *ctx, int kind, const double *b);
+
+/* Potentials == the entries of PotentialNBodySystem.potentials (src/nbody_system.jl:72-122);
+ * each nbx_add_* replaces the closure get_accelerating_function returns for that parameter
+ * type (src/nbody_to_ode.jl:156-242).  Evaluation order is fixed: lennard_jones,
+ * electrostatic, magnetostatic, gravitational, then SPC/Fw bonded terms. */
+/* GravitationalParameters(G), gravitational_acceleration!  src/basic_potentials.jl:306-331 */
+NBX_API int nbx_add_gravity(nbx_ctx *ctx, double G);
+/* LennardJonesParameters(eps, sigma, R), pairwise_lennard_jones_acceleration!  :240-272 */
+NBX_API int nbx_add_lj(nbx_ctx *ctx, double eps, double sigma, double R);
+/* ElectrostaticParameters(k, R) (R may be +Inf), pairwise_electrostatic_acceleration! :274-304 */
+NBX_API int nbx_add_coulomb(nbx_ctx *ctx, double k, double R);
+/* MagnetostaticParameters(mu_4pi), magnetostatic_dipdip_acceleration!  :333-365 */
+NBX_API int nbx_add_dipole(nbx_ctx *ctx, double mu_4pi);
+/* SPCFwParameters(rOH, aHOH, kb, ka): harmonic_bond_potential_acceleration! :367-393 and
+ * valence_angle_potential_acceleration! :395-433 (requires water != 0). */
+NBX_API int nbx_add_spcfw(nbx_ctx *ctx, double rOH, double aHOH, double kb, double ka);
+NBX_API int nbx_clear_potentials(nbx_ctx *ctx);
+
+/* Thermostat (src/thermostats.jl; wiring src/nbody_to_ode.jl:377-433).
+ *   BERENDSEN : param = tau  (gamma = 0.5/tau, :72-74)
+ *   NOSEHOOVER: param = tau
+ *   ANDERSEN  : param = nu   (src/nbody_simulation_result.jl:504-540)
+ *   LANGEVIN  : param = gamma (src/nbody_to_ode.jl:567-598)
+ * N, Nc: particle / constraint counts of md_temperature (:87-91): N = n, Nc = 0 for atoms;
+ * N = n (=3*molecules), Nc = 2*molecules for water (src/nbody_to_ode.jl:402-408). */
+NBX_API int nbx_thermostat(nbx_ctx *ctx, int kind, double T0, double param, double kB,
+                           int64_t N, int64_t Nc);
+
+/* Multi-GPU: this context evaluates only target columns [lo, hi) (all columns are sources).
+ * Default [0, n).  Columns outside the range are left untouched in device state and are
+ * written as zeros by nbx_accel.  (No reference equivalent: the reference is serial.) */
+NBX_API int nbx_shard(nbx_ctx *ctx, int64_t lo, int64_t hi);
+
+/* ---- RHS drop-in ---------------------------------------------------------------------- */
+/* soode_system!(dv, v, u, p, t): src/nbody_to_ode.jl:474-488 (PotentialNBodySystem) and
+ * :502-532 (WaterSPCFw).  Host pointers, 3 x ncols each.  dv is overwritten.  With the
+ * Nose-Hoover thermostat v[3n] is rewritten exactly as the reference mutates it
+ * (src/thermostats.jl:126); otherwise v is read-only. */
+NBX_API int nbx_accel(nbx_ctx *ctx, const double *u, double *v, double t, double *dv);
+
+/* ---- device-resident stepping (the fused drop-in for run_simulation) ------------------- */
+/* run_simulation(sim, VelocityVerlet(), dt) : src/nbody_simulation_result.jl:468-487.
+ * upload sets x(0), v(0) and evaluates a(0); step_vv advances nsteps with
+ *   x+ = x + dt v + dt^2/2 a;  a+ = f(v, x+);  v+ = v + dt/2 (a + a+)
+ * (OrdinaryDiffEqSymplecticRK VelocityVerlet, upstream); Berendsen / Nose-Hoover enter
+ * through f, Andersen resamples velocities after each step.  step_em is Euler-Maruyama on
+ * the Langevin SDE (src/nbody_to_ode.jl:575-595).  download copies state back (any pointer
+ * may be NULL). */
+NBX_API int nbx_upload(nbx_ctx *ctx, const double *u, const double *v);
+NBX_API int nbx_step_vv(nbx_ctx *ctx, double dt, int64_t nsteps);
+NBX_API int nbx_step_em(nbx_ctx *ctx, double dt, int64_t nsteps, uint64_t seed);
+NBX_API int nbx_download(nbx_ctx *ctx, double *u, double *v, double *dv);
+NBX_API int nbx_set_seed(nbx_ctx *ctx, uint64_t seed);
+
+/* Split form of one velocity-Verlet step for multi-GPU drivers that exchange positions
+ * between the halves:  begin = position update of the own shard;  the host all-gathers the
+ * SoA position arrays (nbx_device_ptr);  finish = forces + velocity update of the shard. */
+NBX_API int nbx_vv_begin(nbx_ctx *ctx, double dt);
+NBX_API int nbx_vv_finish(nbx_ctx *ctx, double dt);
+/* Evaluate a = f(v, x) of the resident state (all potentials + RHS thermostats). */
+NBX_API int nbx_eval_resident(nbx_ctx *ctx);
+
+/* kinetic_energy src/nbody_simulation_result.jl:209-212; potential_energy :239-264
+ * (lennard_jones_potential :293-319, electrostatic_potential :321-351,
+ * harmonic_bonds_potential :353-372, valence_angle_harmonic_potential :374-397);
+ * temperature = md_temperature src/thermostats.jl:87-91 of the resident velocities.
+ * Any pointer may be NULL. */
+NBX_API int nbx_energy(nbx_ctx *ctx, double *ekin, double *epot, double *temperature);
+
+/* In-cutoff ordered pair set of the LJ predicate (get_interparticle_distance +
+ * `rij_2 < p.R2`, src/basic_potentials.jl:253-258) for the resident positions, as CSR:
+ * offsets[n+1], list[offsets[n]] with the partners of each column in ascending order.
+ * cap = capacity of list in entries; NBX_ERR_CAPACITY if too small (offsets still valid). */
+NBX_API int nbx_neighbors(nbx_ctx *ctx, int64_t *offsets, int32_t *list, int64_t cap);
+
+/* ---- plumbing for the host layer ------------------------------------------------------- */
+/* CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on; NULL = own stream. */
+NBX_API int nbx_set_stream(nbx_ctx *ctx, void *stream);
+NBX_API int nbx_synchronize(nbx_ctx *ctx);
+/* Device pointers of the resident SoA state: which = 0 pos, 1 vel, 2 acc; each is
+ * double[3][*ld] (x-row, y-row, z-row) with row stride *ld >= n. */
+NBX_API int nbx_device_ptr(nbx_ctx *ctx, int which, void **ptr, int64_t *ld);
+/* Device-pointer form of nbx_accel (u, v, dv are DEVICE pointers, AoS 3 x ncols). */
+NBX_API int nbx_accel_device(nbx_ctx *ctx, const double *u_dev, double *v_dev, double t,
+                             double *dv_dev);
+/* Per-phase device timers (CUDA events on ctx's stream).  enable != 0 starts recording;
+ * get returns the summed duration and launch count since the last reset. */
+NBX_API int nbx_timing_enable(nbx_ctx *ctx, int enable);
+NBX_API int nbx_timing_get(nbx_ctx *ctx, int phase, double *total_ms, int64_t *count);
+NBX_API int nbx_timing_reset(nbx_ctx *ctx);
+/* Tuning knobs (integers): "cell_list" (0 = never, 1 = auto),
+ * "rebuild_every", "pair_prefilter", "graph" ...  Unknown key -> NBX_ERR_INVALID. */
+NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, int64_t value);
+NBX_API int nbx_get_info(nbx_ctx *ctx, const char *key, int64_t *value);
+/* DFMA-saturation microbenchmark: the measured FP64 roofline denominator (TFLOP/s). */
+NBX_API int nbx_measure_fp64_peak(nbx_ctx *ctx, double *tflops, double *sm_mhz_effective);
+/* STREAM-style copy bandwidth (GB/s, read+write) of this device, for the HBM roofline. */
+NBX_API int nbx_measure_hbm_peak(nbx_ctx *ctx, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H */

@@ -1,0 +1,278 @@
+"""ctypes binding of libnbody_b200.so -- exactly the symbols include/nbody_b200.h declares.
+
+No CPU fallback: :func:`load` raises if the library is missing, and ``nbx_create`` fails without a
+CUDA device.  :class:`Context` is a thin object wrapper over one ``nbx_ctx``; the reference-shaped
+host API lives in ``api.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnbody_b200.so")
+
+NBX_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_UNSUPPORTED, ERR_CAPACITY = -1, -2, -3, -4, -5
+BC_INFINITE, BC_CUBIC, BC_PERIODIC = 0, 1, 2
+THERMO_NONE, THERMO_BERENDSEN, THERMO_NOSEHOOVER, THERMO_ANDERSEN, THERMO_LANGEVIN = 0, 1, 2, 3, 4
+T_PAIR_ALLPAIRS, T_CELL_BUILD, T_PAIR_CELLS, T_BONDED, T_INTEGRATE, T_TRANSPOSE = 0, 1, 2, 3, 4, 5
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); must list every NBX_API symbol of include/nbody_b200.h
+SIGNATURES = {
+    "nbx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "nbx_destroy": (C.c_int, [_vp]),
+    "nbx_last_error": (C.c_char_p, [_vp]),
+    "nbx_version": (C.c_int, []),
+    "nbx_system": (C.c_int, [_vp, _i64, _dp, _dp, _dp, C.c_int]),
+    "nbx_boundary": (C.c_int, [_vp, C.c_int, _dp]),
+    "nbx_add_gravity": (C.c_int, [_vp, C.c_double]),
+    "nbx_add_lj": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
+    "nbx_add_coulomb": (C.c_int, [_vp, C.c_double, C.c_double]),
+    "nbx_add_dipole": (C.c_int, [_vp, C.c_double]),
+    "nbx_add_spcfw": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "nbx_clear_potentials": (C.c_int, [_vp]),
+    "nbx_thermostat": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, _i64, _i64]),
+    "nbx_shard": (C.c_int, [_vp, _i64, _i64]),
+    "nbx_accel": (C.c_int, [_vp, _dp, _dp, C.c_double, _dp]),
+    "nbx_upload": (C.c_int, [_vp, _dp, _dp]),
+    "nbx_step_vv": (C.c_int, [_vp, C.c_double, _i64]),
+    "nbx_step_em": (C.c_int, [_vp, C.c_double, _i64, C.c_uint64]),
+    "nbx_download": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "nbx_set_seed": (C.c_int, [_vp, C.c_uint64]),
+    "nbx_vv_begin": (C.c_int, [_vp, C.c_double]),
+    "nbx_vv_finish": (C.c_int, [_vp, C.c_double]),
+    "nbx_eval_resident": (C.c_int, [_vp]),
+    "nbx_energy": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "nbx_neighbors": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), _i64]),
+    "nbx_set_stream": (C.c_int, [_vp, _vp]),
+    "nbx_synchronize": (C.c_int, [_vp]),
+    "nbx_device_ptr": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "nbx_accel_device": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp]),
+    "nbx_timing_enable": (C.c_int, [_vp, C.c_int]),
+    "nbx_timing_get": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(_i64)]),
+    "nbx_timing_reset": (C.c_int, [_vp]),
+    "nbx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "nbx_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64)]),
+    "nbx_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
+    "nbx_measure_hbm_peak": (C.c_int, [_vp, _dp]),
+}
+
+_lib = None
+
+
+class NbxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"nbx error {code}: {msg}")
+        self.code = code
+
+
+def load(build_if_missing: bool = False):
+    """dlopen libnbody_b200.so and set the prototypes.  Raises if it is not there (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            if build_if_missing:
+                from . import build as _b
+
+                _b.build()
+            else:
+                raise OSError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                              "there is no CPU fallback for the acceleration path")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _f(a, ncols=None):
+    """float64 (3, ncols) array with Julia's Matrix{Float64} bytes (Fortran order)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2 or a.shape[0] != 3 or (ncols is not None and a.shape[1] != ncols):
+        raise ValueError(f"expected a (3, {ncols if ncols is not None else 'n'}) array, got {a.shape}")
+    return a if a.flags.f_contiguous else np.asfortranarray(a)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Context:
+    """One nbx_ctx: one simulation on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.nbx_create(C.byref(h), int(device))
+        if rc != NBX_OK:
+            raise NbxError(rc, self.lib.nbx_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self.ncols = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nbx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != NBX_OK:
+            raise NbxError(rc, self.lib.nbx_last_error(self.h).decode())
+
+    def _refresh(self):
+        self.ncols = self.info("ncols")
+
+    # -- description -------------------------------------------------------------------
+    def system(self, ms, qs=None, mm=None, water=False):
+        ms = np.ascontiguousarray(ms, dtype=np.float64)
+        qs = None if qs is None else np.ascontiguousarray(qs, dtype=np.float64)
+        mm = None if mm is None else _f(mm, ms.shape[0])
+        if qs is not None and qs.shape != ms.shape:
+            raise ValueError("charges must match masses")
+        self._ck(self.lib.nbx_system(self.h, ms.shape[0], _p(ms), _p(qs), _p(mm), int(bool(water))))
+        self.n = int(ms.shape[0])
+        self._refresh()
+
+    def boundary(self, kind, box=None):
+        b = None if box is None else np.ascontiguousarray(np.atleast_1d(box), dtype=np.float64)
+        self._ck(self.lib.nbx_boundary(self.h, int(kind), _p(b)))
+
+    def add_gravity(self, G):
+        self._ck(self.lib.nbx_add_gravity(self.h, float(G)))
+
+    def add_lj(self, eps, sigma, R):
+        self._ck(self.lib.nbx_add_lj(self.h, float(eps), float(sigma), float(R)))
+
+    def add_coulomb(self, k, R=float("inf")):
+        self._ck(self.lib.nbx_add_coulomb(self.h, float(k), float(R)))
+
+    def add_dipole(self, mu_4pi):
+        self._ck(self.lib.nbx_add_dipole(self.h, float(mu_4pi)))
+
+    def add_spcfw(self, rOH, aHOH, kb, ka):
+        self._ck(self.lib.nbx_add_spcfw(self.h, float(rOH), float(aHOH), float(kb), float(ka)))
+
+    def clear_potentials(self):
+        self._ck(self.lib.nbx_clear_potentials(self.h))
+
+    def thermostat(self, kind, T0=0.0, param=0.0, kB=1.0, N=None, Nc=0):
+        self._ck(self.lib.nbx_thermostat(self.h, int(kind), float(T0), float(param), float(kB),
+                                         int(self.n if N is None else N), int(Nc)))
+        self._refresh()
+
+    def shard(self, lo, hi):
+        self._ck(self.lib.nbx_shard(self.h, int(lo), int(hi)))
+
+    # -- RHS drop-in -------------------------------------------------------------------------
+    def accel(self, u, v=None, t=0.0, out=None):
+        """soode_system!(dv, v, u, p, t): returns dv (3, ncols).  ``v`` is mutated for Nose-Hoover."""
+        u = _f(u, self.ncols)
+        if v is not None:
+            if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.f_contiguous
+                    and v.shape == (3, self.ncols)):
+                raise ValueError("v must be a float64 Fortran-ordered (3, ncols) array (it may be written)")
+        dv = np.empty((3, self.ncols), order="F") if out is None else out
+        self._ck(self.lib.nbx_accel(self.h, _p(u), _p(v), float(t), _p(dv)))
+        return dv
+
+    # -- resident stepping ---------------------------------------------------------------------
+    def upload(self, u, v):
+        self._ck(self.lib.nbx_upload(self.h, _p(_f(u, self.ncols)), _p(_f(v, self.ncols))))
+
+    def step_vv(self, dt, nsteps=1):
+        self._ck(self.lib.nbx_step_vv(self.h, float(dt), int(nsteps)))
+
+    def step_em(self, dt, nsteps=1, seed=0):
+        self._ck(self.lib.nbx_step_em(self.h, float(dt), int(nsteps), int(seed)))
+
+    def vv_begin(self, dt):
+        self._ck(self.lib.nbx_vv_begin(self.h, float(dt)))
+
+    def vv_finish(self, dt):
+        self._ck(self.lib.nbx_vv_finish(self.h, float(dt)))
+
+    def eval_resident(self):
+        self._ck(self.lib.nbx_eval_resident(self.h))
+
+    def set_seed(self, seed):
+        self._ck(self.lib.nbx_set_seed(self.h, int(seed)))
+
+    def download(self, want_u=True, want_v=True, want_dv=False):
+        u = np.empty((3, self.ncols), order="F") if want_u else None
+        v = np.empty((3, self.ncols), order="F") if want_v else None
+        dv = np.empty((3, self.ncols), order="F") if want_dv else None
+        self._ck(self.lib.nbx_download(self.h, _p(u), _p(v), _p(dv)))
+        return u, v, dv
+
+    def energy(self, potential=True):
+        ek, ep, T = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.nbx_energy(self.h, C.byref(ek), C.byref(ep) if potential else None, C.byref(T)))
+        return ek.value, (ep.value if potential else None), T.value
+
+    def neighbors(self, cap=None):
+        n = self.n // 3 if self.info("water") else self.n
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        cap = int(cap if cap is not None else 256 * n)
+        lst = np.zeros(max(cap, 1), dtype=np.int32)
+        self._ck(self.lib.nbx_neighbors(self.h, offsets.ctypes.data_as(C.POINTER(_i64)),
+                                        lst.ctypes.data_as(C.POINTER(C.c_int32)), cap))
+        return offsets, lst[: offsets[-1]]
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.nbx_set_stream(self.h, _vp(stream_ptr) if stream_ptr else None))
+
+    def synchronize(self):
+        self._ck(self.lib.nbx_synchronize(self.h))
+
+    def device_ptr(self, which):
+        p, ld = _vp(), _i64()
+        self._ck(self.lib.nbx_device_ptr(self.h, int(which), C.byref(p), C.byref(ld)))
+        return int(p.value), int(ld.value)
+
+    def accel_device(self, u_ptr, v_ptr, dv_ptr, t=0.0):
+        self._ck(self.lib.nbx_accel_device(self.h, _vp(u_ptr), _vp(v_ptr) if v_ptr else None, float(t), _vp(dv_ptr)))
+
+    def timing_enable(self, on=True):
+        self._ck(self.lib.nbx_timing_enable(self.h, int(bool(on))))
+
+    def timing_get(self, phase):
+        ms, cnt = C.c_double(), _i64()
+        self._ck(self.lib.nbx_timing_get(self.h, int(phase), C.byref(ms), C.byref(cnt)))
+        return ms.value, int(cnt.value)
+
+    def timing_reset(self):
+        self._ck(self.lib.nbx_timing_reset(self.h))
+
+    def set_option(self, key, value):
+        self._ck(self.lib.nbx_set_option(self.h, key.encode(), int(value)))
+
+    def info(self, key):
+        v = _i64()
+        self._ck(self.lib.nbx_get_info(self.h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def measure_fp64_peak(self):
+        tf, mhz = C.c_double(), C.c_double()
+        self._ck(self.lib.nbx_measure_fp64_peak(self.h, C.byref(tf), C.byref(mhz)))
+        return tf.value, mhz.value
+
+    def measure_hbm_peak(self):
+        g = C.c_double()
+        self._ck(self.lib.nbx_measure_hbm_peak(self.h, C.byref(g)))
+        return g.value

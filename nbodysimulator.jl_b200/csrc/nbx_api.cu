@@ -1,0 +1,700 @@
+// nbx_api.cu -- the C ABI of include/nbody_b200.h: context lifetime, system description, the RHS
+// drop-in (soode_system!, src/nbody_to_ode.jl:474-488 and :502-532) and device-resident stepping.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+static thread_local std::string g_create_error;
+
+int fail(nbx_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+int cuda_fail(nbx_ctx *c, cudaError_t e, const char *what)
+{
+    cudaGetLastError(); // clear the sticky-free error state
+    return fail(c, NBX_ERR_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+// ---- timers ----------------------------------------------------------------------------------
+static void timer_flush(nbx_ctx *c, Timer &t)
+{
+    if (t.used == 0) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t k = 0; k + 1 < t.used; k += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.ev[k], t.ev[k + 1]) == cudaSuccess) { t.total_ms += ms; t.count++; }
+    }
+    t.used = 0;
+}
+
+void timer_begin(nbx_ctx *c, int phase)
+{
+    if (!c->timing) return;
+    Timer &t = c->timers[phase];
+    if (t.used + 2 > t.ev.size()) {
+        if (t.ev.size() >= (size_t)2 * kMaxTimers) timer_flush(c, t);
+        else {
+            const size_t grow = t.ev.size() + 64;
+            while (t.ev.size() < grow) { cudaEvent_t e; cudaEventCreate(&e); t.ev.push_back(e); }
+        }
+    }
+    cudaEventRecord(t.ev[t.used], c->stream);
+}
+
+void timer_end(nbx_ctx *c, int phase)
+{
+    if (!c->timing) return;
+    Timer &t = c->timers[phase];
+    cudaEventRecord(t.ev[t.used + 1], c->stream);
+    t.used += 2;
+}
+
+// ---- small kernels that belong to the RHS assembly -----------------------------------------------
+// oxygen columns of water (every third, src/nbody_to_ode.jl:302-314) <-> compact SoA
+__global__ void gather_oxygen_kernel(const double *__restrict__ pos, int64_t ld, int nmol, double *__restrict__ opos,
+                                     int64_t old, double far)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= old) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) opos[d * old + m] = m < nmol ? pos[d * ld + 3 * (int64_t)m] : far;
+}
+
+__global__ void scatter_oxygen_kernel(const double *__restrict__ oacc, int64_t old, int mlo, int mhi,
+                                      double *__restrict__ acc, int64_t ld)
+{
+    const int m = mlo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= mhi) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) acc[d * ld + 3 * (int64_t)m] += oacc[d * old + m];
+}
+
+static int zero_rows(nbx_ctx *c, double *rows, int64_t lo, int64_t hi)
+{
+    if (hi <= lo) return NBX_OK;
+    for (int d = 0; d < 3; ++d)
+        NBX_CUDA(c, cudaMemsetAsync(rows + d * c->npad + lo, 0, sizeof(double) * (size_t)(hi - lo), c->stream));
+    return NBX_OK;
+}
+
+// pos (+ vel, d_scal) -> acc for the target columns [tgt_lo, tgt_hi); everything stays on the stream
+int compute_accel(nbx_ctx *c)
+{
+    const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
+    NBX_TRY(zero_rows(c, c->acc, lo, hi));
+
+    if (c->has_lj) {
+        if (c->water) {
+            const int nmol = (int)(c->n / 3);
+            const int mlo = (int)((lo + 2) / 3), mhi = (int)((hi + 2) / 3);
+            gather_oxygen_kernel<<<(unsigned)((c->opad + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, nmol, c->opos,
+                                                                                         c->opad, kFarAway);
+            NBX_CUDA(c, cudaGetLastError());
+            NBX_TRY(cells_plan(c, c->lj_R, nmol, &c->cl_lj.grid));
+            if (c->cl_lj.grid.valid) {
+                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nmol, c->opad));
+                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, mlo, mhi, 3, c->oacc, c->opad, false));
+            } else {
+                NBX_TRY(launch_allpairs_pbc(c, 0, c->opos, nmol, c->opad, mlo, mhi, 3, c->oacc, c->opad, false));
+            }
+            if (mhi > mlo) {
+                scatter_oxygen_kernel<<<(unsigned)((mhi - mlo + 255) / 256), 256, 0, c->stream>>>(c->oacc, c->opad, mlo, mhi,
+                                                                                                c->acc, c->npad);
+                NBX_CUDA(c, cudaGetLastError());
+            }
+        } else {
+            NBX_TRY(cells_plan(c, c->lj_R, c->n, &c->cl_lj.grid));
+            if (c->cl_lj.grid.valid) {
+                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->n, c->npad));
+                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, true));
+            } else {
+                NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));
+            }
+        }
+    }
+    if (c->has_coul) {
+        const int pot = c->water ? 2 : 1;
+        if (!c->water && c->bc_kind == NBX_BC_INFINITE && isinf(c->el_R2)) {
+            // F += q_j (ri - rj)/r^3, dv += k q_i / m_i F  ==  -k q_i/m_i * sum q_j (rj - ri)/r^3
+            NBX_TRY(launch_allpairs_grav(c, c->charge, 1, -c->el_k, c->acc, true));
+        } else {
+            NBX_TRY(cells_plan(c, c->el_R, c->n, &c->cl_el.grid));
+            if (c->cl_el.grid.valid) {
+                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->n, c->npad));
+                NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, true));
+            } else {
+                NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));
+            }
+        }
+    }
+    if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, true));
+    if (c->has_grav) NBX_TRY(launch_allpairs_grav(c, c->mass, 0, c->G, c->acc, true));
+    if (c->has_spcfw) NBX_TRY(launch_spcfw_bonded(c, c->acc));
+    NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel));
+    return NBX_OK;
+}
+
+static void free_system(nbx_ctx *c)
+{
+    cudaFree(c->mass); cudaFree(c->charge); cudaFree(c->mm);
+    cudaFree(c->pos); cudaFree(c->vel); cudaFree(c->acc); cudaFree(c->acc_old);
+    cudaFree(c->aos_u); cudaFree(c->aos_v); cudaFree(c->aos_dv);
+    cudaFree(c->opos); cudaFree(c->oacc);
+    c->mass = c->charge = c->mm = c->pos = c->vel = c->acc = c->acc_old = nullptr;
+    c->aos_u = c->aos_v = c->aos_dv = c->opos = c->oacc = nullptr;
+    cells_free(&c->cl_lj);
+    cells_free(&c->cl_el);
+    c->resident = false;
+}
+
+static int upload_row(nbx_ctx *c, double *dst, const double *src, int64_t n, double padval)
+{
+    NBX_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return launch_fill(c, dst + n, padval, c->npad - n);
+}
+
+static bool needs_velocity(const nbx_ctx *c)
+{
+    return c->thermo == NBX_THERMO_BERENDSEN || c->thermo == NBX_THERMO_NOSEHOOVER;
+}
+
+static int guard(nbx_ctx *c)
+{
+    if (!c) return NBX_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaSetDevice");
+    return NBX_OK;
+}
+
+static int need_system(nbx_ctx *c, const char *who)
+{
+    if (c->n <= 0) return fail(c, NBX_ERR_INVALID, "%s: call nbx_system first", who);
+    return NBX_OK;
+}
+
+// shared tail of nbx_accel / nbx_accel_device: aos_u/aos_v hold the inputs on the device
+static int accel_from_staging(nbx_ctx *c, bool have_v)
+{
+    NBX_TRY(launch_aos_to_soa(c, c->aos_u, c->pos, c->n));
+    NBX_TRY(check_finite(c, c->pos, c->n));
+    if (have_v) {
+        NBX_TRY(launch_aos_to_soa(c, c->aos_v, c->vel, c->n));
+        NBX_TRY(launch_sum_mv2(c, c->vel, 0, c->n));
+        if (c->thermo == NBX_THERMO_NOSEHOOVER) // zeta = u[zeta_ind], linear index 3n (src/thermostats.jl:122)
+            NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 1, c->aos_u + 3 * c->n, sizeof(double), cudaMemcpyDeviceToDevice,
+                                        c->stream));
+    }
+    NBX_TRY(compute_accel(c));
+    NBX_TRY(launch_soa_to_aos(c, c->acc, c->aos_dv, c->n, c->ncols, c->tgt_lo, c->tgt_hi));
+    c->resident = false;
+    return NBX_OK;
+}
+
+} // namespace nbx
+
+using namespace nbx;
+
+extern "C" {
+
+int nbx_version(void) { return 100; }
+
+const char *nbx_last_error(const nbx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nbx_create(nbx_ctx **out, int device)
+{
+    if (!out) return fail(nullptr, NBX_ERR_INVALID, "nbx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NBX_ERR_CUDA, "nbx_create: no CUDA device (%s); libnbody_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, NBX_ERR_INVALID, "nbx_create: device %d of %d", device, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, NBX_ERR_CUDA, "nbx_create: device %d is sm_%d%d; this library holds sm_100a code only", device,
+                    prop.major, prop.minor);
+    nbx_ctx *c = new (std::nothrow) nbx_ctx();
+    if (!c) return fail(nullptr, NBX_ERR_INVALID, "nbx_create: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_scal, 16 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(c->d_scal, 0, 16 * sizeof(double));
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "nbx_create");
+        delete c;
+        return rc;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return NBX_OK;
+}
+
+int nbx_destroy(nbx_ctx *c)
+{
+    if (!c) return NBX_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_system(c);
+    cudaFree(c->d_scal); cudaFree(c->d_red); cudaFree(c->part);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (auto &t : c->timers)
+        for (cudaEvent_t ev : t.ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return NBX_OK;
+}
+
+int nbx_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const double *mm, int water)
+{
+    NBX_TRY(guard(c));
+    if (n <= 0 || n > (int64_t)1 << 30) return fail(c, NBX_ERR_INVALID, "nbx_system: n = %lld out of range", (long long)n);
+    if (!m) return fail(c, NBX_ERR_INVALID, "nbx_system: masses are required");
+    if (water && n % 3 != 0) return fail(c, NBX_ERR_INVALID, "nbx_system: water needs n %% 3 == 0 (O,H1,H2 triples)");
+    cudaStreamSynchronize(c->stream);
+    free_system(c);
+    c->n = n;
+    c->ncols = n + (c->thermo == NBX_THERMO_NOSEHOOVER ? 1 : 0);
+    c->npad = ((n + kPad - 1) / kPad) * kPad;
+    c->water = water ? 1 : 0;
+    c->has_q = q != nullptr;
+    c->has_mm = mm != nullptr;
+    c->h_m1 = m[0];
+    c->tgt_lo = 0;
+    c->tgt_hi = n;
+    const size_t np = (size_t)c->npad;
+    NBX_TRY(dev_alloc(c, &c->mass, np));
+    NBX_TRY(dev_alloc(c, &c->pos, 3 * np));
+    NBX_TRY(dev_alloc(c, &c->vel, 3 * np));
+    NBX_TRY(dev_alloc(c, &c->acc, 3 * np));
+    NBX_TRY(dev_alloc(c, &c->acc_old, 3 * np));
+    NBX_TRY(dev_alloc(c, &c->aos_u, 3 * (size_t)(n + 1)));
+    NBX_TRY(dev_alloc(c, &c->aos_v, 3 * (size_t)(n + 1)));
+    NBX_TRY(dev_alloc(c, &c->aos_dv, 3 * (size_t)(n + 1)));
+    // padding: mass 1 (never divides by zero), weights 0, positions far away, velocities 0
+    NBX_TRY(upload_row(c, c->mass, m, n, 1.0));
+    NBX_TRY(launch_fill(c, c->pos, kFarAway, 3 * c->npad));
+    NBX_CUDA(c, cudaMemsetAsync(c->vel, 0, sizeof(double) * 3 * np, c->stream));
+    NBX_CUDA(c, cudaMemsetAsync(c->acc, 0, sizeof(double) * 3 * np, c->stream));
+    NBX_CUDA(c, cudaMemsetAsync(c->acc_old, 0, sizeof(double) * 3 * np, c->stream));
+    if (q) {
+        NBX_TRY(dev_alloc(c, &c->charge, np));
+        NBX_TRY(upload_row(c, c->charge, q, n, 0.0));
+    }
+    if (mm) {
+        // host moments are 3 x n AoS like the coordinates
+        NBX_TRY(dev_alloc(c, &c->mm, 3 * np));
+        NBX_CUDA(c, cudaMemsetAsync(c->mm, 0, sizeof(double) * 3 * np, c->stream));
+        NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, mm, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        NBX_TRY(launch_aos_to_soa(c, c->aos_u, c->mm, n));
+    }
+    if (water) {
+        c->opad = ((n / 3 + kPad - 1) / kPad) * kPad;
+        NBX_TRY(dev_alloc(c, &c->opos, 3 * (size_t)c->opad));
+        NBX_TRY(dev_alloc(c, &c->oacc, 3 * (size_t)c->opad));
+        NBX_CUDA(c, cudaMemsetAsync(c->oacc, 0, sizeof(double) * 3 * (size_t)c->opad, c->stream));
+    }
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+int nbx_boundary(nbx_ctx *c, int kind, const double *b)
+{
+    NBX_TRY(guard(c));
+    if (kind == NBX_BC_INFINITE) { c->bc_kind = kind; return NBX_OK; }
+    if (!b) return fail(c, NBX_ERR_INVALID, "nbx_boundary: box is NULL");
+    if (kind == NBX_BC_CUBIC) {
+        if (!(b[0] > 0.0) || !isfinite(b[0])) return fail(c, NBX_ERR_INVALID, "nbx_boundary: cubic box needs 0 < L < Inf");
+        c->bc_kind = kind;
+        c->bc[0] = b[0];
+        return NBX_OK;
+    }
+    if (kind == NBX_BC_PERIODIC) {
+        for (int d = 0; d < 3; ++d)
+            if (!(b[2 * d + 1] > b[2 * d]) || !isfinite(b[2 * d]) || !isfinite(b[2 * d + 1]))
+                return fail(c, NBX_ERR_INVALID, "nbx_boundary: periodic box needs lo < hi, finite");
+        c->bc_kind = kind;
+        for (int k = 0; k < 6; ++k) c->bc[k] = b[k];
+        return NBX_OK;
+    }
+    return fail(c, NBX_ERR_INVALID, "nbx_boundary: unknown kind %d", kind);
+}
+
+int nbx_add_gravity(nbx_ctx *c, double G)
+{
+    NBX_TRY(guard(c));
+    c->has_grav = true; c->G = G;
+    return NBX_OK;
+}
+
+int nbx_add_lj(nbx_ctx *c, double eps, double sigma, double R)
+{
+    NBX_TRY(guard(c));
+    if (!(R > 0.0)) return fail(c, NBX_ERR_INVALID, "nbx_add_lj: R must be > 0");
+    c->has_lj = true; c->lj_eps = eps;
+    c->lj_sigma2 = sigma * sigma; // LennardJonesParameters caches sigma^2 and R^2 (src/basic_potentials.jl:67-69)
+    c->lj_R = R; c->lj_R2 = R * R;
+    return NBX_OK;
+}
+
+int nbx_add_coulomb(nbx_ctx *c, double k, double R)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_add_coulomb"));
+    if (!c->has_q) return fail(c, NBX_ERR_INVALID, "nbx_add_coulomb: the system has no charges");
+    if (!(R > 0.0)) return fail(c, NBX_ERR_INVALID, "nbx_add_coulomb: R must be > 0 (Inf allowed)");
+    c->has_coul = true; c->el_k = k; c->el_R = R; c->el_R2 = R * R;
+    return NBX_OK;
+}
+
+int nbx_add_dipole(nbx_ctx *c, double mu_4pi)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_add_dipole"));
+    if (!c->has_mm) return fail(c, NBX_ERR_INVALID, "nbx_add_dipole: the system has no magnetic moments");
+    c->has_dip = true; c->mu_4pi = mu_4pi;
+    return NBX_OK;
+}
+
+int nbx_add_spcfw(nbx_ctx *c, double rOH, double aHOH, double kb, double ka)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_add_spcfw"));
+    if (!c->water) return fail(c, NBX_ERR_INVALID, "nbx_add_spcfw: the system is not water (O,H1,H2 triples)");
+    c->has_spcfw = true; c->rOH = rOH; c->aHOH = aHOH; c->k_bond = kb; c->k_angle = ka;
+    return NBX_OK;
+}
+
+int nbx_clear_potentials(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    c->has_grav = c->has_lj = c->has_coul = c->has_dip = c->has_spcfw = false;
+    return NBX_OK;
+}
+
+int nbx_thermostat(nbx_ctx *c, int kind, double T0, double param, double kB, int64_t N, int64_t Nc)
+{
+    NBX_TRY(guard(c));
+    if (kind < NBX_THERMO_NONE || kind > NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_thermostat: kind %d", kind);
+    if (kind != NBX_THERMO_NONE && (3 * N - Nc <= 0 || !(kB > 0.0)))
+        return fail(c, NBX_ERR_INVALID, "nbx_thermostat: needs 3N - Nc > 0 and kB > 0");
+    c->thermo = kind; c->T0 = T0; c->tparam = param; c->kB = kB; c->thN = N; c->thNc = Nc;
+    if (c->n > 0) c->ncols = c->n + (kind == NBX_THERMO_NOSEHOOVER ? 1 : 0);
+    return NBX_OK;
+}
+
+int nbx_shard(nbx_ctx *c, int64_t lo, int64_t hi)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_shard"));
+    if (lo < 0 || hi > c->n || lo > hi) return fail(c, NBX_ERR_INVALID, "nbx_shard: [%lld,%lld) outside [0,%lld)", (long long)lo, (long long)hi, (long long)c->n);
+    if (c->water && (lo % 3 || hi % 3)) return fail(c, NBX_ERR_INVALID, "nbx_shard: water shards must hold whole molecules");
+    c->tgt_lo = lo; c->tgt_hi = hi;
+    return NBX_OK;
+}
+
+int nbx_set_stream(nbx_ctx *c, void *stream)
+{
+    NBX_TRY(guard(c));
+    cudaStreamSynchronize(c->stream);
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return NBX_OK;
+}
+
+int nbx_synchronize(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+static int finish_and_check(nbx_ctx *c)
+{
+    int flag[2] = {0, 0};
+    NBX_CUDA(c, cudaMemcpyAsync(flag, c->d_scal + 15, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flag[0]) return fail(c, NBX_ERR_NONFINITE, "non-finite coordinate in u (the reference's wrap loop would not terminate)");
+    return NBX_OK;
+}
+
+int nbx_accel(nbx_ctx *c, const double *u, double *v, double t, double *dv)
+{
+    (void)t;
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_accel"));
+    if (!u || !dv) return fail(c, NBX_ERR_INVALID, "nbx_accel: u and dv are required");
+    const bool have_v = needs_velocity(c);
+    if (have_v && !v) return fail(c, NBX_ERR_INVALID, "nbx_accel: this thermostat needs v");
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (have_v) NBX_CUDA(c, cudaMemcpyAsync(c->aos_v, v, bytes, cudaMemcpyHostToDevice, c->stream));
+    NBX_TRY(accel_from_staging(c, have_v));
+    NBX_CUDA(c, cudaMemcpyAsync(dv, c->aos_dv, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (c->thermo == NBX_THERMO_NOSEHOOVER) // v[zeta_ind] = ...  (src/thermostats.jl:126)
+        NBX_CUDA(c, cudaMemcpyAsync(v + 3 * c->n, c->d_scal + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return finish_and_check(c);
+}
+
+int nbx_accel_device(nbx_ctx *c, const double *u_dev, double *v_dev, double t, double *dv_dev)
+{
+    (void)t;
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_accel_device"));
+    if (!u_dev || !dv_dev) return fail(c, NBX_ERR_INVALID, "nbx_accel_device: u and dv are required");
+    const bool have_v = needs_velocity(c);
+    if (have_v && !v_dev) return fail(c, NBX_ERR_INVALID, "nbx_accel_device: this thermostat needs v");
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u_dev, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (have_v) NBX_CUDA(c, cudaMemcpyAsync(c->aos_v, v_dev, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    NBX_TRY(accel_from_staging(c, have_v));
+    NBX_CUDA(c, cudaMemcpyAsync(dv_dev, c->aos_dv, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->thermo == NBX_THERMO_NOSEHOOVER)
+        NBX_CUDA(c, cudaMemcpyAsync(v_dev + 3 * c->n, c->d_scal + 2, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return NBX_OK; // asynchronous on ctx's stream; nbx_synchronize() to wait
+}
+
+int nbx_upload(nbx_ctx *c, const double *u, const double *v)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_upload"));
+    if (!u || !v) return fail(c, NBX_ERR_INVALID, "nbx_upload: u and v are required");
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u, bytes, cudaMemcpyHostToDevice, c->stream));
+    NBX_CUDA(c, cudaMemcpyAsync(c->aos_v, v, bytes, cudaMemcpyHostToDevice, c->stream));
+    NBX_TRY(launch_aos_to_soa(c, c->aos_u, c->pos, c->n));
+    NBX_TRY(launch_aos_to_soa(c, c->aos_v, c->vel, c->n));
+    NBX_TRY(check_finite(c, c->pos, c->n));
+    NBX_TRY(launch_sum_mv2(c, c->vel, 0, c->n)); // every rank holds all velocities at upload time
+    if (c->thermo == NBX_THERMO_NOSEHOOVER) {
+        NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 1, c->aos_u + 3 * c->n, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 2, c->aos_v + 3 * c->n, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->rng_step = 0;
+    NBX_TRY(compute_accel(c)); // a(0)
+    c->resident = true;
+    return finish_and_check(c);
+}
+
+static int need_resident(nbx_ctx *c, const char *who)
+{
+    NBX_TRY(need_system(c, who));
+    if (!c->resident) return fail(c, NBX_ERR_INVALID, "%s: no resident state (call nbx_upload)", who);
+    return NBX_OK;
+}
+
+int nbx_eval_resident(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_eval_resident"));
+    return compute_accel(c);
+}
+
+int nbx_vv_begin(nbx_ctx *c, double dt)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_vv_begin"));
+    return launch_vv_pos(c, dt);
+}
+
+int nbx_vv_finish(nbx_ctx *c, double dt)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_vv_finish"));
+    double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
+    NBX_TRY(compute_accel(c));  // a(t+dt) from x(t+dt) and, for the RHS thermostats, v(t)
+    NBX_TRY(launch_vv_vel(c, dt));
+    if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
+    return NBX_OK;
+}
+
+int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_step_vv"));
+    if (c->tgt_lo != 0 || c->tgt_hi != c->n)
+        return fail(c, NBX_ERR_INVALID, "nbx_step_vv: sharded context; drive nbx_vv_begin / all-gather / nbx_vv_finish");
+    if (c->thermo == NBX_THERMO_LANGEVIN)
+        return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
+    for (int64_t s = 0; s < nsteps; ++s) {
+        NBX_TRY(launch_vv_pos(c, dt));
+        double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
+        NBX_TRY(compute_accel(c));
+        NBX_TRY(launch_vv_vel(c, dt));
+        if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
+    }
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+int nbx_set_seed(nbx_ctx *c, uint64_t seed)
+{
+    NBX_TRY(guard(c));
+    c->seed = seed; c->rng_step = 0;
+    return NBX_OK;
+}
+
+int nbx_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_step_em"));
+    if (c->thermo != NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_step_em: needs the Langevin thermostat");
+    if (c->water) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_em: the water SDE variant (src/nbody_to_ode.jl:600-680) is not built");
+    if (seed) c->seed = seed;
+    for (int64_t s = 0; s < nsteps; ++s) {
+        if (s > 0) NBX_TRY(compute_accel(c)); // a(x_s); the first one is resident already
+        NBX_TRY(launch_em_step(c, dt));
+    }
+    NBX_TRY(compute_accel(c)); // leave a(x_end) resident
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+int nbx_download(nbx_ctx *c, double *u, double *v, double *dv)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_download"));
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    const bool nose = c->thermo == NBX_THERMO_NOSEHOOVER;
+    if (u) {
+        NBX_TRY(launch_soa_to_aos(c, c->pos, c->aos_u, c->n, c->ncols, 0, c->n));
+        if (nose) NBX_CUDA(c, cudaMemcpyAsync(c->aos_u + 3 * c->n, c->d_scal + 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        NBX_CUDA(c, cudaMemcpyAsync(u, c->aos_u, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (v) {
+        NBX_TRY(launch_soa_to_aos(c, c->vel, c->aos_v, c->n, c->ncols, 0, c->n));
+        if (nose) NBX_CUDA(c, cudaMemcpyAsync(c->aos_v + 3 * c->n, c->d_scal + 2, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        NBX_CUDA(c, cudaMemcpyAsync(v, c->aos_v, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (dv) {
+        NBX_TRY(launch_soa_to_aos(c, c->acc, c->aos_dv, c->n, c->ncols, c->tgt_lo, c->tgt_hi));
+        NBX_CUDA(c, cudaMemcpyAsync(dv, c->aos_dv, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+int nbx_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_energy"));
+    if (ekin || temperature) NBX_TRY(reduce_kinetic(c, ekin, temperature));
+    if (epot) NBX_TRY(reduce_potential(c, epot));
+    return NBX_OK;
+}
+
+int nbx_neighbors(nbx_ctx *c, int64_t *offsets, int32_t *list, int64_t cap)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_neighbors"));
+    if (!c->has_lj) return fail(c, NBX_ERR_INVALID, "nbx_neighbors: no Lennard-Jones potential (the cutoff predicate) configured");
+    if (!offsets || (!list && cap > 0)) return fail(c, NBX_ERR_INVALID, "nbx_neighbors: NULL output");
+    if (c->water) {
+        const int nmol = (int)(c->n / 3);
+        gather_oxygen_kernel<<<(unsigned)((c->opad + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, nmol, c->opos, c->opad, kFarAway);
+        NBX_TRY(cells_plan(c, c->lj_R, nmol, &c->cl_lj.grid));
+        return cells_neighbors(c, &c->cl_lj, c->opos, nmol, c->opad, c->lj_R2, offsets, list, cap);
+    }
+    NBX_TRY(cells_plan(c, c->lj_R, c->n, &c->cl_lj.grid));
+    return cells_neighbors(c, &c->cl_lj, c->pos, c->n, c->npad, c->lj_R2, offsets, list, cap);
+}
+
+int nbx_device_ptr(nbx_ctx *c, int which, void **ptr, int64_t *ld)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_device_ptr"));
+    if (!ptr) return fail(c, NBX_ERR_INVALID, "nbx_device_ptr: ptr is NULL");
+    switch (which) {
+    case 0: *ptr = c->pos; break;
+    case 1: *ptr = c->vel; break;
+    case 2: *ptr = c->acc; break;
+    case 3: *ptr = c->d_scal; break; // [0] = sum m v^2 of the shard after a step (all-reduce it across ranks)
+    default: return fail(c, NBX_ERR_INVALID, "nbx_device_ptr: which = %d", which);
+    }
+    if (ld) *ld = which == 3 ? 16 : c->npad;
+    return NBX_OK;
+}
+
+int nbx_timing_enable(nbx_ctx *c, int enable)
+{
+    NBX_TRY(guard(c));
+    c->timing = enable != 0;
+    return NBX_OK;
+}
+
+int nbx_timing_get(nbx_ctx *c, int phase, double *total_ms, int64_t *count)
+{
+    NBX_TRY(guard(c));
+    if (phase < 0 || phase >= NBX_T_COUNT) return fail(c, NBX_ERR_INVALID, "nbx_timing_get: phase %d", phase);
+    timer_flush(c, c->timers[phase]);
+    if (total_ms) *total_ms = c->timers[phase].total_ms;
+    if (count) *count = c->timers[phase].count;
+    return NBX_OK;
+}
+
+int nbx_timing_reset(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    for (auto &t : c->timers) { timer_flush(c, t); t.total_ms = 0.0; t.count = 0; }
+    return NBX_OK;
+}
+
+int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
+{
+    NBX_TRY(guard(c));
+    if (!key) return fail(c, NBX_ERR_INVALID, "nbx_set_option: key is NULL");
+    if (!strcmp(key, "cell_list")) c->opt_cell_list = (int)value;
+    else if (!strcmp(key, "prefilter")) c->opt_prefilter = (int)value;
+    else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else return fail(c, NBX_ERR_INVALID, "nbx_set_option: unknown key '%s'", key);
+    return NBX_OK;
+}
+
+int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
+{
+    NBX_TRY(guard(c));
+    if (!key || !value) return fail(c, NBX_ERR_INVALID, "nbx_get_info: NULL argument");
+    if (!strcmp(key, "n")) *value = c->n;
+    else if (!strcmp(key, "npad")) *value = c->npad;
+    else if (!strcmp(key, "ncols")) *value = c->ncols;
+    else if (!strcmp(key, "water")) *value = c->water;
+    else if (!strcmp(key, "sm_count")) *value = c->sm_count;
+    else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;
+    else if (!strcmp(key, "cells_el")) *value = c->cl_el.grid.valid ? c->cl_el.grid.ncell : 0;
+    else if (!strcmp(key, "allpairs_grid")) *value = c->last_grid;
+    else if (!strcmp(key, "allpairs_chunks")) *value = c->last_nchunk;
+    else return fail(c, NBX_ERR_INVALID, "nbx_get_info: unknown key '%s'", key);
+    return NBX_OK;
+}
+
+int nbx_measure_fp64_peak(nbx_ctx *c, double *tflops, double *sm_mhz_effective)
+{
+    NBX_TRY(guard(c));
+    return measure_fp64_peak(c, tflops, sm_mhz_effective);
+}
+
+int nbx_measure_hbm_peak(nbx_ctx *c, double *gbs)
+{
+    NBX_TRY(guard(c));
+    return measure_hbm_peak(c, gbs);
+}
+
+} // extern "C"

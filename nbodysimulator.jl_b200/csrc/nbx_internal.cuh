@@ -1,0 +1,271 @@
+// nbx_internal.cuh -- context, error plumbing and sm_100a PTX helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nbody_b200.h"
+
+namespace nbx {
+
+constexpr int kPad = 1024;           // SoA rows are padded to a multiple of this many doubles
+constexpr double kFarAway = 1.0e100; // position of padding sources (weight 0) in the infinite box
+constexpr int kMaxTimers = 8192;     // event pairs kept per phase between resets
+
+struct Timer {
+    std::vector<cudaEvent_t> ev; // start/stop interleaved
+    size_t used = 0;             // events used (2 per launch)
+    double total_ms = 0.0;
+    int64_t count = 0;
+};
+
+struct CellGrid {
+    bool valid = false;      // cell list usable for the current box / cutoff
+    int nc[3] = {0, 0, 0};   // cells per dimension
+    int64_t ncell = 0;
+    double lo[3] = {0, 0, 0};
+    double len[3] = {0, 0, 0}; // box edge per dimension
+};
+
+// One cell list (grid + the particle data in cell order).  A context keeps two: the LJ list (all
+// atoms, or the oxygen sub-system of water) and the Coulomb-cutoff list (all atoms).
+struct CellList {
+    CellGrid grid;
+    int64_t n = 0;              // particles binned by the last build
+    int *cell_of = nullptr;     // [n] cell id per particle
+    int *count = nullptr;       // [ncell+1] histogram
+    int *start = nullptr;       // [ncell+1] exclusive scan of count
+    int *fill = nullptr;        // [ncell+1] scatter cursors
+    int *sums = nullptr;        // scan block totals
+    int *sorted_idx = nullptr;  // [n] particle index of the k-th slot in cell order
+    int *scell = nullptr;       // [n] cell id of the k-th slot
+    double *spos = nullptr;     // [3][sld] positions in cell order (unwrapped, as the reference uses them)
+    double *sw = nullptr;       // [sld] weights (charges) in cell order
+    int64_t sld = 0;
+    int64_t cap_n = 0, cap_cells = 0;
+};
+
+} // namespace nbx
+
+struct nbx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+
+    // ---- system -------------------------------------------------------------------------
+    int64_t n = 0;      // particle columns
+    double h_m1 = 0.0;  // mass of the first body (the reference's Andersen/Langevin sigma uses bodies[1].m)
+    int64_t ncols = 0;  // columns of u/v/dv at the boundary (n or n+1)
+    int64_t npad = 0;   // SoA row stride
+    int water = 0;
+    bool has_q = false, has_mm = false;
+    double *mass = nullptr, *charge = nullptr, *mm = nullptr; // [npad], [npad], [3][npad]
+    double *pos = nullptr, *vel = nullptr, *acc = nullptr, *acc_old = nullptr; // [3][npad]
+    double *aos_u = nullptr, *aos_v = nullptr, *aos_dv = nullptr;              // [3*(n+1)] staging
+    bool resident = false; // pos/vel/acc hold a simulation state
+
+    // ---- boundary -----------------------------------------------------------------------
+    int bc_kind = NBX_BC_INFINITE;
+    double bc[6] = {0, 0, 0, 0, 0, 0};
+
+    // ---- potentials ---------------------------------------------------------------------
+    bool has_grav = false; double G = 0;
+    bool has_lj = false; double lj_eps = 0, lj_sigma2 = 0, lj_R = 0, lj_R2 = 0;
+    bool has_coul = false; double el_k = 0, el_R = 0, el_R2 = 0;
+    bool has_dip = false; double mu_4pi = 0;
+    bool has_spcfw = false; double rOH = 0, aHOH = 0, k_bond = 0, k_angle = 0;
+
+    // ---- thermostat ---------------------------------------------------------------------
+    int thermo = NBX_THERMO_NONE;
+    double T0 = 0, tparam = 0, kB = 0;
+    int64_t thN = 0, thNc = 0;
+    double *d_scal = nullptr;  // device scalars: [0] sum m v^2, [1] zeta, [2] zeta_dot, [3..15] scratch
+    double *d_red = nullptr;   // block partials for reductions
+    int64_t red_cap = 0;
+    uint64_t seed = 0x9E3779B97F4A7C15ull;
+    uint64_t rng_step = 0;
+
+    // ---- sharding -----------------------------------------------------------------------
+    int64_t tgt_lo = 0, tgt_hi = 0;
+
+    // ---- all-pairs scratch ----------------------------------------------------------------
+    double *part = nullptr; // [nchunk][3][ntgt_pad] partial sums
+    size_t part_bytes = 0;
+    std::vector<const void *> attr_done; // kernels whose dynamic-smem attribute is set
+    int last_grid = 0, last_nchunk = 0;
+
+    // ---- water oxygen sub-system (compact SoA of the O columns) ----------------------------
+    double *opos = nullptr, *oacc = nullptr; // [3][opad]
+    int64_t opad = 0;
+
+    // ---- cell lists ----------------------------------------------------------------------
+    nbx::CellList cl_lj, cl_el;
+    int opt_cell_list = 1;
+    int opt_prefilter = 1;
+    int opt_graph = 1;
+
+    // ---- neighbour scratch ------------------------------------------------------------------
+    // ---- host staging -----------------------------------------------------------------------
+    double *h_pin = nullptr; size_t h_pin_bytes = 0;
+
+    // ---- timing -----------------------------------------------------------------------------
+    bool timing = false;
+    nbx::Timer timers[NBX_T_COUNT];
+};
+
+namespace nbx {
+
+int fail(nbx_ctx *c, int code, const char *fmt, ...);
+int cuda_fail(nbx_ctx *c, cudaError_t e, const char *what);
+
+#define NBX_CUDA(ctx, expr)                                           \
+    do {                                                              \
+        cudaError_t e__ = (expr);                                     \
+        if (e__ != cudaSuccess) return nbx::cuda_fail(ctx, e__, #expr); \
+    } while (0)
+
+#define NBX_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != NBX_OK) return rc__; \
+    } while (0)
+
+// RAII-ish phase timer (records only when ctx->timing).
+void timer_begin(nbx_ctx *c, int phase);
+void timer_end(nbx_ctx *c, int phase);
+
+template <typename T>
+int dev_alloc(nbx_ctx *c, T **p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return NBX_OK;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc");
+    return NBX_OK;
+}
+
+// ---- kernels implemented across the .cu files (host launchers) ----------------------------
+// nbx_allpairs.cu
+int launch_allpairs_grav(nbx_ctx *c, const double *w, int scale_kind, double scale, double *acc_out, bool accumulate);
+int launch_allpairs_dipole(nbx_ctx *c, double *acc_out, bool accumulate);
+int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_t ld, int64_t lo, int64_t hi,
+                        int mstride, double *acc_out, int64_t ld_out, bool accumulate);
+// nbx_cells.cu
+int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g);
+int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld);
+int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi, int mstride, double *acc_out,
+                       int64_t ld_out, bool accumulate);
+int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
+                    int32_t *list, int64_t cap);
+void cells_free(CellList *cl);
+// nbx_bonded.cu
+int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);
+// nbx_integrate.cu
+int launch_aos_to_soa(nbx_ctx *c, const double *aos, double *soa, int64_t ncols_used);
+int launch_soa_to_aos(nbx_ctx *c, const double *soa, double *aos, int64_t n, int64_t ncols_total, int64_t lo, int64_t hi);
+int launch_fill(nbx_ctx *c, double *p, double v, int64_t count);
+int launch_sum_mv2(nbx_ctx *c, const double *vel, int64_t lo, int64_t hi); // -> d_scal[0]
+int launch_thermostat_rhs(nbx_ctx *c, double *acc, const double *vel);
+int launch_vv_pos(nbx_ctx *c, double dt);
+int launch_vv_vel(nbx_ctx *c, double dt);
+int launch_em_step(nbx_ctx *c, double dt);
+int launch_andersen(nbx_ctx *c, double dt);
+int check_finite(nbx_ctx *c, const double *soa, int64_t n);
+int reduce_kinetic(nbx_ctx *c, double *ekin, double *temp);
+int reduce_potential(nbx_ctx *c, double *epot);
+int measure_fp64_peak(nbx_ctx *c, double *tflops, double *mhz);
+int measure_hbm_peak(nbx_ctx *c, double *gbs);
+// nbx_api.cu
+int compute_accel(nbx_ctx *c); // pos, vel -> acc (all potentials + RHS thermostats)
+
+// ---- device helpers --------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// MUFU.RSQ64H seed: ~2^-22 relative accuracy, no special-case handling.
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+// w * x^(-3/2) to ~3 ulp from the seed: with a = y0^2 (exact: y0 has 21 significant bits),
+// e = 1 - x a,  x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + e (3/2 + 15/8 e) + O(e^3)), e^3 < 1e-19.
+__device__ __forceinline__ double w_rinv3(double r2, double w)
+{
+    const double y0 = rsqrt_seed(r2);
+    const double a = y0 * y0;
+    const double e = fma(-r2, a, 1.0);
+    const double c = a * (y0 * w);
+    const double p = fma(1.875, e, 1.5);
+    const double q = p * e;
+    return fma(c, q, c);
+}
+// get_interparticle_distance wrap loops (src/boundary_conditions.jl:111-165), bit-exact:
+// repeated rounded subtraction/addition of the box edge, bounded to 64 trips per side so a
+// wild coordinate cannot hang the GPU (the reference would spin; NaN/Inf is rejected earlier).
+__device__ __forceinline__ double wrap_cubic(double x, double radius, double size)
+{
+    for (int k = 0; k < 64 && x >= radius; ++k) x = __dsub_rn(x, size);
+    for (int k = 0; k < 64 && x < -radius; ++k) x = __dadd_rn(x, size);
+    return x;
+}
+__device__ __forceinline__ double wrap_range(double x, double lo, double hi)
+{
+    const double len = __dsub_rn(hi, lo);
+    for (int k = 0; k < 64 && x < lo; ++k) x = __dadd_rn(x, len);
+    for (int k = 0; k < 64 && x >= hi; ++k) x = __dsub_rn(x, len);
+    return x;
+}
+// r2 = x^2 + y^2 + z^2, left to right, no FMA contraction (:162).
+__device__ __forceinline__ double r2_unfused(double x, double y, double z)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+#endif
+
+} // namespace nbx

@@ -1,0 +1,133 @@
+"""Multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
+
+The reference is strictly serial; the data-parallel axis is the target-particle
+index ``i`` of ``soode_system!`` (src/nbody_to_ode.jl:475).  Rank r evaluates the target columns
+[lo_r, hi_r) against ALL sources, so one velocity-Verlet step needs exactly one exchange: the
+all-gather of the freshly updated positions (24 B per particle), plus an 8-byte all-reduce of
+sum m v^2 when a thermostat needs the global temperature.
+
+The plumbing works on an *engine* (duck-typed):
+    engine.n                       particle columns
+    engine.shard(lo, hi)           restrict the engine to its targets
+    engine.pos_rows()  -> tensor   (3, ld) view of the SoA position rows (device memory, no copy)
+    engine.scalars()   -> tensor   (16,) view of the scalar block ([0] = shard's sum m v^2)
+    engine.vv_begin(dt) / engine.vv_finish(dt) / engine.needs_temperature
+``CudaEngine`` wraps a libnbody_b200 context; the CPU tests drive the same plumbing over gloo with a
+NumPy engine (tests/test_parallel_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition(n: int, world: int, rank: int, multiple: int = 1):
+    """Contiguous target range of ``rank``: equal blocks of ceil(n/world) rounded up to ``multiple``
+    (3 for water: molecules stay whole)."""
+    per = -(-n // world)
+    per = -(-per // multiple) * multiple
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi, per
+
+
+class CudaEngine:
+    """libnbody_b200 context + zero-copy torch views of its device state."""
+
+    def __init__(self, ctx, device_index: int):
+        import torch
+
+        self.ctx = ctx
+        self.n = ctx.n
+        self.device = torch.device("cuda", device_index)
+        self.needs_temperature = False
+        # run the library on torch's current stream so NCCL calls issued by torch are ordered with it
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _view(self, which, shape):
+        import torch
+
+        ptr, ld = self.ctx.device_ptr(which)
+        shape = tuple(ld if s is None else s for s in shape)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                        "strides": None}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def shard(self, lo, hi):
+        self.ctx.shard(lo, hi)
+
+    def pos_rows(self):
+        return self._view(0, (3, None))
+
+    def scalars(self):
+        return self._view(3, (16,))
+
+    def vv_begin(self, dt):
+        self.ctx.vv_begin(dt)
+
+    def vv_finish(self, dt):
+        self.ctx.vv_finish(dt)
+
+
+class ShardedStepper:
+    """Velocity Verlet over a process group: x-update of the own shard, all-gather, forces + v-update."""
+
+    def __init__(self, engine, group=None, multiple: int = 1):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.lo, self.hi, self.per = partition(engine.n, self.world, self.rank, multiple)
+        engine.shard(self.lo, self.hi)
+        self.even = self.per * self.world == engine.n
+        self._tmp = None
+
+    def _all_gather_positions(self):
+        import torch
+
+        rows = self.engine.pos_rows()
+        n, per, dist = self.engine.n, self.per, self.dist
+        if self.world == 1:
+            return
+        if self.even:
+            # in place: each rank's block already sits at its final offset of the row
+            for d in range(3):
+                dist.all_gather_into_tensor(rows[d, :n], rows[d, self.lo:self.hi], group=self.group)
+            return
+        if self._tmp is None:
+            self._tmp = (torch.zeros(3 * per, dtype=rows.dtype, device=rows.device),
+                         torch.zeros(self.world * 3 * per, dtype=rows.dtype, device=rows.device))
+        send, recv = self._tmp
+        cnt = self.hi - self.lo
+        for d in range(3):
+            send[d * per:d * per + cnt] = rows[d, self.lo:self.hi]
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        recv = recv.view(self.world, 3, per)
+        for r in range(self.world):
+            lo, hi, _ = partition(n, self.world, r, 1)
+            lo, hi = min(n, r * per), min(n, r * per + per)
+            if hi > lo and r != self.rank:
+                rows[:, lo:hi] = recv[r, :, :hi - lo]
+
+    def step(self, dt: float, nsteps: int = 1):
+        for _ in range(nsteps):
+            self.engine.vv_begin(dt)
+            self._all_gather_positions()
+            self.engine.vv_finish(dt)
+            if self.engine.needs_temperature and self.world > 1:
+                s = self.engine.scalars()
+                self.dist.all_reduce(s[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+def numpy_reference_partition_check(n, world, multiple=1):
+    """All ranks' ranges tile [0, n) exactly (host-logic self check used by the CPU tests)."""
+    covered = np.zeros(n, dtype=np.int32)
+    for r in range(world):
+        lo, hi, _ = partition(n, world, r, multiple)
+        covered[lo:hi] += 1
+    return bool((covered == 1).all())

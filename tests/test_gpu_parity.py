@@ -1,0 +1,387 @@
+"""Parity of the CUDA hot path (through the C ABI, ctypes) with the CPU oracle on identical inputs.
+
+Tolerance (BASELINE.json north_star): per-body accelerations <= 1e-12 relative in fp64
+(||a_gpu - a_ref||_2 / ||a_ref||_2 per body); neighbour lists bit-exact.
+Run on the B200 box: python -m pytest tests -m gpu
+"""
+import numpy as np
+import pytest
+
+import nbody_b200.workloads as wl
+from tests._common import F, make_context, make_oracle, rel_err_per_body
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+NT = 8  # oracle threads (targets are independent; per-target arithmetic is the serial reference's)
+
+
+def _check(a, ref, tol=TOL, floor_frac=1e-9):
+    assert a.shape == ref.shape
+    assert np.isfinite(a).all()
+    norms = np.linalg.norm(ref, axis=0)
+    floor = floor_frac * np.sqrt(np.mean(norms ** 2)) if norms.size else 0.0
+    err = np.linalg.norm(a - ref, axis=0) / np.maximum(norms, floor if floor > 0 else 1.0)
+    worst = int(np.argmax(err))
+    assert err[worst] <= tol, f"body {worst}: rel err {err[worst]:.3e} > {tol:.1e} (median {np.median(err):.2e})"
+    return err
+
+
+def _rand(n, seed, scale=1.0):
+    rng = np.random.Generator(np.random.Philox(seed))
+    u = F(rng.random((3, n)) * scale)
+    v = F(rng.standard_normal((3, n)))
+    return rng, u, v
+
+
+# ------------------------------------------------------------------------------------------
+# gravity (src/basic_potentials.jl:306-331)
+# ------------------------------------------------------------------------------------------
+def test_gravity_figure_eight(oracle):
+    # test/gravitational_test.jl:7-18
+    u = F([[-0.995492, 0.995492, 0.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    v = F([[-0.347902, -0.347902, 0.695804], [-0.53393, -0.53393, 1.067860], [0.0, 0.0, 0.0]])
+    spec = dict(ms=np.ones(3), gravity=dict(G=1.0))
+    ref = make_oracle(oracle, spec).rhs(u, v.copy(order="F"))
+    ctx = make_context(spec)
+    _check(ctx.accel(u), ref)
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1000, 1025, 5000])
+def test_gravity_random_sizes(oracle, n):
+    rng, u, v = _rand(n, 100 + n)
+    ms = rng.random(n) + 0.1
+    spec = dict(ms=ms, gravity=dict(G=6.67408e-11))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    if n == 1:
+        assert np.array_equal(a, np.zeros((3, 1)))
+    else:
+        _check(a, ref)
+
+
+def test_gravity_plummer_16k_full(oracle):
+    u, v, ms = wl.plummer(16384)
+    spec = dict(ms=ms, gravity=dict(G=1.0))
+    s = make_oracle(oracle, spec)
+    ref = s.rhs(u, v, NT)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    err = rel_err_per_body(a, ref)
+    # bodies whose net acceleration nearly cancels are judged against extended precision
+    bad = np.nonzero(err > TOL)[0]
+    if bad.size:
+        exact = oracle.gravity_targets_ld(u, ms, 1.0, bad, NT)
+        e_gpu = rel_err_per_body(a[:, bad], exact)
+        e_ref = rel_err_per_body(ref[:, bad], exact)
+        assert (e_gpu <= np.maximum(TOL, 2.0 * e_ref)).all(), (e_gpu.max(), e_ref.max())
+    assert np.median(err) < 1e-14
+    # bit-reproducible from call to call
+    assert np.array_equal(a, ctx.accel(u))
+
+
+def test_gravity_plummer_262k_subsample(oracle):
+    """BASELINE config 2 at full size: 1,024 targets against all 262,144 sources."""
+    n = 262144
+    u, v, ms = wl.plummer(n)
+    spec = dict(ms=ms, gravity=dict(G=1.0))
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert np.isfinite(a).all()
+    targets = np.random.Generator(np.random.Philox(7)).choice(n, 1024, replace=False)
+    ref = make_oracle(oracle, spec).accel_targets(u, targets, NT)
+    exact = oracle.gravity_targets_ld(u, ms, 1.0, targets, NT)
+    e_gpu = rel_err_per_body(a[:, targets], exact)
+    e_ref = rel_err_per_body(ref, exact)
+    e_pair = rel_err_per_body(a[:, targets], ref)
+    ok = (e_pair <= TOL) | (e_gpu <= np.maximum(TOL, 2.0 * e_ref))
+    assert ok.all(), (e_pair.max(), e_gpu.max(), e_ref.max())
+    # size-independent property: total momentum change vanishes (Newton's third law)
+    p = (a * ms).sum(axis=1)
+    scale = np.abs(a * ms).sum(axis=1)
+    assert (np.abs(p) <= 1e-11 * scale).all()
+
+
+def test_gravity_shard_matches_full(oracle):
+    n = 3000
+    rng, u, v = _rand(n, 5)
+    spec = dict(ms=rng.random(n) + 0.5, gravity=dict(G=1.0))
+    ctx = make_context(spec)
+    full = ctx.accel(u).copy()
+    ctx.shard(1000, 2300)
+    part = ctx.accel(u)
+    assert np.array_equal(part[:, 1000:2300], full[:, 1000:2300])  # bit-identical: order of summation is fixed
+    assert not part[:, :1000].any() and not part[:, 2300:].any()
+
+
+# ------------------------------------------------------------------------------------------
+# Coulomb / dipole, InfiniteBox (src/basic_potentials.jl:274-304, :333-365)
+# ------------------------------------------------------------------------------------------
+def test_coulomb_allpairs(oracle):
+    n = 3001
+    rng, u, v = _rand(n, 21)
+    spec = dict(ms=rng.random(n) + 0.5, qs=rng.standard_normal(n), coulomb=dict(k=9e9))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    _check(make_context(spec).accel(u), ref)
+
+
+def test_coulomb_config5a_subsample(oracle):
+    w = wl.charged_lattice(65536)
+    spec = dict(ms=w["ms"], qs=w["qs"], coulomb=w["coulomb"])
+    a = make_context(spec).accel(w["u"])
+    targets = np.arange(0, 65536, 97)
+    ref = make_oracle(oracle, spec).accel_targets(w["u"], targets, NT)
+    _check(a[:, targets], ref, tol=1e-11)  # alternating charges on a lattice: heavy cancellation
+
+
+def test_dipole_allpairs(oracle):
+    n = 2500
+    rng, u, v = _rand(n, 33)
+    spec = dict(ms=rng.random(n) + 0.5, mm=F(rng.standard_normal((3, n))), dipole=dict(mu_4pi=1e-7))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    _check(make_context(spec).accel(u), ref)
+
+
+def test_dipole_config5b_subsample(oracle):
+    w = wl.dipole_lattice(65536)
+    spec = dict(ms=w["ms"], mm=w["mm"], dipole=w["dipole"])
+    a = make_context(spec).accel(w["u"])
+    targets = np.arange(0, 65536, 131)
+    ref = make_oracle(oracle, spec).accel_targets(w["u"], targets, NT)
+    _check(a[:, targets], ref, tol=1e-11)
+
+
+def test_all_potentials_together(oracle):
+    n = 700
+    rng, u, v = _rand(n, 44, 1.3)
+    spec = dict(ms=rng.random(n) + 0.5, qs=rng.standard_normal(n), mm=F(rng.standard_normal((3, n))),
+                bc=("cubic", 1.3), lj=dict(eps=0.7, sigma=0.05, R=0.3), coulomb=dict(k=2.5, R=0.4),
+                dipole=dict(mu_4pi=1e-3), gravity=dict(G=0.3))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    _check(make_context(spec).accel(u), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# Lennard-Jones with cutoff (src/basic_potentials.jl:240-272) under each boundary kind
+# ------------------------------------------------------------------------------------------
+def test_lj_config1_shipped_example(oracle):
+    """examples/liquid_argon.jl as shipped: 216 atoms, R = 0.5 L (no cell list possible)."""
+    w = wl.liquid_argon_si()
+    rng = np.random.Generator(np.random.Philox(1))
+    u = F(w["u"] + 0.05 * w["lj"]["sigma"] * rng.standard_normal(w["u"].shape))
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    ctx = make_context(spec)
+    _check(ctx.accel(u), ref)
+    assert ctx.info("cells_lj") == 0
+
+
+@pytest.mark.parametrize("bc", [("infinite",), ("periodic", (0.0, 1.3, 0.0, 1.3, 0.0, 1.3)),
+                                ("periodic", (-0.2, 0.9, 0.1, 1.5, -1.0, 0.4)), ("cubic", 1.3)])
+def test_lj_boundary_kinds(oracle, bc):
+    n = 600
+    rng, u, v = _rand(n, 55, 1.3)
+    u = F(u * 1.7 - 0.4)  # deliberately outside the box too
+    spec = dict(ms=rng.random(n) + 0.5, bc=bc, lj=dict(eps=0.7, sigma=0.06, R=0.31 if bc[0] != "infinite" else 50.0))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    _check(make_context(spec).accel(u), ref)
+
+
+def _fcc(cells, jitter, seed, drift=False):
+    w = wl.fcc_argon_reduced(cells)
+    rng = np.random.Generator(np.random.Philox(seed))
+    u = w["u"] + jitter * rng.standard_normal(w["u"].shape)
+    if drift:  # the reference never wraps positions: atoms drift out of the box by whole box lengths
+        u = u + w["L"] * rng.integers(-3, 4, size=u.shape)
+    return w, F(u)
+
+
+@pytest.mark.parametrize("drift", [False, True])
+def test_lj_cell_list_forces(oracle, drift):
+    w, u = _fcc(12, 0.05, 3, drift)  # 6,912 atoms, 9 cells per dimension
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert ctx.info("cells_lj") == 9 ** 3
+    _check(a, ref)
+    # the cell list changes the candidate set only: switching it off gives the same pair set
+    ctx.set_option("cell_list", 0)
+    b = ctx.accel(u)
+    assert ctx.info("cells_lj") == 0
+    _check(b, ref)
+
+
+@pytest.mark.parametrize("drift", [False, True])
+def test_lj_neighbor_lists_bit_exact(oracle, drift):
+    w, u = _fcc(10, 0.08, 9, drift)  # 4,000 atoms
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    s = make_oracle(oracle, spec)
+    ctx = make_context(spec)
+    ctx.upload(u, w["v"])
+    off, lst = ctx.neighbors()
+    assert ctx.info("cells_lj") > 0
+    n = u.shape[1]
+    for i in range(0, n, 7):
+        assert np.array_equal(lst[off[i]:off[i + 1]], s.neighbors(u, i, w["lj"]["R"]))
+    # every list, not just the sampled ones: symmetric and the right total count
+    total = sum(len(s.neighbors(u, i, w["lj"]["R"])) for i in range(0, n, 97))
+    assert total == sum(off[i + 1] - off[i] for i in range(0, n, 97))
+    ctx.set_option("cell_list", 0)
+    off2, lst2 = ctx.neighbors()
+    assert np.array_equal(off, off2) and np.array_equal(lst, lst2)
+
+
+def test_lj_pairs_on_the_cutoff_boundary(oracle):
+    """Pairs within a few ulp of R: the strict `r2 < R2` decision must match the reference's un-fused fp64."""
+    L, R = 10.0, 2.5
+    rng = np.random.Generator(np.random.Philox(77))
+    base = rng.random((3, 300)) * L
+    d = rng.standard_normal((3, 300))
+    d /= np.linalg.norm(d, axis=0)
+    scale = R * (1.0 + np.repeat(np.arange(-3, 3), 50) * 2.0 ** -52)
+    u = F(np.concatenate([base, base + d * scale], axis=1))
+    spec = dict(ms=np.ones(600), bc=("cubic", L), lj=dict(eps=1.0, sigma=1.0, R=R))
+    s = make_oracle(oracle, spec)
+    ctx = make_context(spec)
+    ctx.upload(u, np.zeros_like(u))
+    off, lst = ctx.neighbors()
+    for i in range(600):
+        assert np.array_equal(lst[off[i]:off[i + 1]], s.neighbors(u, i, R)), i
+
+
+# ------------------------------------------------------------------------------------------
+# SPC/Fw water RHS (src/nbody_to_ode.jl:502-532)
+# ------------------------------------------------------------------------------------------
+def _water(side, seed, Rel=None):
+    w = wl.water_omm(side, seed=seed, Rel=Rel)
+    rng = np.random.Generator(np.random.Philox(seed + 1))
+    u = F(w["u"] + 0.004 * rng.standard_normal(w["u"].shape))
+    spec = dict(ms=w["ms"], qs=w["qs"], water=True, bc=("cubic", w["L"]), lj=w["lj"], coulomb=w["coulomb"],
+                spcfw=w["spcfw"])
+    return w, u, spec
+
+
+def test_water_216_example_cutoffs(oracle):
+    """examples/water_spc_fw_omm_units.jl: 216 molecules, Rel = 0.49 L (all-pairs with PBC)."""
+    w, u, spec = _water(6, 2)
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    _check(make_context(spec).accel(u), ref)
+
+
+def test_water_cell_list_cutoffs(oracle):
+    """1,728 molecules with the example's absolute cutoffs: both pair terms go through cell lists."""
+    w, u, spec = _water(12, 4, Rel=0.9162)
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert ctx.info("cells_lj") > 0 and ctx.info("cells_el") > 0
+    _check(a, ref)
+
+
+# ------------------------------------------------------------------------------------------
+# RHS thermostats (src/thermostats.jl:76-91, :121-128)
+# ------------------------------------------------------------------------------------------
+def test_berendsen_rhs(oracle):
+    w, u = _fcc(6, 0.05, 5)
+    n = u.shape[1]
+    th = dict(kind="berendsen", T=90.0, tau=10 * w["dt"], kB=w["kB"], N=n, Nc=0)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"], thermostat=th)
+    ref = make_oracle(oracle, spec).rhs(u, w["v"].copy(order="F"), NT)
+    _check(make_context(spec).accel(u, w["v"].copy(order="F")), ref)
+
+
+def test_nosehoover_rhs(oracle):
+    w, u = _fcc(6, 0.05, 6)
+    n = u.shape[1]
+    th = dict(kind="nosehoover", T=90.0, tau=20 * w["dt"], kB=w["kB"], N=n, Nc=0)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"], thermostat=th)
+    u1 = F(np.concatenate([u, [[0.37], [0.0], [0.0]]], axis=1))   # zeta lives in element (1, n+1)
+    v1 = F(np.concatenate([w["v"], np.zeros((3, 1))], axis=1))
+    v_ref = v1.copy(order="F")
+    ref = make_oracle(oracle, spec).rhs(u1, v_ref, NT)
+    v_gpu = v1.copy(order="F")
+    a = make_context(spec).accel(u1, v_gpu)
+    _check(a[:, :n], ref[:, :n])
+    assert not a[:, n].any()
+    assert v_gpu[0, n] == pytest.approx(v_ref[0, n], rel=1e-13)   # the reference mutates v[zeta_ind]
+    assert np.array_equal(v_gpu[:, :n], v1[:, :n])
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident velocity Verlet against the oracle stepper
+# ------------------------------------------------------------------------------------------
+def test_velocity_verlet_gravity(oracle):
+    u = F([[-0.995492, 0.995492, 0.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    v = F([[-0.347902, -0.347902, 0.695804], [-0.53393, -0.53393, 1.067860], [0.0, 0.0, 0.0]])
+    spec = dict(ms=np.ones(3), gravity=dict(G=1.0))
+    dt = np.pi / 130
+    ur, vr = oracle.velocity_verlet(make_oracle(oracle, spec), u, v, dt, 260)
+    ctx = make_context(spec)
+    ctx.upload(u, v)
+    ctx.step_vv(dt, 260)
+    ug, vg, _ = ctx.download()
+    assert np.abs(ug - ur).max() < 1e-10 and np.abs(vg - vr).max() < 1e-10
+    assert np.abs(ug - u).max() < 1e-3  # test/gravitational_test.jl:54-60: the orbit closes
+
+
+@pytest.mark.parametrize("thermo", [None, "berendsen", "nosehoover"])
+def test_velocity_verlet_lj(oracle, thermo):
+    w, u = _fcc(5, 0.03, 8)
+    n = u.shape[1]
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    v = w["v"]
+    if thermo:
+        spec["thermostat"] = dict(kind=thermo, T=90.0, tau=10 * w["dt"], kB=w["kB"], N=n, Nc=0)
+    if thermo == "nosehoover":
+        u = F(np.concatenate([u, np.zeros((3, 1))], axis=1))
+        v = F(np.concatenate([v, np.zeros((3, 1))], axis=1))
+    ur, vr = oracle.velocity_verlet(make_oracle(oracle, spec), u, v.copy(order="F"), w["dt"], 20)
+    ctx = make_context(spec)
+    ctx.upload(u, v)
+    ctx.step_vv(w["dt"], 20)
+    ug, vg, _ = ctx.download()
+    assert np.abs(ug - ur).max() < 1e-9 * np.abs(ur).max()
+    assert np.abs(vg[:, :n] - vr[:, :n]).max() < 1e-9 * np.abs(vr).max()
+
+
+def test_energy_matches_oracle(oracle):
+    w, u, spec = _water(5, 12, Rel=0.9)
+    s = make_oracle(oracle, spec)
+    ctx = make_context(spec)
+    ctx.thermostat(0, kB=w["kB"], N=u.shape[1], Nc=2 * w["nmol"])
+    ctx.upload(u, w["v"])
+    ek, ep, T = ctx.energy()
+    assert ek == pytest.approx(s.kinetic_energy(w["v"]), rel=1e-13)
+    assert ep == pytest.approx(s.potential_energy(u), rel=1e-11)
+    assert T == pytest.approx(s.temperature(w["v"], w["kB"], N=u.shape[1], Nc=2 * w["nmol"]), rel=1e-13)
+
+
+# ------------------------------------------------------------------------------------------
+# error behaviour at the boundary
+# ------------------------------------------------------------------------------------------
+def test_errors_are_reported_not_thrown():
+    from nbody_b200._lib import Context, NbxError, ERR_INVALID, ERR_NONFINITE
+
+    ctx = Context(0)
+    with pytest.raises(NbxError) as e:
+        ctx.add_coulomb(1.0)          # before nbx_system
+    assert e.value.code == ERR_INVALID
+    ctx.system(np.ones(10))
+    with pytest.raises(NbxError) as e:
+        ctx.add_coulomb(1.0)          # no charges: the reference would fail reading `.q`
+    assert e.value.code == ERR_INVALID
+    with pytest.raises(NbxError):
+        ctx.boundary(1, [-1.0])
+    ctx.boundary(1, [2.0])
+    ctx.add_lj(1.0, 1.0, 0.9)
+    u = F(np.random.default_rng(0).random((3, 10)))
+    ctx.accel(u)
+    u[1, 3] = np.nan
+    with pytest.raises(NbxError) as e:    # the reference's wrap loop would never terminate
+        ctx.accel(u)
+    assert e.value.code == ERR_NONFINITE
+    with pytest.raises(NbxError) as e:
+        ctx.step_vv(0.1, 1)               # nothing resident
+    assert e.value.code == ERR_INVALID
