@@ -286,7 +286,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(u.nbytes),
                 "d2h_bytes_per_step": int(dv.nbytes), "api": "nbx_accel (RHS drop-in, host pointers)"},
-        "gpu_launches": int((k_cnt + i_cnt + k_cnt)),
+        "gpu_launches": 5 * args.steps,  # per step: vv_pos, allpairs, reduce, vv_vel, final_sum
         "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)

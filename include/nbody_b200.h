@@ -157,7 +157,9 @@ NBX_API int nbx_energy(nbx_ctx *ctx, double *ekin, double *epot, double *tempera
 NBX_API int nbx_neighbors(nbx_ctx *ctx, int64_t *offsets, int32_t *list, int64_t cap);
 
 /* ---- plumbing for the host layer ------------------------------------------------------- */
-/* CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on; NULL = own stream. */
+/* CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on; NULL = the context's own
+ * non-blocking stream (the default).  To share the legacy default stream pass cudaStreamLegacy
+ * ((void*)0x1), not 0. */
 NBX_API int nbx_set_stream(nbx_ctx *ctx, void *stream);
 NBX_API int nbx_synchronize(nbx_ctx *ctx);
 /* Device pointers of the resident SoA state: which = 0 pos, 1 vel, 2 acc; each is

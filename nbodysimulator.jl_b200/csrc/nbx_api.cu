@@ -290,8 +290,8 @@ int nbx_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const do
     NBX_TRY(dev_alloc(c, &c->aos_u, 3 * (size_t)(n + 1)));
     NBX_TRY(dev_alloc(c, &c->aos_v, 3 * (size_t)(n + 1)));
     NBX_TRY(dev_alloc(c, &c->aos_dv, 3 * (size_t)(n + 1)));
-    // padding: mass 1 (never divides by zero), weights 0, positions far away, velocities 0
-    NBX_TRY(upload_row(c, c->mass, m, n, 1.0));
+    // padding: weights (mass, charge, moments) 0, positions far away, velocities 0
+    NBX_TRY(upload_row(c, c->mass, m, n, 0.0));
     NBX_TRY(launch_fill(c, c->pos, kFarAway, 3 * c->npad));
     NBX_CUDA(c, cudaMemsetAsync(c->vel, 0, sizeof(double) * 3 * np, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(c->acc, 0, sizeof(double) * 3 * np, c->stream));

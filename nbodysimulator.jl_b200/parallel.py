@@ -41,7 +41,8 @@ class CudaEngine:
         self.device = torch.device("cuda", device_index)
         self.needs_temperature = False
         # run the library on torch's current stream so NCCL calls issued by torch are ordered with it
-        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # (torch's default stream has handle 0 == "own stream" in the C ABI; 0x1 is cudaStreamLegacy)
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
 
     def _view(self, which, shape):
         import torch

@@ -16,7 +16,10 @@ TOL = 1e-12
 NT = 8  # oracle threads (targets are independent; per-target arithmetic is the serial reference's)
 
 
-def _check(a, ref, tol=TOL, floor_frac=1e-9):
+def _check(a, ref, tol=TOL, floor_frac=1e-3):
+    """Per-body relative L2 error <= tol.  Bodies whose net acceleration cancels to less than
+    floor_frac of the system's RMS acceleration (e.g. the symmetric body of the figure-eight, whose
+    reference value is an exact 0 = x - x) are judged against floor_frac * RMS instead of their own norm."""
     assert a.shape == ref.shape
     assert np.isfinite(a).all()
     norms = np.linalg.norm(ref, axis=0)
