@@ -155,6 +155,73 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: LJ argon atom-steps/s (config 3 on one GPU)
+# ------------------------------------------------------------------------------------------------
+LJ_FLOP_PER_ATOM_STEP = 24.0 * 38.5      # algorithmic minimum, in-cutoff pairs only
+LJ_BYTES_PER_ATOM_STEP = 200.0           # fused VV 144 B + cell rebuild 56 B
+
+
+def lj_secondary(local, steps, warmup, hbm_peak, fp64_peak, cells=LJ_CELLS):
+    """1,048,576-atom FCC argon box, cubic PBC, R = 2.25 sigma, Berendsen, velocity Verlet on the device."""
+    import torch
+
+    import nbody_b200.workloads as wl
+    from nbody_b200 import _lib
+
+    w = wl.fcc_argon_reduced(cells)
+    n = w["u"].shape[1]
+    rng = np.random.Generator(np.random.Philox(2))
+    u = np.asfortranarray(w["u"] + 0.05 * rng.standard_normal(w["u"].shape))
+    ctx = _lib.Context(local)
+    ctx.system(w["ms"])
+    ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+    ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+    ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 10 * w["dt"], w["kB"], n, 0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+    ctx.upload(u, w["v"])
+    for _ in range(max(warmup, 3)):
+        ctx.vv_begin(w["dt"]); ctx.vv_finish(w["dt"])
+    torch.cuda.synchronize()
+    ctx.timing_reset()
+    ctx.timing_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.vv_begin(w["dt"]); ctx.vv_finish(w["dt"])
+    e1.record()
+    torch.cuda.synchronize()
+    ctx.timing_enable(False)
+    ms = e0.elapsed_time(e1)
+    pair_ms, pair_cnt = ctx.timing_get(_lib.T_PAIR_CELLS)
+    build_ms, _ = ctx.timing_get(_lib.T_CELL_BUILD)
+    int_ms, _ = ctx.timing_get(_lib.T_INTEGRATE)
+    value = n * steps / (ms * 1e-3)
+    _, _, T = ctx.energy(potential=False)
+    out = {
+        "metric": "LJ argon atom-steps/s (1,048,576 atoms, cell list, Berendsen, velocity Verlet)",
+        "value": value, "unit": "atom-steps/s", "ms_per_step": ms / steps, "steps": steps, "n_atoms": n,
+        "cells": ctx.info("cells_lj"), "temperature_after": T,
+        "inputs": "25 MB positions: smaller than L2, cell rebuild every step; not flushed",
+        "ms_per_step_pair_kernel": pair_ms / max(pair_cnt, 1), "ms_per_step_cell_build": build_ms / steps,
+        "ms_per_step_integrate": int_ms / steps,
+        "roofline_fp64": {"achieved": LJ_FLOP_PER_ATOM_STEP * value / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": LJ_FLOP_PER_ATOM_STEP * value / 1e12 / fp64_peak if fp64_peak else None},
+        "roofline_hbm": {"achieved": LJ_BYTES_PER_ATOM_STEP * value / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": LJ_BYTES_PER_ATOM_STEP * value / 1e9 / hbm_peak if hbm_peak else None},
+    }
+    ctx.close()
+    return out
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -289,6 +356,13 @@ def run_b200(args):
         "gpu_launches": 5 * args.steps,  # per step: vv_pos, allpairs, reduce, vv_vel, final_sum
         "roofline": roofline, "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_lj:
+        hbm, src = measured_hbm_peak()
+        try:
+            out["lj"] = lj_secondary(local, max(args.steps, 5), args.warmup, hbm, peak_tf)
+            out["lj"]["roofline_hbm"]["peak_source"] = src
+        except Exception as e:  # the headline line must still be printed
+            out["lj"] = {"error": repr(e)}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -300,6 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-lj", action="store_true", help="skip the secondary LJ argon measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
