@@ -110,7 +110,6 @@ class ShardedStepper:
         dist.all_gather_into_tensor(recv, send, group=self.group)
         recv = recv.view(self.world, 3, per)
         for r in range(self.world):
-            lo, hi, _ = partition(n, self.world, r, 1)
             lo, hi = min(n, r * per), min(n, r * per + per)
             if hi > lo and r != self.rank:
                 rows[:, lo:hi] = recv[r, :, :hi - lo]
