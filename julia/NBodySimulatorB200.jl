@@ -1,0 +1,155 @@
+# NBodySimulatorB200.jl -- the reference-side binding of libnbody_b200.so (pure `ccall`, no CUDA.jl).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither this image nor the GPU box has Julia.  The same
+# sequence of C-ABI calls is exercised from Python ctypes (nbodysimulator.jl_b200/_lib.py, tests/).
+# Every ccall below matches one prototype of include/nbody_b200.h.
+#
+# Two adapters over the one C ABI (SURVEY.md section 8b):
+#   (1) RHS drop-in   : B200Problem(sim) -> a normal SecondOrderODEProblem whose soode_system! is
+#                       `ccall(:nbx_accel, ...)`; any DiffEq integrator / callback / accessor works.
+#   (2) fused drop-in : run_simulation(sim, B200VelocityVerlet(); dt, saveat) runs the whole loop on
+#                       the device and wraps the saved frames in a SimulationResult.
+module NBodySimulatorB200
+
+using NBodySimulator
+using NBodySimulator: NBodySimulation, PotentialNBodySystem, WaterSPCFw, get_masses,
+                      gather_bodies_initial_coordinates, InfiniteBox, PeriodicBoundaryConditions,
+                      CubicPeriodicBoundaryConditions, BerendsenThermostat, NoseHooverThermostat,
+                      AndersenThermostat, LangevinThermostat, NullThermostat
+using SciMLBase, RecursiveArrayTools
+
+const LIB = get(ENV, "NBODY_B200_LIB", "libnbody_b200.so")
+
+struct NbxError <: Exception
+    code::Cint
+    msg::String
+end
+
+mutable struct B200Context
+    h::Ptr{Cvoid}
+    n::Int
+    ncols::Int
+    function B200Context(device::Integer = 0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:nbx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, device)
+        rc == 0 || throw(NbxError(rc, unsafe_string(ccall((:nbx_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+        ctx = new(ref[], 0, 0)
+        finalizer(c -> ccall((:nbx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+
+function check(ctx::B200Context, rc::Cint)
+    rc == 0 && return nothing
+    throw(NbxError(rc, unsafe_string(ccall((:nbx_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h))))
+end
+
+# ---- lowering an NBodySimulation to the context (mirrors nbody_to_ode.jl:263-433) ----------------
+function configure!(ctx::B200Context, s::NBodySimulation)
+    sys = s.system
+    ms = Vector{Float64}(get_masses(sys))
+    n = length(ms)
+    if sys isa WaterSPCFw
+        qs = repeat([sys.qO, sys.qH, sys.qH], length(sys.bodies))
+        check(ctx, ccall((:nbx_system, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                         ctx.h, n, ms, Vector{Float64}(qs), C_NULL, 1))
+    else
+        pots = sys.potentials
+        qs = haskey(pots, :electrostatic) ? Float64[b.q for b in sys.bodies] : nothing
+        mm = haskey(pots, :magnetostatic) ? Float64[b.mm[k] for k in 1:3, b in sys.bodies] : nothing
+        check(ctx, ccall((:nbx_system, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                         ctx.h, n, ms, qs === nothing ? C_NULL : qs, mm === nothing ? C_NULL : mm, 0))
+    end
+    ctx.n = n
+
+    bc = s.boundary_conditions
+    if bc isa CubicPeriodicBoundaryConditions
+        check(ctx, ccall((:nbx_boundary, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.h, 1, Float64[bc.L]))
+    elseif bc isa PeriodicBoundaryConditions
+        check(ctx, ccall((:nbx_boundary, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.h, 2, Float64[bc[i] for i in 1:6]))
+    else
+        check(ctx, ccall((:nbx_boundary, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), ctx.h, 0, C_NULL))
+    end
+
+    if sys isa WaterSPCFw
+        lj, el, sp = sys.lj_parameters, sys.e_parameters, sys.scpfw_parameters
+        check(ctx, ccall((:nbx_add_lj, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Float64), ctx.h, lj.ϵ, lj.σ, lj.R))
+        check(ctx, ccall((:nbx_add_coulomb, LIB), Cint, (Ptr{Cvoid}, Float64, Float64), ctx.h, el.k, el.R))
+        check(ctx, ccall((:nbx_add_spcfw, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Float64, Float64),
+                         ctx.h, sp.rOH, sp.aHOH, sp.kb, sp.ka))
+    else
+        for (name, p) in sys.potentials
+            if name == :lennard_jones
+                check(ctx, ccall((:nbx_add_lj, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Float64), ctx.h, p.ϵ, p.σ, p.R))
+            elseif name == :electrostatic
+                check(ctx, ccall((:nbx_add_coulomb, LIB), Cint, (Ptr{Cvoid}, Float64, Float64), ctx.h, p.k, p.R))
+            elseif name == :magnetostatic
+                check(ctx, ccall((:nbx_add_dipole, LIB), Cint, (Ptr{Cvoid}, Float64), ctx.h, p.μ_4π))
+            elseif name == :gravitational
+                check(ctx, ccall((:nbx_add_gravity, LIB), Cint, (Ptr{Cvoid}, Float64), ctx.h, p.G))
+            else
+                error("potential $name has no B200 kernel; keep its closure on the host")
+            end
+        end
+    end
+
+    th = s.thermostat
+    (N, Nc, _) = NBodySimulator.get_degrees_of_freedom(sys)
+    kind, T0, par = th isa BerendsenThermostat ? (1, th.T, th.τ) :
+                    th isa NoseHooverThermostat ? (2, th.T, th.τ) :
+                    th isa AndersenThermostat ? (3, th.T, th.ν) :
+                    th isa LangevinThermostat ? (4, th.T, th.γ) : (0, 0.0, 0.0)
+    check(ctx, ccall((:nbx_thermostat, LIB), Cint, (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Int64, Int64),
+                     ctx.h, kind, T0, par, s.kb, N, Nc))
+    ctx.ncols = n + (kind == 2 ? 1 : 0)
+    return ctx
+end
+
+# ---- (1) RHS drop-in --------------------------------------------------------------------------------
+"""
+    B200Problem(simulation; device = 0)
+
+Same object `SciMLBase.SecondOrderODEProblem(simulation)` returns (src/nbody_to_ode.jl:460-491), with
+`soode_system!` evaluated on the GPU.  `u`, `v`, `dv` are the solver's own `Matrix{Float64}` (3 x ncols).
+"""
+function B200Problem(s::NBodySimulation; device::Integer = 0)
+    ctx = configure!(B200Context(device), s)
+    (u0, v0, n) = gather_bodies_initial_coordinates(s)
+    function soode_system!(dv, v, u, p, t)
+        check(ctx, ccall((:nbx_accel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                         ctx.h, u, v, t, dv))
+        return nothing
+    end
+    return SecondOrderODEProblem(soode_system!, v0, u0, s.tspan)
+end
+
+# ---- (2) fused drop-in --------------------------------------------------------------------------------
+struct B200VelocityVerlet end
+
+function NBodySimulator.run_simulation(s::NBodySimulation, ::B200VelocityVerlet; dt, saveat::Integer = 1, device = 0)
+    ctx = configure!(B200Context(device), s)
+    (u0, v0, n) = gather_bodies_initial_coordinates(s)
+    check(ctx, ccall((:nbx_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx.h, u0, v0))
+    nsteps = round(Int, (s.tspan[2] - s.tspan[1]) / dt)
+    ts = [s.tspan[1]]
+    frames = [ArrayPartition(copy(v0), copy(u0))]
+    done = 0
+    while done < nsteps
+        k = min(saveat, nsteps - done)
+        check(ctx, ccall((:nbx_step_vv, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), ctx.h, dt, k))
+        done += k
+        u = similar(u0); v = similar(v0)
+        check(ctx, ccall((:nbx_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                         ctx.h, u, v, C_NULL))
+        push!(ts, s.tspan[1] + done * dt)
+        push!(frames, ArrayPartition(v, u))
+    end
+    # a DiffEq-shaped solution so that get_position / temperature / energies / rdf / msd work unchanged
+    prob = B200Problem(s; device = device)
+    sol = SciMLBase.build_solution(prob, B200VelocityVerlet(), ts, frames; retcode = SciMLBase.ReturnCode.Success)
+    return NBodySimulator.SimulationResult(sol, s)
+end
+
+export B200Context, B200Problem, B200VelocityVerlet
+
+end # module

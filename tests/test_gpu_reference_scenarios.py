@@ -129,21 +129,22 @@ def _argon(n_side=5, T=120.0):
 
 def test_lennard_jones_three_atoms_temperature_and_energy():
     # test/lennard_jones_test.jl:46-97
-    kb = 1.38e-23
+    kb = 8.3144598e-3
     T = 120.0
-    eps, sigma = T * kb, 3.4e-10
-    m = 39.95 * 1.6747e-27
-    L, tau = 5 * sigma, 1e-14
+    eps, sigma = T * kb, 0.34
+    m = 39.95
+    L, tau = 5 * sigma, 0.5e-3
     v = math.sqrt(3 * kb * T / m)
-    bodies = [MassBody([0, 0, 0], [v, 0, 0], m), MassBody([1.3 * sigma, 0, 0], [0, v, 0], m),
-              MassBody([0, 1.3 * sigma, 1.0 * sigma], [0, 0, v], m)]
+    bodies = [MassBody([L / 3, L / 3, 2 * L / 3], [0, 0, -v], m), MassBody([L / 3, 2 * L / 3, L / 3], [0, -v, 0], m),
+              MassBody([2 * L / 3, L / 3, L / 3], [-v, 0, 0], m)]
     pot = {"lennard_jones": LennardJonesParameters(eps, sigma, 2.25 * sigma)}
+    t2 = 100 * tau
     for bc in (PeriodicBoundaryConditions(L), CubicPeriodicBoundaryConditions(L)):
-        sim = NBodySimulation(PotentialNBodySystem(bodies, pot), (0.0, 200 * tau), bc, kb)
+        sim = NBodySimulation(PotentialNBodySystem(bodies, pot), (0.0, t2), bc, kb)
         sr = run_simulation(sim, VelocityVerlet(), dt=tau)
         assert temperature(sr, 0.0) == pytest.approx(T, abs=1e-6)                          # :77-79
         assert kinetic_energy(sr, 0.0) == pytest.approx(3 * m * v * v / 2, rel=1e-14)        # :81-82
-        e0, e1 = total_energy(sr, 0.0), total_energy(sr, 200 * tau)
+        e0, e1 = total_energy(sr, 0.0), total_energy(sr, t2)
         assert abs(e1 - e0) <= 0.1 * abs(e0)                                                 # :84-97
         assert initial_energy(sim) == pytest.approx(e0, rel=1e-12)
 
