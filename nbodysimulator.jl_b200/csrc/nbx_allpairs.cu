@@ -385,6 +385,11 @@ int launch_allpairs_grav(nbx_ctx *c, const double *w, int scale_kind, double sca
     p.tgt_lo = (int)c->tgt_lo;
     p.ntgt = (int)(c->tgt_hi - c->tgt_lo);
     if (p.ntgt <= 0) return NBX_OK;
+    if (c->opt_sym && c->tgt_lo == 0 && c->tgt_hi == c->n && c->n >= c->sym_min_n) {
+        const bool is_mass = (w == c->mass);
+        return launch_sympairs(c, w, is_mass ? c->mass_uniform : c->charge_uniform, is_mass ? c->h_m1 : c->h_q1,
+                               scale_kind, scale, acc_out, accumulate);
+    }
     GravPolicy::Args a{x, y, z};
     NBX_TRY((run_allpairs<GravPolicy, G_T, G_THREADS, G_S, G_NST, G_MINB>(c, &p, a)));
     return run_reduce(c, p, GravPolicy::NACC, scale_kind, scale, c->mass, 1, acc_out, c->npad, accumulate);

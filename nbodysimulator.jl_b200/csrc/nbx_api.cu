@@ -279,6 +279,11 @@ int nbx_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const do
     c->has_q = q != nullptr;
     c->has_mm = mm != nullptr;
     c->h_m1 = m[0];
+    c->mass_uniform = true;
+    for (int64_t i = 1; i < n && c->mass_uniform; ++i) c->mass_uniform = (m[i] == m[0]);
+    c->charge_uniform = q != nullptr;
+    c->h_q1 = q ? q[0] : 0.0;
+    for (int64_t i = 1; q && i < n && c->charge_uniform; ++i) c->charge_uniform = (q[i] == q[0]);
     c->tgt_lo = 0;
     c->tgt_hi = n;
     const size_t np = (size_t)c->npad;
@@ -664,6 +669,9 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     if (!strcmp(key, "cell_list")) c->opt_cell_list = (int)value;
     else if (!strcmp(key, "prefilter")) c->opt_prefilter = (int)value;
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
+    else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
+    else if (!strcmp(key, "uniform_weights")) { if (!value) c->mass_uniform = c->charge_uniform = false; }
     else return fail(c, NBX_ERR_INVALID, "nbx_set_option: unknown key '%s'", key);
     return NBX_OK;
 }

@@ -10,7 +10,9 @@
 namespace nbx {
 
 constexpr int kPad = 1024;           // SoA rows are padded to a multiple of this many doubles
-constexpr double kFarAway = 1.0e100; // position of padding sources (weight 0) in the infinite box
+// Padding sources sit here: r^2 = 3e300 is finite, but r^-3 underflows to exactly 0, so a padding source
+// contributes exactly nothing to the unbounded kernels whatever its weight.
+constexpr double kFarAway = 1.0e150;
 constexpr int kMaxTimers = 8192;     // event pairs kept per phase between resets
 
 struct Timer {
@@ -106,6 +108,10 @@ struct nbx_ctx {
     int opt_cell_list = 1;
     int opt_prefilter = 1;
     int opt_graph = 1;
+    int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
+    int64_t sym_min_n = 8192;
+    bool mass_uniform = false, charge_uniform = false; // all weights equal (value = first element)
+    double h_q1 = 0.0;
 
     // ---- neighbour scratch ------------------------------------------------------------------
     // ---- host staging -----------------------------------------------------------------------
@@ -151,6 +157,9 @@ int dev_alloc(nbx_ctx *c, T **p, size_t count)
 // nbx_allpairs.cu
 int launch_allpairs_grav(nbx_ctx *c, const double *w, int scale_kind, double scale, double *acc_out, bool accumulate);
 int launch_allpairs_dipole(nbx_ctx *c, double *acc_out, bool accumulate);
+// nbx_sympairs.cu
+int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int scale_kind, double scale,
+                    double *acc_out, bool accumulate);
 int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_t ld, int64_t lo, int64_t hi,
                         int mstride, double *acc_out, int64_t ld_out, bool accumulate);
 // nbx_cells.cu

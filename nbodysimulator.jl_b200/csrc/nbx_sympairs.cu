@@ -1,0 +1,283 @@
+// nbx_sympairs.cu -- all-pairs 1/r^2 central forces with Newton's third law (sm_100a).
+//
+// Same result as the ordered kernel of nbx_allpairs.cu for gravitational_acceleration!
+// (src/basic_potentials.jl:306-331) and the unbounded Coulomb case (:274-304), but every UNORDERED
+// pair {i,j} is evaluated once and applied to both bodies: 20 FP64-pipe instructions per unordered
+// pair (18 when all weights are equal) instead of 2 x 16.
+//
+// Decomposition (half ring over tiles): the padded index range is cut into NT tiles of TS = 128*T
+// bodies.  Tile A interacts with tiles B = A+k (mod NT), k = 1..NT/2 (k = NT/2 only for A < NT/2, so
+// each unordered tile pair is visited once) and with itself (k = 0, ordered + self-masked).  A work
+// item is (A, segment of the k range); a persistent grid walks the items round-robin.
+//
+// Inside a CTA (4 warps): every lane keeps T bodies of A stationary in registers (positions, weights,
+// accumulators).  The B tile arrives in shared memory by TMA bulk copies (2-stage ring).  It is cut
+// into sets of 32*U bodies; a warp loads one set (U bodies per lane) and passes it around the warp
+// with shuffles: 32 ring steps visit all (32T) x (32U) pairs, the B-side accumulators travel with the
+// bodies.  The four warps' B-side sums of a set are added in a fixed order through shared memory and
+// written to the partial slot of ring offset k; the A-side sums go to the slot of the item's segment.
+// sym_reduce_kernel adds all slots of a body in ascending slot order -> bit-reproducible.
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+struct SymParams {
+    const double *x, *y, *z, *w;
+    int n, npad;
+    int NT, K, S;          // tiles, ring offsets 1..K, segments of the offset range [0..K]
+    int seg_len;           // offsets per segment (over the K+1 offsets 0..K)
+    double *part;          // [(S + K)][3][npad]
+};
+
+template <int T, int U, bool UNIFORM, bool DIAG>
+__device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&ay)[T], const double (&az)[T],
+                                          const double (&aw)[T], double (&fx)[T], double (&fy)[T], double (&fz)[T],
+                                          double (&bx)[U], double (&by)[U], double (&bz)[U], double (&bw)[U],
+                                          double (&gx)[U], double (&gy)[U], double (&gz)[U], int lane, int ibase,
+                                          int jbase)
+{
+    const int src = (lane + 1) & 31;
+#pragma unroll 1
+    for (int s = 0; s < 32; ++s) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const double dx = bx[u] - ax[t], dy = by[u] - ay[t], dz = bz[u] - az[t];
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (DIAG) {
+                    // body index of source u at this step vs target t (same tile)
+                    const int j = jbase + u * 32 + ((lane + s) & 31);
+                    const int i = ibase + t * 32 + lane;
+                    r2 = (i == j) ? 1.0 : r2; // dx = dy = dz = 0 -> contributes exactly 0
+                }
+                const double y0 = rsqrt_seed(r2);
+                const double a = y0 * y0;
+                const double e = fma(-r2, a, 1.0);
+                const double y3 = a * y0;
+                const double p = fma(1.875, e, 1.5);
+                const double q = p * e;
+                const double g = fma(y3, q, y3); // r^-3 to ~3 ulp
+                if (UNIFORM) {
+                    fx[t] = fma(g, dx, fx[t]); fy[t] = fma(g, dy, fy[t]); fz[t] = fma(g, dz, fz[t]);
+                    if (!DIAG) { gx[u] = fma(-g, dx, gx[u]); gy[u] = fma(-g, dy, gy[u]); gz[u] = fma(-g, dz, gz[u]); }
+                } else {
+                    const double sj = g * bw[u];
+                    fx[t] = fma(sj, dx, fx[t]); fy[t] = fma(sj, dy, fy[t]); fz[t] = fma(sj, dz, fz[t]);
+                    if (!DIAG) {
+                        const double si = -(g * aw[t]);
+                        gx[u] = fma(si, dx, gx[u]); gy[u] = fma(si, dy, gy[u]); gz[u] = fma(si, dz, gz[u]);
+                    }
+                }
+            }
+        }
+        // pass the B bodies (and their accumulators) to the neighbouring lane
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            bx[u] = __shfl_sync(0xffffffffu, bx[u], src);
+            by[u] = __shfl_sync(0xffffffffu, by[u], src);
+            bz[u] = __shfl_sync(0xffffffffu, bz[u], src);
+            if (!UNIFORM) bw[u] = __shfl_sync(0xffffffffu, bw[u], src);
+            if (!DIAG) {
+                gx[u] = __shfl_sync(0xffffffffu, gx[u], src);
+                gy[u] = __shfl_sync(0xffffffffu, gy[u], src);
+                gz[u] = __shfl_sync(0xffffffffu, gz[u], src);
+            }
+        }
+    }
+    // after 32 passes every body (and its accumulator) is back in the lane that loaded it
+}
+
+template <int T, int U, bool UNIFORM, int MINB>
+__global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
+{
+    constexpr int TS = 128 * T;       // bodies per tile
+    constexpr int SET = 32 * U;       // bodies per ring set
+    constexpr int NSET = TS / SET;
+    constexpr uint32_t STAGE_BYTES = 4 * TS * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);      // [2][4][TS]
+    double *red = ring + 2 * 4 * TS;                            // [4 warps][3][SET]
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    const int nitems = p.NT * p.S;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int A = item / p.S, seg = item - A * p.S;
+        const int k0 = seg * p.seg_len;
+        const int k1 = min(k0 + p.seg_len, p.K + 1);
+        const int A0 = A * TS;
+
+        double ax[T], ay[T], az[T], aw[T], fx[T], fy[T], fz[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int i = A0 + warp * (32 * T) + t * 32 + lane;
+            ax[t] = p.x[i]; ay[t] = p.y[i]; az[t] = p.z[i];
+            aw[t] = UNIFORM ? 1.0 : p.w[i];
+            fx[t] = fy[t] = fz[t] = 0.0;
+        }
+
+        // offsets of this item that really exist (k = K is owned by the lower half of the tiles)
+        auto live = [&](int k) { return !(k == p.K && A >= p.K && p.K > 0) && !(k > 0 && p.NT == 1); };
+        auto issue = [&](int k, int st) {
+            const int B0 = ((A + k) % p.NT) * TS;
+            double *dst = ring + (size_t)st * 4 * TS;
+            mbar_expect_tx(&full[st], STAGE_BYTES);
+            bulk_g2s(dst, p.x + B0, TS * sizeof(double), &full[st]);
+            bulk_g2s(dst + TS, p.y + B0, TS * sizeof(double), &full[st]);
+            bulk_g2s(dst + 2 * TS, p.z + B0, TS * sizeof(double), &full[st]);
+            bulk_g2s(dst + 3 * TS, p.w + B0, TS * sizeof(double), &full[st]);
+        };
+        auto next_live = [&](int k) { while (k < k1 && !live(k)) ++k; return k; };
+
+        int k = next_live(k0);
+        int st = 0;
+        if (tid == 0 && k < k1) issue(k, 0);
+        while (k < k1) {
+            const int kn = next_live(k + 1);
+            if (tid == 0 && kn < k1) issue(kn, st ^ 1); // stage st^1 was released by the barrier that ended block k-1
+            mbar_wait(&full[st], (parity >> st) & 1u);
+            parity ^= 1u << st;
+            const double *bsx = ring + (size_t)st * 4 * TS, *bsy = bsx + TS, *bsz = bsy + TS, *bsw = bsz + TS;
+            const int B0 = ((A + k) % p.NT) * TS;
+            const int ibase = A0 + warp * (32 * T);
+            for (int set = 0; set < NSET; ++set) {
+                double bx[U], by[U], bz[U], bw[U], gx[U], gy[U], gz[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int o = set * SET + u * 32 + lane;
+                    bx[u] = bsx[o]; by[u] = bsy[o]; bz[u] = bsz[o];
+                    bw[u] = UNIFORM ? 1.0 : bsw[o];
+                    gx[u] = gy[u] = gz[u] = 0.0;
+                }
+                if (k == 0) {
+                    ring_pass<T, U, UNIFORM, true>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
+                                                   B0 + set * SET);
+                } else {
+                    ring_pass<T, U, UNIFORM, false>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
+                                                    B0 + set * SET);
+                    // B-side sums of the four warps, added in warp order, go to the slot of ring offset k
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        red[(warp * 3 + 0) * SET + u * 32 + lane] = gx[u];
+                        red[(warp * 3 + 1) * SET + u * 32 + lane] = gy[u];
+                        red[(warp * 3 + 2) * SET + u * 32 + lane] = gz[u];
+                    }
+                    __syncthreads();
+                    double *slot = p.part + (size_t)(p.S + k - 1) * 3 * p.npad;
+                    for (int e = tid; e < 3 * SET; e += 128) {
+                        const int c = e / SET, o = e - c * SET;
+                        const double s = ((red[(0 * 3 + c) * SET + o] + red[(1 * 3 + c) * SET + o]) +
+                                          red[(2 * 3 + c) * SET + o]) + red[(3 * 3 + c) * SET + o];
+                        slot[(size_t)c * p.npad + B0 + set * SET + o] = s;
+                    }
+                    __syncthreads();
+                }
+            }
+            __syncthreads(); // all warps are done with stage st
+            st ^= 1;
+            k = kn;
+        }
+
+        double *slot = p.part + (size_t)seg * 3 * p.npad;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int i = A0 + warp * (32 * T) + t * 32 + lane;
+            slot[i] = fx[t];
+            slot[(size_t)p.npad + i] = fy[t];
+            slot[2 * (size_t)p.npad + i] = fz[t];
+        }
+    }
+}
+
+// acc_i (+)= f_i * sum over slots, ascending.  B-side slot K exists only for tiles >= K.
+__global__ void sym_reduce_kernel(const double *__restrict__ part, int npad, int n, int S, int K, int TS, int kind,
+                                  double scale, const double *__restrict__ mass, const double *__restrict__ charge,
+                                  double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az,
+                                  int accumulate)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int tile = i / TS;
+    int nslots = S + K;
+    if (K > 0 && tile < K) nslots -= 1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int sl = 0; sl < nslots; ++sl) {
+        const double *b = part + (size_t)sl * 3 * npad;
+        s0 += b[i]; s1 += b[(size_t)npad + i]; s2 += b[2 * (size_t)npad + i];
+    }
+    double f = scale;
+    if (kind == 1) f = scale * charge[i] / mass[i];
+    if (accumulate) { ax[i] += f * s0; ay[i] += f * s1; az[i] += f * s2; }
+    else { ax[i] = f * s0; ay[i] = f * s1; az[i] = f * s2; }
+}
+
+template <int T, int U, bool UNIFORM, int MINB>
+static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, double scale, double *acc_out,
+                   bool accumulate)
+{
+    constexpr int TS = 128 * T, SET = 32 * U;
+    SymParams p{};
+    p.x = c->pos; p.y = c->pos + c->npad; p.z = c->pos + 2 * c->npad; p.w = w;
+    p.n = (int)c->n; p.npad = (int)c->npad;
+    p.NT = p.npad / TS;
+    p.K = p.NT / 2;
+    const int grid_full = c->sm_count * MINB;
+    // enough items for a balanced static round-robin (>= ~24 per CTA), at least 2 offsets per segment
+    int S = (24 * grid_full + p.NT - 1) / p.NT;
+    const int max_S = (p.K + 1 + 1) / 2;
+    if (S > max_S) S = max_S;
+    if (S < 1) S = 1;
+    p.seg_len = (p.K + 1 + S - 1) / S;
+    p.S = (p.K + 1 + p.seg_len - 1) / p.seg_len;
+    const size_t bytes = (size_t)(p.S + p.K) * 3 * p.npad * sizeof(double);
+    if (bytes > c->part_bytes) {
+        if (c->part) { cudaFree(c->part); c->part = nullptr; c->part_bytes = 0; }
+        cudaError_t e = cudaMalloc((void **)&c->part, bytes);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(symmetric partials)");
+        c->part_bytes = bytes;
+    }
+    p.part = c->part;
+    auto kern = sym_kernel<T, U, UNIFORM, MINB>;
+    const size_t smem = (size_t)(2 * 4 * TS + 4 * 3 * SET) * sizeof(double);
+    const void *key = reinterpret_cast<const void *>(kern);
+    bool done = false;
+    for (const void *k : c->attr_done) done = done || (k == key);
+    if (!done) {
+        NBX_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->attr_done.push_back(key);
+    }
+    const long items = (long)p.NT * p.S;
+    const int grid = (int)(items < grid_full ? items : grid_full);
+    timer_begin(c, NBX_T_PAIR_ALLPAIRS);
+    kern<<<grid, 128, smem, c->stream>>>(p);
+    timer_end(c, NBX_T_PAIR_ALLPAIRS);
+    NBX_CUDA(c, cudaGetLastError());
+    c->last_grid = grid;
+    c->last_nchunk = p.S;
+    double f = scale;
+    if (UNIFORM) f *= wval;
+    sym_reduce_kernel<<<(p.n + 255) / 256, 256, 0, c->stream>>>(c->part, p.npad, p.n, p.S, p.K, TS, scale_kind, f, c->mass,
+                                                               c->charge, acc_out, acc_out + c->npad,
+                                                               acc_out + 2 * c->npad, accumulate ? 1 : 0);
+    NBX_CUDA(c, cudaGetLastError());
+    return NBX_OK;
+}
+
+// Whole-system (unsharded) evaluation; uniform = all weights equal to wval.
+int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int scale_kind, double scale,
+                    double *acc_out, bool accumulate)
+{
+    if (uniform) return run_sym<4, 4, true, 3>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    return run_sym<4, 4, false, 3>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+}
+
+} // namespace nbx

@@ -106,6 +106,29 @@ def test_gravity_plummer_262k_subsample(oracle):
     assert (np.abs(p) <= 1e-11 * scale).all()
 
 
+@pytest.mark.parametrize("uniform", [False, True])
+@pytest.mark.parametrize("n", [8192, 9000, 20481])
+def test_gravity_symmetric_pairs_kernel(oracle, n, uniform):
+    """Newton's-third-law kernel (whole-system evaluations, n >= 8192) against the oracle and against
+    the ordered kernel; general and equal-mass variants; n not a multiple of the tile size."""
+    rng, u, v = _rand(n, 900 + n)
+    ms = np.full(n, 0.37) if uniform else rng.random(n) + 0.1
+    spec = dict(ms=ms, gravity=dict(G=1.3))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    ctx = make_context(spec)
+    a_sym = ctx.accel(u).copy()
+    _check(a_sym, ref)
+    assert np.array_equal(a_sym, ctx.accel(u))          # deterministic
+    ctx.set_option("symmetric_pairs", 0)
+    a_ord = ctx.accel(u)
+    _check(a_ord, ref)
+    _check(a_sym, a_ord)
+    if uniform:                                          # the equal-weight fast path changes nothing beyond rounding
+        ctx.set_option("symmetric_pairs", 1)
+        ctx.set_option("uniform_weights", 0)
+        _check(ctx.accel(u), a_sym, tol=1e-13)
+
+
 def test_gravity_shard_matches_full(oracle):
     n = 3000
     rng, u, v = _rand(n, 5)
