@@ -256,7 +256,8 @@ def run_b200(args):
                 ctx.vv_begin(dt)
                 ctx.vv_finish(dt)
 
-    stepper = ShardedStepper(eng) if world > 1 else _Solo()
+    # N > 1: pair sharding (Newton's-third-law kernel on every rank + reduce-scatter of the accelerations)
+    stepper = ShardedStepper(eng, mode=args.mode) if world > 1 else _Solo()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
 
     def barrier():
@@ -319,15 +320,16 @@ def run_b200(args):
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peak_tf, eff_mhz = ctx.measure_fp64_peak()
     kernel_ms = k_ms / max(k_cnt, 1)
+    instr_pp = 9 if (world == 1 or args.mode == "pairs") else 16  # FP64-pipe instructions per ORDERED pair
     pairs_per_launch = float(hi - lo) * float(n - 1)
     achieved_tf = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp64", "kernel": "allpairs_kernel<GravPolicy>", "achieved": achieved_tf, "peak": peak_tf,
+        "bound": "fp64", "kernel": "sym_kernel<8,2,uniform> (Newton 3rd law, 18 FP64 instr per unordered pair = 9 per ordered pair)" if (world == 1 or args.mode == "pairs") else "allpairs_kernel<GravPolicy> (16 FP64 instr per ordered pair)", "achieved": achieved_tf, "peak": peak_tf,
         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
         "peak_source": "DFMA saturation microbenchmark measured live on this device (MEASURED_PEAKS.json has no "
                        "FP64 figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
         "peak_effective_sm_mhz": eff_mhz, "flop_per_pair": FLOP_PER_PAIR,
-        "fp64_instr_per_pair": 16, "pipe_bound_frac_of_peak": FLOP_PER_PAIR / (16 * 2.0),
+        "fp64_instr_per_pair": instr_pp, "pipe_bound_frac_of_peak": FLOP_PER_PAIR / (instr_pp * 2.0),
         "kernel_ms": kernel_ms, "kernel_launches": k_cnt, "kernel_share_of_step": k_ms / ms_total,
         "integrate_ms_per_step": i_ms / max(args.steps, 1),
     }
@@ -348,7 +350,7 @@ def run_b200(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "gravity_plummer_262144", "n_bodies": n, "integrator": "velocity_verlet",
                    "dt": DT_GRAVITY, "l2": "flushed between timed steps (256 MB write, untimed)",
-                   "parallelism": f"target-block sharding x{world}, per-step position all-gather" if world > 1 else "1 GPU",
+                   "parallelism": (f"pair sharding x{world}: position all-gather + acceleration reduce-scatter per step" if args.mode == "pairs" else f"target-block sharding x{world}, per-step position all-gather") if world > 1 else "1 GPU",
                    "allpairs_grid": ctx.info("allpairs_grid"), "allpairs_chunks": ctx.info("allpairs_chunks")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(u.nbytes),
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-lj", action="store_true", help="skip the secondary LJ argon measurement")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "targets"], help="multi-GPU decomposition")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

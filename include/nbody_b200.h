@@ -114,6 +114,14 @@ NBX_API int nbx_thermostat(nbx_ctx *ctx, int kind, double T0, double param, doub
  * written as zeros by nbx_accel.  (No reference equivalent: the reference is serial.) */
 NBX_API int nbx_shard(nbx_ctx *ctx, int64_t lo, int64_t hi);
 
+/* Multi-GPU, alternative for unbounded 1/r^2 systems (gravity, Coulomb with R = Inf in an InfiniteBox):
+ * pair sharding.  The unordered pair set is split over nranks contexts (Newton's third law kernel,
+ * ring offsets k = rank mod nranks); after nbx_vv_forces every context holds a PARTIAL acceleration
+ * for ALL columns in the acc rows (nbx_device_ptr which = 2) and the host adds them across ranks
+ * (reduce-scatter / all-reduce) before nbx_vv_finish.  Combine with nbx_shard(lo, hi), which then only
+ * selects the columns this context integrates. */
+NBX_API int nbx_shard_pairs(nbx_ctx *ctx, int rank, int nranks);
+
 /* ---- RHS drop-in ---------------------------------------------------------------------- */
 /* soode_system!(dv, v, u, p, t): src/nbody_to_ode.jl:474-488 (PotentialNBodySystem) and
  * :502-532 (WaterSPCFw).  Host pointers, 3 x ncols each.  dv is overwritten.  With the
@@ -139,6 +147,9 @@ NBX_API int nbx_set_seed(nbx_ctx *ctx, uint64_t seed);
  * between the halves:  begin = position update of the own shard;  the host all-gathers the
  * SoA position arrays (nbx_device_ptr);  finish = forces + velocity update of the shard. */
 NBX_API int nbx_vv_begin(nbx_ctx *ctx, double dt);
+/* optional middle step: evaluate the pair potentials only (needed with nbx_shard_pairs, where the host
+ * sums the partial accelerations across ranks between nbx_vv_forces and nbx_vv_finish) */
+NBX_API int nbx_vv_forces(nbx_ctx *ctx);
 NBX_API int nbx_vv_finish(nbx_ctx *ctx, double dt);
 /* Evaluate a = f(v, x) of the resident state (all potentials + RHS thermostats). */
 NBX_API int nbx_eval_resident(nbx_ctx *ctx);

@@ -40,6 +40,8 @@ SIGNATURES = {
     "nbx_clear_potentials": (C.c_int, [_vp]),
     "nbx_thermostat": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, _i64, _i64]),
     "nbx_shard": (C.c_int, [_vp, _i64, _i64]),
+    "nbx_shard_pairs": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "nbx_vv_forces": (C.c_int, [_vp]),
     "nbx_accel": (C.c_int, [_vp, _dp, _dp, C.c_double, _dp]),
     "nbx_upload": (C.c_int, [_vp, _dp, _dp]),
     "nbx_step_vv": (C.c_int, [_vp, C.c_double, _i64]),
@@ -203,8 +205,14 @@ class Context:
     def vv_begin(self, dt):
         self._ck(self.lib.nbx_vv_begin(self.h, float(dt)))
 
+    def vv_forces(self):
+        self._ck(self.lib.nbx_vv_forces(self.h))
+
     def vv_finish(self, dt):
         self._ck(self.lib.nbx_vv_finish(self.h, float(dt)))
+
+    def shard_pairs(self, rank, nranks):
+        self._ck(self.lib.nbx_shard_pairs(self.h, int(rank), int(nranks)))
 
     def eval_resident(self):
         self._ck(self.lib.nbx_eval_resident(self.h))

@@ -385,7 +385,8 @@ int launch_allpairs_grav(nbx_ctx *c, const double *w, int scale_kind, double sca
     p.tgt_lo = (int)c->tgt_lo;
     p.ntgt = (int)(c->tgt_hi - c->tgt_lo);
     if (p.ntgt <= 0) return NBX_OK;
-    if (c->opt_sym && c->tgt_lo == 0 && c->tgt_hi == c->n && c->n >= c->sym_min_n) {
+    const bool whole = c->tgt_lo == 0 && c->tgt_hi == c->n;
+    if (c->pair_nranks > 1 || (c->opt_sym && whole && c->n >= c->sym_min_n)) {
         const bool is_mass = (w == c->mass);
         return launch_sympairs(c, w, is_mass ? c->mass_uniform : c->charge_uniform, is_mass ? c->h_m1 : c->h_q1,
                                scale_kind, scale, acc_out, accumulate);

@@ -92,11 +92,21 @@ static int zero_rows(nbx_ctx *c, double *rows, int64_t lo, int64_t hi)
     return NBX_OK;
 }
 
-// pos (+ vel, d_scal) -> acc for the target columns [tgt_lo, tgt_hi); everything stays on the stream
-int compute_accel(nbx_ctx *c)
+// Pair potentials: pos -> acc.  Target sharding: the columns [tgt_lo, tgt_hi) get their full
+// accelerations.  Pair sharding (pair_nranks > 1): ALL columns get this rank's partial sums, which the
+// host adds across ranks (reduce-scatter) before nbx_vv_finish.  Everything stays on the stream.
+int compute_pairs(nbx_ctx *c)
 {
+    const bool pair_mode = c->pair_nranks > 1;
+    if (pair_mode) {
+        const bool central_only = !c->has_lj && !c->has_dip && !c->has_spcfw && !c->water &&
+                                  (!c->has_coul || (c->bc_kind == NBX_BC_INFINITE && isinf(c->el_R2)));
+        if (!central_only)
+            return fail(c, NBX_ERR_UNSUPPORTED, "pair sharding covers unbounded gravity / Coulomb only; use nbx_shard");
+        NBX_TRY(zero_rows(c, c->acc, 0, c->n));
+    }
     const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
-    NBX_TRY(zero_rows(c, c->acc, lo, hi));
+    if (!pair_mode) NBX_TRY(zero_rows(c, c->acc, lo, hi));
 
     if (c->has_lj) {
         if (c->water) {
@@ -145,8 +155,16 @@ int compute_accel(nbx_ctx *c)
     if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, true));
     if (c->has_grav) NBX_TRY(launch_allpairs_grav(c, c->mass, 0, c->G, c->acc, true));
     if (c->has_spcfw) NBX_TRY(launch_spcfw_bonded(c, c->acc));
-    NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel));
     return NBX_OK;
+}
+
+// pos, vel (+ d_scal) -> acc: pair potentials, then the RHS thermostat terms (src/nbody_to_ode.jl:484-486)
+int compute_accel(nbx_ctx *c)
+{
+    if (c->pair_nranks > 1)
+        return fail(c, NBX_ERR_INVALID, "pair-sharded context: drive nbx_vv_forces / reduce / nbx_vv_finish");
+    NBX_TRY(compute_pairs(c));
+    return launch_thermostat_rhs(c, c->acc, c->vel);
 }
 
 static void free_system(nbx_ctx *c)
@@ -199,7 +217,13 @@ static int accel_from_staging(nbx_ctx *c, bool have_v)
             NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 1, c->aos_u + 3 * c->n, sizeof(double), cudaMemcpyDeviceToDevice,
                                         c->stream));
     }
-    NBX_TRY(compute_accel(c));
+    {   // the RHS drop-in always returns complete accelerations of the own targets (no pair sharding)
+        const int pr = c->pair_rank, pn = c->pair_nranks;
+        c->pair_rank = 0; c->pair_nranks = 1;
+        const int rc = compute_accel(c);
+        c->pair_rank = pr; c->pair_nranks = pn;
+        if (rc != NBX_OK) return rc;
+    }
     NBX_TRY(launch_soa_to_aos(c, c->acc, c->aos_dv, c->n, c->ncols, c->tgt_lo, c->tgt_hi));
     c->resident = false;
     return NBX_OK;
@@ -407,6 +431,15 @@ int nbx_thermostat(nbx_ctx *c, int kind, double T0, double param, double kB, int
     return NBX_OK;
 }
 
+int nbx_shard_pairs(nbx_ctx *c, int rank, int nranks)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_shard_pairs"));
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, NBX_ERR_INVALID, "nbx_shard_pairs: rank %d of %d", rank, nranks);
+    c->pair_rank = rank; c->pair_nranks = nranks;
+    return NBX_OK;
+}
+
 int nbx_shard(nbx_ctx *c, int64_t lo, int64_t hi)
 {
     NBX_TRY(guard(c));
@@ -494,7 +527,14 @@ int nbx_upload(nbx_ctx *c, const double *u, const double *v)
         NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 2, c->aos_v + 3 * c->n, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
     c->rng_step = 0;
-    NBX_TRY(compute_accel(c)); // a(0)
+    {   // a(0): every rank holds the whole state at upload time, so evaluate it unsharded
+        const int pr = c->pair_rank, pn = c->pair_nranks;
+        c->pair_rank = 0; c->pair_nranks = 1;
+        const int rc = compute_accel(c);
+        c->pair_rank = pr; c->pair_nranks = pn;
+        if (rc != NBX_OK) return rc;
+    }
+    c->forces_done = false;
     c->resident = true;
     return finish_and_check(c);
 }
@@ -520,12 +560,28 @@ int nbx_vv_begin(nbx_ctx *c, double dt)
     return launch_vv_pos(c, dt);
 }
 
+int nbx_vv_forces(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_vv_forces"));
+    double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
+    NBX_TRY(compute_pairs(c)); // a(t+dt) from x(t+dt): full for the own targets, or partial for all (pair sharding)
+    c->forces_done = true;
+    return NBX_OK;
+}
+
 int nbx_vv_finish(nbx_ctx *c, double dt)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_vv_finish"));
-    double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
-    NBX_TRY(compute_accel(c));  // a(t+dt) from x(t+dt) and, for the RHS thermostats, v(t)
+    if (!c->forces_done) {
+        if (c->pair_nranks > 1)
+            return fail(c, NBX_ERR_INVALID, "nbx_vv_finish: pair-sharded contexts need nbx_vv_forces + a cross-rank sum first");
+        double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
+        NBX_TRY(compute_pairs(c));
+    }
+    c->forces_done = false;
+    NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel)); // RHS thermostats use v(t) and the temperature of v(t)
     NBX_TRY(launch_vv_vel(c, dt));
     if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
     return NBX_OK;
@@ -630,7 +686,7 @@ int nbx_device_ptr(nbx_ctx *c, int which, void **ptr, int64_t *ld)
     switch (which) {
     case 0: *ptr = c->pos; break;
     case 1: *ptr = c->vel; break;
-    case 2: *ptr = c->acc; break;
+    case 2: *ptr = c->acc; break; // NOTE: acc and acc_old swap every step; query after nbx_vv_forces
     case 3: *ptr = c->d_scal; break; // [0] = sum m v^2 of the shard after a step (all-reduce it across ranks)
     default: return fail(c, NBX_ERR_INVALID, "nbx_device_ptr: which = %d", which);
     }
@@ -671,6 +727,7 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
+    else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;
     else if (!strcmp(key, "uniform_weights")) { if (!value) c->mass_uniform = c->charge_uniform = false; }
     else return fail(c, NBX_ERR_INVALID, "nbx_set_option: unknown key '%s'", key);
     return NBX_OK;

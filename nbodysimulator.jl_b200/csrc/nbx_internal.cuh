@@ -110,6 +110,9 @@ struct nbx_ctx {
     int opt_graph = 1;
     int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
     int64_t sym_min_n = 8192;
+    int opt_sym_variant = 0;
+    int pair_rank = 0, pair_nranks = 1; // pair sharding: this context evaluates ring offsets k = rank mod nranks
+    bool forces_done = false;           // nbx_vv_forces ran; nbx_vv_finish only has to finish the step
     bool mass_uniform = false, charge_uniform = false; // all weights equal (value = first element)
     double h_q1 = 0.0;
 

@@ -6,17 +6,19 @@
 // pair (18 when all weights are equal) instead of 2 x 16.
 //
 // Decomposition (half ring over tiles): the padded index range is cut into NT tiles of TS = 128*T
-// bodies.  Tile A interacts with tiles B = A+k (mod NT), k = 1..NT/2 (k = NT/2 only for A < NT/2, so
-// each unordered tile pair is visited once) and with itself (k = 0, ordered + self-masked).  A work
-// item is (A, segment of the k range); a persistent grid walks the items round-robin.
+// bodies.  Tile A interacts with tiles B = A+k (mod NT), k = 1..NT/2 (for even NT, k = NT/2 only for
+// A < NT/2, so each unordered tile pair is visited once) and with itself (k = 0, ordered, self-masked).
+// Multi-GPU: rank r of R owns the ring offsets k = r, r+R, r+2R, ... ("pair sharding"); every rank then
+// holds a partial acceleration for ALL bodies and the host sums them with one reduce-scatter.
+// A work item is (A, segment of the rank's offset list); a persistent grid walks the items round-robin.
 //
 // Inside a CTA (4 warps): every lane keeps T bodies of A stationary in registers (positions, weights,
 // accumulators).  The B tile arrives in shared memory by TMA bulk copies (2-stage ring).  It is cut
 // into sets of 32*U bodies; a warp loads one set (U bodies per lane) and passes it around the warp
 // with shuffles: 32 ring steps visit all (32T) x (32U) pairs, the B-side accumulators travel with the
 // bodies.  The four warps' B-side sums of a set are added in a fixed order through shared memory and
-// written to the partial slot of ring offset k; the A-side sums go to the slot of the item's segment.
-// sym_reduce_kernel adds all slots of a body in ascending slot order -> bit-reproducible.
+// written to the partial slot of that ring offset; the A-side sums go to the slot of the item's
+// segment.  sym_reduce_kernel adds all slots of a body in ascending slot order -> bit-reproducible.
 #include "nbx_internal.cuh"
 
 namespace nbx {
@@ -24,12 +26,13 @@ namespace nbx {
 struct SymParams {
     const double *x, *y, *z, *w;
     int n, npad;
-    int NT, K, S;          // tiles, ring offsets 1..K, segments of the offset range [0..K]
-    int seg_len;           // offsets per segment (over the K+1 offsets 0..K)
-    double *part;          // [(S + K)][3][npad]
+    int NT, K;             // tiles; largest ring offset
+    int kr0, kstride, M;   // this rank's offsets k(m) = kr0 + m * kstride, m = 0..M-1
+    int S, seg_len;        // segments of the local offset list
+    double *part;          // [(S + M)][3][npad]: A-side slots per segment, then B-side slots per local offset
 };
 
-template <int T, int U, bool UNIFORM, bool DIAG>
+template <int T, int U, bool UNIFORM, bool DIAG, int UNR>
 __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&ay)[T], const double (&az)[T],
                                           const double (&aw)[T], double (&fx)[T], double (&fy)[T], double (&fz)[T],
                                           double (&bx)[U], double (&by)[U], double (&bz)[U], double (&bw)[U],
@@ -37,7 +40,7 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
                                           int jbase)
 {
     const int src = (lane + 1) & 31;
-#pragma unroll 1
+#pragma unroll(UNR)
     for (int s = 0; s < 32; ++s) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -88,7 +91,13 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
     // after 32 passes every body (and its accumulator) is back in the lane that loaded it
 }
 
-template <int T, int U, bool UNIFORM, int MINB>
+// offset k of tile A is skipped when it would visit a tile pair twice (even NT, k = NT/2, upper half)
+__host__ __device__ __forceinline__ bool sym_live(int k, int A, int NT, int K)
+{
+    return !((NT & 1) == 0 && k == K && K > 0 && A >= K);
+}
+
+template <int T, int U, bool UNIFORM, int MINB, int UNR>
 __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
 {
     constexpr int TS = 128 * T;       // bodies per tile
@@ -112,8 +121,8 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     const int nitems = p.NT * p.S;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int A = item / p.S, seg = item - A * p.S;
-        const int k0 = seg * p.seg_len;
-        const int k1 = min(k0 + p.seg_len, p.K + 1);
+        const int m0 = seg * p.seg_len;
+        const int m1 = min(m0 + p.seg_len, p.M);
         const int A0 = A * TS;
 
         double ax[T], ay[T], az[T], aw[T], fx[T], fy[T], fz[T];
@@ -125,10 +134,9 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             fx[t] = fy[t] = fz[t] = 0.0;
         }
 
-        // offsets of this item that really exist (k = K is owned by the lower half of the tiles)
-        auto live = [&](int k) { return !(k == p.K && A >= p.K && p.K > 0) && !(k > 0 && p.NT == 1); };
-        auto issue = [&](int k, int st) {
-            const int B0 = ((A + k) % p.NT) * TS;
+        auto kof = [&](int m) { return p.kr0 + m * p.kstride; };
+        auto issue = [&](int m, int st) {
+            const int B0 = ((A + kof(m)) % p.NT) * TS;
             double *dst = ring + (size_t)st * 4 * TS;
             mbar_expect_tx(&full[st], STAGE_BYTES);
             bulk_g2s(dst, p.x + B0, TS * sizeof(double), &full[st]);
@@ -136,17 +144,18 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             bulk_g2s(dst + 2 * TS, p.z + B0, TS * sizeof(double), &full[st]);
             bulk_g2s(dst + 3 * TS, p.w + B0, TS * sizeof(double), &full[st]);
         };
-        auto next_live = [&](int k) { while (k < k1 && !live(k)) ++k; return k; };
+        auto next_live = [&](int m) { while (m < m1 && !sym_live(kof(m), A, p.NT, p.K)) ++m; return m; };
 
-        int k = next_live(k0);
+        int m = next_live(m0);
         int st = 0;
-        if (tid == 0 && k < k1) issue(k, 0);
-        while (k < k1) {
-            const int kn = next_live(k + 1);
-            if (tid == 0 && kn < k1) issue(kn, st ^ 1); // stage st^1 was released by the barrier that ended block k-1
+        if (tid == 0 && m < m1) issue(m, 0);
+        while (m < m1) {
+            const int mn = next_live(m + 1);
+            if (tid == 0 && mn < m1) issue(mn, st ^ 1); // stage st^1 was released by the barrier that ended the previous block
             mbar_wait(&full[st], (parity >> st) & 1u);
             parity ^= 1u << st;
             const double *bsx = ring + (size_t)st * 4 * TS, *bsy = bsx + TS, *bsz = bsy + TS, *bsw = bsz + TS;
+            const int k = kof(m);
             const int B0 = ((A + k) % p.NT) * TS;
             const int ibase = A0 + warp * (32 * T);
             for (int set = 0; set < NSET; ++set) {
@@ -159,12 +168,12 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
                     gx[u] = gy[u] = gz[u] = 0.0;
                 }
                 if (k == 0) {
-                    ring_pass<T, U, UNIFORM, true>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
-                                                   B0 + set * SET);
+                    ring_pass<T, U, UNIFORM, true, 1>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
+                                                      B0 + set * SET);
                 } else {
-                    ring_pass<T, U, UNIFORM, false>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
-                                                    B0 + set * SET);
-                    // B-side sums of the four warps, added in warp order, go to the slot of ring offset k
+                    ring_pass<T, U, UNIFORM, false, UNR>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane,
+                                                         ibase, B0 + set * SET);
+                    // B-side sums of the four warps, added in warp order, go to the slot of this ring offset
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         red[(warp * 3 + 0) * SET + u * 32 + lane] = gx[u];
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
                         red[(warp * 3 + 2) * SET + u * 32 + lane] = gz[u];
                     }
                     __syncthreads();
-                    double *slot = p.part + (size_t)(p.S + k - 1) * 3 * p.npad;
+                    double *slot = p.part + (size_t)(p.S + m) * 3 * p.npad;
                     for (int e = tid; e < 3 * SET; e += 128) {
                         const int c = e / SET, o = e - c * SET;
                         const double s = ((red[(0 * 3 + c) * SET + o] + red[(1 * 3 + c) * SET + o]) +
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             }
             __syncthreads(); // all warps are done with stage st
             st ^= 1;
-            k = kn;
+            m = mn;
         }
 
         double *slot = p.part + (size_t)seg * 3 * p.npad;
@@ -198,21 +207,27 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     }
 }
 
-// acc_i (+)= f_i * sum over slots, ascending.  B-side slot K exists only for tiles >= K.
-__global__ void sym_reduce_kernel(const double *__restrict__ part, int npad, int n, int S, int K, int TS, int kind,
-                                  double scale, const double *__restrict__ mass, const double *__restrict__ charge,
-                                  double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az,
-                                  int accumulate)
+// acc_i (+)= f_i * (A-side slots in segment order, then the B-side slots of the offsets that reached body i)
+__global__ void sym_reduce_kernel(const SymParams p, int TS, int kind, double scale, const double *__restrict__ mass,
+                                  const double *__restrict__ charge, double *__restrict__ ax, double *__restrict__ ay,
+                                  double *__restrict__ az, int accumulate)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= p.n) return;
     const int tile = i / TS;
-    int nslots = S + K;
-    if (K > 0 && tile < K) nslots -= 1;
+    const size_t np = (size_t)p.npad;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int sl = 0; sl < nslots; ++sl) {
-        const double *b = part + (size_t)sl * 3 * npad;
-        s0 += b[i]; s1 += b[(size_t)npad + i]; s2 += b[2 * (size_t)npad + i];
+    for (int sl = 0; sl < p.S; ++sl) {
+        const double *b = p.part + (size_t)sl * 3 * np;
+        s0 += b[i]; s1 += b[np + i]; s2 += b[2 * np + i];
+    }
+    for (int m = 0; m < p.M; ++m) {
+        const int k = p.kr0 + m * p.kstride;
+        if (k == 0) continue;                                       // the diagonal block has no B side
+        const int A = (tile - k % p.NT + p.NT) % p.NT;               // the tile that visited us at this offset
+        if (!sym_live(k, A, p.NT, p.K)) continue;
+        const double *b = p.part + (size_t)(p.S + m) * 3 * np;
+        s0 += b[i]; s1 += b[np + i]; s2 += b[2 * np + i];
     }
     double f = scale;
     if (kind == 1) f = scale * charge[i] / mass[i];
@@ -220,7 +235,7 @@ __global__ void sym_reduce_kernel(const double *__restrict__ part, int npad, int
     else { ax[i] = f * s0; ay[i] = f * s1; az[i] = f * s2; }
 }
 
-template <int T, int U, bool UNIFORM, int MINB>
+template <int T, int U, bool UNIFORM, int MINB, int UNR>
 static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, double scale, double *acc_out,
                    bool accumulate)
 {
@@ -230,15 +245,18 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
     p.n = (int)c->n; p.npad = (int)c->npad;
     p.NT = p.npad / TS;
     p.K = p.NT / 2;
+    p.kr0 = c->pair_rank;
+    p.kstride = c->pair_nranks;
+    p.M = p.kr0 <= p.K ? (p.K - p.kr0) / p.kstride + 1 : 0;
     const int grid_full = c->sm_count * MINB;
     // enough items for a balanced static round-robin (>= ~24 per CTA), at least 2 offsets per segment
     int S = (24 * grid_full + p.NT - 1) / p.NT;
-    const int max_S = (p.K + 1 + 1) / 2;
+    const int max_S = (p.M + 1) / 2;
     if (S > max_S) S = max_S;
     if (S < 1) S = 1;
-    p.seg_len = (p.K + 1 + S - 1) / S;
-    p.S = (p.K + 1 + p.seg_len - 1) / p.seg_len;
-    const size_t bytes = (size_t)(p.S + p.K) * 3 * p.npad * sizeof(double);
+    p.seg_len = p.M > 0 ? (p.M + S - 1) / S : 1;
+    p.S = p.M > 0 ? (p.M + p.seg_len - 1) / p.seg_len : 1;
+    const size_t bytes = (size_t)(p.S + p.M) * 3 * p.npad * sizeof(double);
     if (bytes > c->part_bytes) {
         if (c->part) { cudaFree(c->part); c->part = nullptr; c->part_bytes = 0; }
         cudaError_t e = cudaMalloc((void **)&c->part, bytes);
@@ -246,7 +264,7 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
         c->part_bytes = bytes;
     }
     p.part = c->part;
-    auto kern = sym_kernel<T, U, UNIFORM, MINB>;
+    auto kern = sym_kernel<T, U, UNIFORM, MINB, UNR>;
     const size_t smem = (size_t)(2 * 4 * TS + 4 * 3 * SET) * sizeof(double);
     const void *key = reinterpret_cast<const void *>(kern);
     bool done = false;
@@ -265,19 +283,34 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
     c->last_nchunk = p.S;
     double f = scale;
     if (UNIFORM) f *= wval;
-    sym_reduce_kernel<<<(p.n + 255) / 256, 256, 0, c->stream>>>(c->part, p.npad, p.n, p.S, p.K, TS, scale_kind, f, c->mass,
-                                                               c->charge, acc_out, acc_out + c->npad,
-                                                               acc_out + 2 * c->npad, accumulate ? 1 : 0);
+    sym_reduce_kernel<<<(p.n + 255) / 256, 256, 0, c->stream>>>(p, TS, scale_kind, f, c->mass, c->charge, acc_out,
+                                                               acc_out + c->npad, acc_out + 2 * c->npad,
+                                                               accumulate ? 1 : 0);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
 }
 
-// Whole-system (unsharded) evaluation; uniform = all weights equal to wval.
+// Evaluates this rank's share of the unordered pairs (everything when pair_nranks == 1) and writes /
+// accumulates the (partial) accelerations of ALL n bodies.  uniform = all weights equal to wval.
 int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int scale_kind, double scale,
                     double *acc_out, bool accumulate)
 {
-    if (uniform) return run_sym<4, 4, true, 3>(c, w, wval, scale_kind, scale, acc_out, accumulate);
-    return run_sym<4, 4, false, 3>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    // variants (option "sym_variant"): T stationary and U travelling bodies per lane, CTAs per SM, ring unroll.
+    // Measured on the 262,144-body sphere (r01): <8,2,2,2> 44.6 ms, <4,4,3,2> 46.6 ms, <4,4,3,1> 49.2 ms.
+    switch (c->opt_sym_variant) {
+    case 1:
+        if (uniform) return run_sym<4, 4, true, 3, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<4, 4, false, 3, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 2:
+        if (uniform) return run_sym<8, 2, true, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 2, false, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 3:
+        if (uniform) return run_sym<8, 1, true, 3, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 1, false, 3, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    default:
+        if (uniform) return run_sym<8, 2, true, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 2, false, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    }
 }
 
 } // namespace nbx

@@ -1,17 +1,26 @@
 """Multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
 
 The reference is strictly serial; the data-parallel axis is the target-particle
-index ``i`` of ``soode_system!`` (src/nbody_to_ode.jl:475).  Rank r evaluates the target columns
-[lo_r, hi_r) against ALL sources, so one velocity-Verlet step needs exactly one exchange: the
-all-gather of the freshly updated positions (24 B per particle), plus an 8-byte all-reduce of
-sum m v^2 when a thermostat needs the global temperature.
+index ``i`` of ``soode_system!`` (src/nbody_to_ode.jl:475).  Two decompositions:
+
+* ``mode="targets"`` (any potential): rank r evaluates the target columns [lo_r, hi_r) against ALL
+  sources.  One exchange per velocity-Verlet step: the all-gather of the updated positions (24 B per
+  particle).
+* ``mode="pairs"`` (unbounded gravity / Coulomb): the unordered pair set is split over the ranks
+  (Newton's-third-law kernel, ring offsets k = rank mod world), every rank ends up with a partial
+  acceleration of ALL particles, and a reduce-scatter of the acceleration rows (24 B per particle)
+  completes the own block.  Two exchanges per step, 1.6x less arithmetic.
+
+Both add an 8-byte all-reduce of sum m v^2 when a thermostat needs the global temperature.
 
 The plumbing works on an *engine* (duck-typed):
     engine.n                       particle columns
-    engine.shard(lo, hi)           restrict the engine to its targets
+    engine.shard(lo, hi)           restrict the engine to the columns it integrates
+    engine.shard_pairs(rank, world)  (pairs mode) select the engine's share of the pair set
     engine.pos_rows()  -> tensor   (3, ld) view of the SoA position rows (device memory, no copy)
+    engine.acc_rows()  -> tensor   (3, ld) view of the SoA acceleration rows after vv_forces
     engine.scalars()   -> tensor   (16,) view of the scalar block ([0] = shard's sum m v^2)
-    engine.vv_begin(dt) / engine.vv_finish(dt) / engine.needs_temperature
+    engine.vv_begin(dt) / engine.vv_forces() / engine.vv_finish(dt) / engine.needs_temperature
 ``CudaEngine`` wraps a libnbody_b200 context; the CPU tests drive the same plumbing over gloo with a
 NumPy engine (tests/test_parallel_gloo.py).
 """
@@ -43,24 +52,34 @@ class CudaEngine:
         # run the library on torch's current stream so NCCL calls issued by torch are ordered with it
         # (torch's default stream has handle 0 == "own stream" in the C ABI; 0x1 is cudaStreamLegacy)
         ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
+        self._views = {}
 
     def _view(self, which, shape):
         import torch
 
         ptr, ld = self.ctx.device_ptr(which)
-        shape = tuple(ld if s is None else s for s in shape)
+        key = (which, ptr)
+        if key not in self._views:
+            shape = tuple(ld if s is None else s for s in shape)
 
-        class _Raw:
-            __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
-                                        "strides": None}
+            class _Raw:
+                __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                            "strides": None}
 
-        return torch.as_tensor(_Raw(), device=self.device)
+            self._views[key] = torch.as_tensor(_Raw(), device=self.device)
+        return self._views[key]
 
     def shard(self, lo, hi):
         self.ctx.shard(lo, hi)
 
+    def shard_pairs(self, rank, world):
+        self.ctx.shard_pairs(rank, world)
+
     def pos_rows(self):
         return self._view(0, (3, None))
+
+    def acc_rows(self):
+        return self._view(2, (3, None))  # acc and acc_old swap every step: looked up by pointer each time
 
     def scalars(self):
         return self._view(3, (16,))
@@ -68,24 +87,33 @@ class CudaEngine:
     def vv_begin(self, dt):
         self.ctx.vv_begin(dt)
 
+    def vv_forces(self):
+        self.ctx.vv_forces()
+
     def vv_finish(self, dt):
         self.ctx.vv_finish(dt)
 
 
 class ShardedStepper:
-    """Velocity Verlet over a process group: x-update of the own shard, all-gather, forces + v-update."""
+    """Velocity Verlet over a process group (see the module docstring for the two modes)."""
 
-    def __init__(self, engine, group=None, multiple: int = 1):
+    def __init__(self, engine, group=None, multiple: int = 1, mode: str = "targets"):
         import torch.distributed as dist
 
+        if mode not in ("targets", "pairs"):
+            raise ValueError(mode)
         self.dist = dist
         self.engine = engine
         self.group = group
+        self.mode = mode
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.lo, self.hi, self.per = partition(engine.n, self.world, self.rank, multiple)
         engine.shard(self.lo, self.hi)
+        if mode == "pairs":
+            engine.shard_pairs(self.rank, self.world)
         self.even = self.per * self.world == engine.n
+        self.backend = dist.get_backend(group)
         self._tmp = None
 
     def _all_gather_positions(self):
@@ -114,10 +142,28 @@ class ShardedStepper:
             if hi > lo and r != self.rank:
                 rows[:, lo:hi] = recv[r, :, :hi - lo]
 
+    def _sum_partial_accelerations(self):
+        """pairs mode: acc rows hold this rank's partial sums for ALL particles -> the own block gets the
+        sum over ranks (reduce-scatter in place on NCCL with equal blocks, all-reduce otherwise)."""
+        rows = self.engine.acc_rows()
+        n, dist = self.engine.n, self.dist
+        if self.world == 1:
+            return
+        if self.even and self.backend == "nccl":
+            for d in range(3):
+                dist.reduce_scatter_tensor(rows[d, self.lo:self.hi], rows[d, :n], op=dist.ReduceOp.SUM,
+                                           group=self.group)
+        else:
+            for d in range(3):
+                dist.all_reduce(rows[d, :n], op=dist.ReduceOp.SUM, group=self.group)
+
     def step(self, dt: float, nsteps: int = 1):
         for _ in range(nsteps):
             self.engine.vv_begin(dt)
             self._all_gather_positions()
+            self.engine.vv_forces()
+            if self.mode == "pairs":
+                self._sum_partial_accelerations()
             self.engine.vv_finish(dt)
             if self.engine.needs_temperature and self.world > 1:
                 s = self.engine.scalars()
