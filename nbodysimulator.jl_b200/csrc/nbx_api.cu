@@ -117,7 +117,7 @@ int compute_pairs(nbx_ctx *c)
             NBX_CUDA(c, cudaGetLastError());
             NBX_TRY(cells_plan(c, c->lj_R, nmol, &c->cl_lj.grid));
             if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nmol, c->opad));
+                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nmol, c->opad, 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, mlo, mhi, 3, c->oacc, c->opad, false));
             } else {
                 NBX_TRY(launch_allpairs_pbc(c, 0, c->opos, nmol, c->opad, mlo, mhi, 3, c->oacc, c->opad, false));
@@ -130,7 +130,7 @@ int compute_pairs(nbx_ctx *c)
         } else {
             NBX_TRY(cells_plan(c, c->lj_R, c->n, &c->cl_lj.grid));
             if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->n, c->npad));
+                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->n, c->npad, 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, true));
             } else {
                 NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));
@@ -145,7 +145,7 @@ int compute_pairs(nbx_ctx *c)
         } else {
             NBX_TRY(cells_plan(c, c->el_R, c->n, &c->cl_el.grid));
             if (c->cl_el.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->n, c->npad));
+                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->n, c->npad, c->water ? 3 : 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, true));
             } else {
                 NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));

@@ -12,7 +12,17 @@
 //
 // Rebuild: cell id + histogram (atomics) -> exclusive scan -> scatter -> per-cell sort by particle
 // index (makes the order, hence every sum, deterministic) -> gather positions into cell order.
+//
+// Pair kernel (cell_pairs2_kernel): one lane per target.  Phase 1 scans the 27 surrounding cells
+// (9 x-rows, each one contiguous slot range plus at most one periodic wrap-around cell) with an fp32
+// distance test on wrapped coordinates in cell units; the threshold carries a margin that covers the
+// fp32 error, so it can only ever over-accept.  Survivors (about 15 % of the candidates in a liquid)
+// go to a per-lane queue in shared memory.  Phase 2 drains the queues in lock step: the reference's
+// exact fp64 predicate decides, and the force is evaluated only there.
 #include "nbx_internal.cuh"
+
+#include <cmath>
+#include <cstring>
 
 namespace nbx {
 
@@ -45,12 +55,17 @@ int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g)
 // ------------------------------------------------------------------------------------------------
 // rebuild kernels
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_coord(double x, double L, int nc)
+// binning copy of a coordinate, wrapped into [0, L) (cf. src/nbody_simulation_result.jl:571)
+__device__ __forceinline__ double wrapped_coord(double x, double L)
 {
     double w = x - L * floor(x / L);
     if (w < 0.0) w += L;
     if (w >= L) w -= L;
-    int cx = (int)(w * ((double)nc / L));
+    return w;
+}
+__device__ __forceinline__ int cell_coord(double x, double L, int nc)
+{
+    int cx = (int)(wrapped_coord(x, L) * ((double)nc / L));
     return cx < 0 ? 0 : (cx >= nc ? nc - 1 : cx);
 }
 
@@ -171,18 +186,22 @@ __global__ void cell_sort_kernel(const int *__restrict__ start, int ncell, int *
     }
 }
 
+// particle data into cell order: exact coordinates + weight (one 32-byte record per slot), and the fp32
+// prefilter record: wrapped coordinates in cell units [0, nc) + the exclusion key (particle index, or
+// molecule index = i / 3 for the own-molecule exclusion of src/nbody_to_ode.jl:331-351)
 __global__ void gather_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ w,
-                              const int *__restrict__ sorted_idx, const int *__restrict__ cell_of, int n,
-                              double *__restrict__ spos, int64_t sld, double *__restrict__ sw,
+                              const int *__restrict__ sorted_idx, const int *__restrict__ cell_of, int n, double L,
+                              int nc, int key_div, double4 *__restrict__ sp4, float4 *__restrict__ sl4,
                               int *__restrict__ scell)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int i = sorted_idx[k];
-    spos[k] = px[i];
-    spos[sld + k] = px[ld + i];
-    spos[2 * sld + k] = px[2 * ld + i];
-    if (w) sw[k] = w[i];
+    const double x = px[i], y = px[ld + i], z = px[2 * ld + i];
+    sp4[k] = make_double4(x, y, z, w ? w[i] : 0.0);
+    const double s = (double)nc / L;
+    sl4[k] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
+                         (float)(wrapped_coord(z, L) * s), __int_as_float(i / key_div));
     scell[k] = cell_of[i];
 }
 
@@ -193,10 +212,9 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
         NBX_TRY(dev_alloc(c, &cl->cell_of, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sorted_idx, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->scell, (size_t)np));
-        NBX_TRY(dev_alloc(c, &cl->spos, (size_t)3 * np));
-        NBX_TRY(dev_alloc(c, &cl->sw, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->sp4, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->sl4, (size_t)np));
         cl->cap_n = np;
-        cl->sld = np;
     }
     if (ncell > cl->cap_cells) {
         const int64_t nb = (ncell + kScanBlock - 1) / kScanBlock;
@@ -211,7 +229,7 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
 
 // Rebuild cl for the n particles of the SoA rows px (stride ld); w = optional per-particle weight
 // (charge) carried into cell order.
-int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld)
+int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld, int key_div)
 {
     const CellGrid &g = cl->grid;
     if (!g.valid) return fail(c, NBX_ERR_INVALID, "cells_build without a valid grid");
@@ -228,8 +246,8 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int
     scan_total_kernel<<<1, 32, 0, c->stream>>>(cl->start, ncell, cl->sums, nb);
     scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, ni, cl->start, cl->fill, cl->sorted_idx);
     cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, c->stream>>>(cl->start, ncell, cl->sorted_idx);
-    gather_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, cl->cell_of, ni, cl->spos,
-                                                          cl->sld, cl->sw, cl->scell);
+    gather_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, cl->cell_of, ni, g.len[0],
+                                                          g.nc[0], key_div, cl->sp4, cl->sl4, cl->scell);
     timer_end(c, NBX_T_CELL_BUILD);
     NBX_CUDA(c, cudaGetLastError());
     cl->n = n;
@@ -240,10 +258,13 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int
 // pair kernel: one thread per target (cell order), 27 neighbour cells, exact reference predicate
 // ------------------------------------------------------------------------------------------------
 struct CellPairArgs {
-    const double *sx, *sy, *sz, *sw;
+    const double4 *sp4;
+    const float4 *sl4;
     const int *sorted_idx, *scell, *start;
     int n, nc;
     double L, radius, R2, sigma2;
+    float R2f;     // prefilter threshold on the fp32 squared distance in cell units (margin included)
+    int hi_radius; // high word of `radius`: |x| with a smaller high word needs no wrapping
 };
 
 template <int POT, int EXCL, int MODE>
@@ -269,7 +290,8 @@ __device__ __forceinline__ void cell_pair_visit(const CellPairArgs &a, int k, do
                     const int j = a.sorted_idx[m];
                     const bool excl = EXCL == 0 ? (j == i) : ((j / 3) == (i / 3));
                     if (excl) continue;
-                    double rx = __dsub_rn(xi, a.sx[m]), ry = __dsub_rn(yi, a.sy[m]), rz = __dsub_rn(zi, a.sz[m]);
+                    const double4 pj = a.sp4[m];
+                    double rx = __dsub_rn(xi, pj.x), ry = __dsub_rn(yi, pj.y), rz = __dsub_rn(zi, pj.z);
                     rx = wrap_cubic(rx, a.radius, a.L);
                     ry = wrap_cubic(ry, a.radius, a.L);
                     rz = wrap_cubic(rz, a.radius, a.L);
@@ -284,7 +306,7 @@ __device__ __forceinline__ void cell_pair_visit(const CellPairArgs &a, int k, do
                                 const double s12 = s6 * s6;
                                 f = (2.0 * s12 - s6) * inv;
                             } else {
-                                f = w_rinv3(r2, a.sw[m]);
+                                f = w_rinv3(r2, pj.w);
                             }
                             f0 = fma(f, rx, f0);
                             f1 = fma(f, ry, f1);
@@ -313,7 +335,8 @@ __global__ void __launch_bounds__(128) cell_force_kernel(const CellPairArgs a, d
     if (i < lo || i >= hi) return;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
     int cnt = 0;
-    cell_pair_visit<POT, EXCL, 0>(a, k, a.sx[k], a.sy[k], a.sz[k], i, a.scell[k], f0, f1, f2, cnt, nullptr);
+    const double4 pi = a.sp4[k];
+    cell_pair_visit<POT, EXCL, 0>(a, k, pi.x, pi.y, pi.z, i, a.scell[k], f0, f1, f2, cnt, nullptr);
     double coeff = scale / mass[(size_t)i * mstride];
     if (POT == 1) coeff *= charge[i];
     if (accumulate) {
@@ -334,7 +357,8 @@ __global__ void __launch_bounds__(128) cell_neigh_kernel(const CellPairArgs a, i
     double f0 = 0, f1 = 0, f2 = 0;
     int cnt = 0;
     int32_t *mine = MODE == 2 ? list + offsets[i] : nullptr;
-    cell_pair_visit<0, EXCL, MODE>(a, k, a.sx[k], a.sy[k], a.sz[k], i, a.scell[k], f0, f1, f2, cnt, mine);
+    const double4 pi = a.sp4[k];
+    cell_pair_visit<0, EXCL, MODE>(a, k, pi.x, pi.y, pi.z, i, a.scell[k], f0, f1, f2, cnt, mine);
     if (MODE == 1) counts[i] = cnt;
     if (MODE == 2) { // ascending partner order, as the reference's j loop visits them
         for (int p = 1; p < cnt; ++p) {
@@ -346,13 +370,185 @@ __global__ void __launch_bounds__(128) cell_neigh_kernel(const CellPairArgs a, i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pair kernel v2: fp32 prefilter -> per-lane survivor queue -> exact fp64 predicate + force
+// ------------------------------------------------------------------------------------------------
+constexpr int kQCap = 32; // survivors a lane can hold before the warp drains its queues
+
+// 1/x to < 1 ulp-ish (error e^3, e = seed error ~2^-22) without the IEEE division's slow path
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y0, p, y0);
+}
+
+// MODE 0: accelerations; 1: in-cutoff partner counts; 2: partner lists (CSR via offsets)
+// POT 0: Lennard-Jones (src/basic_potentials.jl:253-266); 1: Coulomb (:288-297).  The exclusion (self, or own
+// molecule) is the key stored in sl4[].w.
+template <int POT, int MODE>
+__global__ void __launch_bounds__(128) cell_pairs2_kernel(const CellPairArgs a, double scale,
+                                                          const double *__restrict__ mass, int mstride,
+                                                          const double *__restrict__ charge, int lo, int hi,
+                                                          double *__restrict__ acc, int64_t ld, int accumulate,
+                                                          int *__restrict__ counts, const int64_t *__restrict__ offsets,
+                                                          int32_t *__restrict__ list)
+{
+    __shared__ int q[kQCap * 128];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int k = blockIdx.x * 128 + tid;
+    const int kk = k < a.n ? k : a.n - 1;
+    const float4 me = a.sl4[kk];
+    const int key = __float_as_int(me.w);
+    const int i = a.sorted_idx[kk];
+    const bool live = k < a.n && i >= lo && i < hi;
+    const double4 pi = a.sp4[kk];
+    const int cid = a.scell[kk];
+    const int nc = a.nc;
+    const int cx = cid % nc, cy = (cid / nc) % nc, cz = cid / (nc * nc);
+    const float fnc = (float)nc;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    int cnt = 0, found = 0;
+    int32_t *mine = (MODE == 2 && live) ? list + offsets[i] : nullptr;
+
+    // phase 2: every lane drains its own queue; the reference's predicate decides
+    auto pair = [&](const double4 pj, int m) {
+        double rx = __dsub_rn(pi.x, pj.x), ry = __dsub_rn(pi.y, pj.y), rz = __dsub_rn(pi.z, pj.z);
+        const int hx = __double2hiint(rx) & 0x7fffffff, hy = __double2hiint(ry) & 0x7fffffff,
+                  hz = __double2hiint(rz) & 0x7fffffff;
+        if (max(hx, max(hy, hz)) >= a.hi_radius) { // rare: the pair straddles a periodic face
+            rx = wrap_cubic(rx, a.radius, a.L);
+            ry = wrap_cubic(ry, a.radius, a.L);
+            rz = wrap_cubic(rz, a.radius, a.L);
+        }
+        const double r2 = r2_unfused(rx, ry, rz);
+        // r2 >= 0 and R2 > 0: IEEE order == order of the bit patterns (keeps the test off the FP64 pipe)
+        if (__double_as_longlong(r2) < __double_as_longlong(a.R2)) {
+            if (MODE == 0) {
+                double f;
+                if (POT == 0) {
+                    const double inv = rcp_fast(r2);
+                    const double qq = a.sigma2 * inv;
+                    const double s6 = qq * qq * qq;
+                    f = (s6 * inv) * fma(2.0, s6, -1.0); // (2 s12 - s6) / r2
+                } else {
+                    f = w_rinv3(r2, pj.w);
+                }
+                f0 = fma(f, rx, f0);
+                f1 = fma(f, ry, f1);
+                f2 = fma(f, rz, f2);
+            } else {
+                if (MODE == 2) mine[found] = a.sorted_idx[m];
+                ++found;
+            }
+        }
+    };
+    auto flush = [&]() {
+        const int wmax = __reduce_max_sync(FULL, cnt);
+        for (int s = 0; s < wmax; s += 2) { // two gathers in flight per lane
+            const bool v0 = s < cnt, v1 = s + 1 < cnt;
+            const int m0 = v0 ? q[s * 128 + tid] : kk, m1 = v1 ? q[(s + 1) * 128 + tid] : kk;
+            const double4 p0 = a.sp4[m0], p1 = a.sp4[m1];
+            if (v0) pair(p0, m0);
+            if (v1) pair(p1, m1);
+        }
+        cnt = 0;
+    };
+
+    // phase 1: fp32 test of the slots [b, e) against the (shifted) target
+    auto test = [&](const float4 cj, int m, float tx, float ty, float tz) {
+        const float dx = tx - cj.x, dy = ty - cj.y, dz = tz - cj.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (r2 < a.R2f && __float_as_int(cj.w) != key) {
+            q[cnt * 128 + tid] = m;
+            ++cnt;
+        }
+    };
+    auto scan = [&](int b, int e, float tx, float ty, float tz) {
+        int m = b;
+        for (;;) {
+            // four records in flight per lane: the loop is bound by load latency, not by arithmetic
+            while (m + 4 <= e && cnt <= kQCap - 4) {
+                const float4 c0 = __ldg(&a.sl4[m]), c1 = __ldg(&a.sl4[m + 1]), c2 = __ldg(&a.sl4[m + 2]),
+                             c3 = __ldg(&a.sl4[m + 3]);
+                test(c0, m, tx, ty, tz);
+                test(c1, m + 1, tx, ty, tz);
+                test(c2, m + 2, tx, ty, tz);
+                test(c3, m + 3, tx, ty, tz);
+                m += 4;
+            }
+            while (m < e && e - m < 4 && cnt < kQCap) {
+                test(__ldg(&a.sl4[m]), m, tx, ty, tz);
+                ++m;
+            }
+            if (!__any_sync(FULL, m < e)) break;
+            flush(); // some lane's queue is (nearly) full
+        }
+    };
+
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int dz = r / 3 - 1, dy = r - (r / 3) * 3 - 1;
+        int z = cz + dz, y = cy + dy;
+        float tz = me.z, ty = me.y;
+        // a neighbour cell reached through a periodic face holds the image w_j -+ nc of its particles
+        if (z < 0) { z += nc; tz += fnc; } else if (z >= nc) { z -= nc; tz -= fnc; }
+        if (y < 0) { y += nc; ty += fnc; } else if (y >= nc) { y -= nc; ty -= fnc; }
+        const int row = (z * nc + y) * nc;
+        const int xa = cx > 0 ? cx - 1 : 0, xb = cx < nc - 1 ? cx + 1 : nc - 1;
+        int b = a.start[row + xa], e = a.start[row + xb + 1];
+        if (!live) e = b;
+        scan(b, e, me.x, ty, tz);
+        int b2 = 0, e2 = 0;
+        float tx = me.x;
+        if (cx == 0) { b2 = a.start[row + nc - 1]; e2 = a.start[row + nc]; tx += fnc; }
+        else if (cx == nc - 1) { b2 = a.start[row]; e2 = a.start[row + 1]; tx -= fnc; }
+        if (!live) e2 = b2;
+        if (__any_sync(FULL, e2 > b2)) scan(b2, e2, tx, ty, tz);
+    }
+    flush();
+
+    if (!live) return;
+    if (MODE == 0) {
+        double coeff = scale / mass[(size_t)i * mstride];
+        if (POT == 1) coeff *= charge[i];
+        if (accumulate) {
+            acc[i] += coeff * f0; acc[ld + i] += coeff * f1; acc[2 * ld + i] += coeff * f2;
+        } else {
+            acc[i] = coeff * f0; acc[ld + i] = coeff * f1; acc[2 * ld + i] = coeff * f2;
+        }
+    } else if (MODE == 1) {
+        counts[i] = found;
+    } else { // ascending partner order, as the reference's j loop visits them
+        for (int p = 1; p < found; ++p) {
+            const int32_t v = mine[p];
+            int m = p - 1;
+            while (m >= 0 && mine[m] > v) { mine[m + 1] = mine[m]; --m; }
+            mine[m + 1] = v;
+        }
+    }
+}
+
 static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
 {
     CellPairArgs a{};
-    a.sx = cl->spos; a.sy = cl->spos + cl->sld; a.sz = cl->spos + 2 * cl->sld; a.sw = cl->sw;
+    a.sp4 = cl->sp4; a.sl4 = cl->sl4;
     a.sorted_idx = cl->sorted_idx; a.scell = cl->scell; a.start = cl->start;
     a.n = (int)cl->n; a.nc = cl->grid.nc[0];
     a.L = c->bc[0]; a.radius = 0.5 * c->bc[0]; a.R2 = R2; a.sigma2 = c->lj_sigma2;
+    // fp32 prefilter: coordinates in cell units lie in [0, nc] (|rounding| <= nc 2^-25 each); a component of
+    // the displacement is off by < 4 nc 2^-24, so for r ~ R <= 1 cell the squared distance is off by
+    // < 2 sqrt(3) * 4 nc 2^-24 + O(2^-22) relative.  The margin doubles that.
+    const double cell = a.L / (double)a.nc;
+    const double margin = 32.0 * (double)a.nc * 5.9604644775390625e-8 + 1e-5;
+    a.R2f = nextafterf((float)(R2 / (cell * cell) * (1.0 + margin)), INFINITY);
+    int64_t bits;
+    memcpy(&bits, &a.radius, sizeof bits);
+    a.hi_radius = (int)(bits >> 32);
     return a;
 }
 
@@ -365,7 +561,18 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
     const int blocks = (n + 127) / 128;
     const int acc_flag = accumulate ? 1 : 0;
     timer_begin(c, NBX_T_PAIR_CELLS);
-    if (pot == 0) {
+    if (c->opt_prefilter) {
+        if (pot == 0) {
+            const CellPairArgs a = make_args(c, cl, c->lj_R2);
+            cell_pairs2_kernel<0, 0><<<blocks, 128, 0, c->stream>>>(a, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
+                                                                  (int)lo, (int)hi, acc_out, ld_out, acc_flag, nullptr,
+                                                                  nullptr, nullptr);
+        } else { // the exclusion (self / own molecule) was fixed when the list was built (key_div)
+            const CellPairArgs a = make_args(c, cl, c->el_R2);
+            cell_pairs2_kernel<1, 0><<<blocks, 128, 0, c->stream>>>(a, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi,
+                                                                  acc_out, ld_out, acc_flag, nullptr, nullptr, nullptr);
+        }
+    } else if (pot == 0) {
         const CellPairArgs a = make_args(c, cl, c->lj_R2);
         cell_force_kernel<0, 0><<<blocks, 128, 0, c->stream>>>(a, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
                                                              (int)lo, (int)hi, acc_out, ld_out, acc_flag);
@@ -430,10 +637,14 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
     double b[6] = {c->bc[0], c->bc[1], c->bc[2], c->bc[3], c->bc[4], c->bc[5]};
     if (c->bc_kind == NBX_BC_CUBIC) b[1] = 0.5 * c->bc[0];
     if (use_cells) {
-        int rc = cells_build(c, cl, px, nullptr, n, ld);
+        int rc = cells_build(c, cl, px, nullptr, n, ld, 1);
         if (rc != NBX_OK) { cudaFree(d_counts); return rc; }
         a = make_args(c, cl, R2);
-        cell_neigh_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, d_counts, nullptr, nullptr);
+        if (c->opt_prefilter)
+            cell_pairs2_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0, d_counts,
+                                                                  nullptr, nullptr);
+        else
+            cell_neigh_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, d_counts, nullptr, nullptr);
     } else {
         brute_neigh_kernel<<<blocks, 128, 0, c->stream>>>(px, ld, ni, c->bc_kind, b[0], b[1], b[2], b[3], b[4], b[5],
                                                          R2, 1, d_counts, nullptr, nullptr);
@@ -455,7 +666,10 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
         if (rc == NBX_OK) rc = dev_alloc(c, &d_list, (size_t)total);
         if (rc == NBX_OK) {
             cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream);
-            if (use_cells)
+            if (use_cells && c->opt_prefilter)
+                cell_pairs2_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0,
+                                                                      d_counts, d_off, d_list);
+            else if (use_cells)
                 cell_neigh_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, d_counts, d_off, d_list);
             else
                 brute_neigh_kernel<<<blocks, 128, 0, c->stream>>>(px, ld, ni, c->bc_kind, b[0], b[1], b[2], b[3], b[4],
@@ -474,7 +688,7 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
 void cells_free(CellList *cl)
 {
     cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->fill); cudaFree(cl->sums);
-    cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->spos); cudaFree(cl->sw);
+    cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->sp4); cudaFree(cl->sl4);
     *cl = CellList{};
 }
 

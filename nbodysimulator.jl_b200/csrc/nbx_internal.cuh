@@ -42,9 +42,8 @@ struct CellList {
     int *sums = nullptr;        // scan block totals
     int *sorted_idx = nullptr;  // [n] particle index of the k-th slot in cell order
     int *scell = nullptr;       // [n] cell id of the k-th slot
-    double *spos = nullptr;     // [3][sld] positions in cell order (unwrapped, as the reference uses them)
-    double *sw = nullptr;       // [sld] weights (charges) in cell order
-    int64_t sld = 0;
+    double4 *sp4 = nullptr;     // [n] cell order: x, y, z unwrapped (as the reference's predicate uses them), w = charge
+    float4 *sl4 = nullptr;      // [n] cell order: wrapped coordinates in cell units (fp32 prefilter), w = exclusion key bits
     int64_t cap_n = 0, cap_cells = 0;
 };
 
@@ -167,7 +166,7 @@ int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_
                         int mstride, double *acc_out, int64_t ld_out, bool accumulate);
 // nbx_cells.cu
 int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g);
-int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld);
+int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld, int key_div);
 int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi, int mstride, double *acc_out,
                        int64_t ld_out, bool accumulate);
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,

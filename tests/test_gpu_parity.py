@@ -259,6 +259,48 @@ def test_lj_neighbor_lists_bit_exact(oracle, drift):
     assert np.array_equal(off, off2) and np.array_equal(lst, lst2)
 
 
+def test_lj_prefilter_never_changes_the_pair_set(oracle):
+    """The fp32 prefilter of the v2 cell kernel only prunes candidates: lists equal those of the exact
+    all-candidates kernel (option prefilter=0), forces agree with the oracle on both paths."""
+    w, u = _fcc(10, 0.08, 21, True)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    ctx = make_context(spec)
+    ctx.upload(u, w["v"])
+    off, lst = ctx.neighbors()
+    ctx.set_option("prefilter", 0)
+    off0, lst0 = ctx.neighbors()
+    a0 = ctx.accel(u)
+    ctx.set_option("prefilter", 1)
+    a = ctx.accel(u)
+    assert np.array_equal(off, off0) and np.array_equal(lst, lst0)
+    _check(a, ref)
+    _check(a0, ref)
+
+
+def test_lj_dense_clusters_overflow_the_survivor_queue(oracle):
+    """More than 64 partners inside the cutoff (the per-lane queue capacity) and cells of very different
+    occupancy: the mid-scan drain path and the 3-cells-per-dimension grid."""
+    rng = np.random.Generator(np.random.Philox(404))
+    L, R = 9.3, 3.0  # nc = 3
+    n = 1500
+    centres = rng.random((3, 6)) * L
+    u = centres[:, rng.integers(0, 6, n)] + 0.9 * rng.standard_normal((3, n))
+    u[:, :300] = rng.random((3, 300)) * L
+    u = F(u)
+    spec = dict(ms=rng.random(n) + 0.5, bc=("cubic", L), lj=dict(eps=0.3, sigma=0.4, R=R))
+    s = make_oracle(oracle, spec)
+    ref = s.rhs(u, np.zeros_like(u), NT)
+    ctx = make_context(spec)
+    ctx.upload(u, np.zeros_like(u))
+    off, lst = ctx.neighbors(cap=n * n)
+    assert ctx.info("cells_lj") == 27
+    assert (np.diff(off) > 64).any()
+    for i in range(0, n, 11):
+        assert np.array_equal(lst[off[i]:off[i + 1]], s.neighbors(u, i, R)), i
+    _check(ctx.accel(u), ref, tol=5e-12)  # near-overlapping pairs: r^-14 terms of both signs cancel
+
+
 def test_lj_pairs_on_the_cutoff_boundary(oracle):
     """Pairs within a few ulp of R: the strict `r2 < R2` decision must match the reference's un-fused fp64."""
     L, R = 10.0, 2.5
