@@ -106,18 +106,26 @@ int compute_pairs(nbx_ctx *c)
         NBX_TRY(zero_rows(c, c->acc, 0, c->n));
     }
     const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
-    if (!pair_mode) NBX_TRY(zero_rows(c, c->acc, lo, hi));
+    // the first potential overwrites its targets' rows; only terms that can but add need zeroed rows
+    bool written = pair_mode;
+    auto acc_flag = [&]() { const bool a = written; written = true; return a; };
+    auto ensure_zero = [&]() -> int {
+        if (!written) NBX_TRY(zero_rows(c, c->acc, lo, hi));
+        written = true;
+        return NBX_OK;
+    };
 
     if (c->has_lj) {
         if (c->water) {
             const int nmol = (int)(c->n / 3);
             const int mlo = (int)((lo + 2) / 3), mhi = (int)((hi + 2) / 3);
+            NBX_TRY(ensure_zero());
             gather_oxygen_kernel<<<(unsigned)((c->opad + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, nmol, c->opos,
                                                                                          c->opad, kFarAway);
             NBX_CUDA(c, cudaGetLastError());
             NBX_TRY(cells_plan(c, c->lj_R, nmol, &c->cl_lj.grid));
             if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nmol, c->opad, 1));
+                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nullptr, nmol, c->opad, 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, mlo, mhi, 3, c->oacc, c->opad, false));
             } else {
                 NBX_TRY(launch_allpairs_pbc(c, 0, c->opos, nmol, c->opad, mlo, mhi, 3, c->oacc, c->opad, false));
@@ -130,10 +138,10 @@ int compute_pairs(nbx_ctx *c)
         } else {
             NBX_TRY(cells_plan(c, c->lj_R, c->n, &c->cl_lj.grid));
             if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->n, c->npad, 1));
-                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, true));
+                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->gid, c->n, c->npad, 1));
+                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, acc_flag()));
             } else {
-                NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));
+                NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, acc_flag()));
             }
         }
     }
@@ -141,20 +149,24 @@ int compute_pairs(nbx_ctx *c)
         const int pot = c->water ? 2 : 1;
         if (!c->water && c->bc_kind == NBX_BC_INFINITE && isinf(c->el_R2)) {
             // F += q_j (ri - rj)/r^3, dv += k q_i / m_i F  ==  -k q_i/m_i * sum q_j (rj - ri)/r^3
-            NBX_TRY(launch_allpairs_grav(c, c->charge, 1, -c->el_k, c->acc, true));
+            NBX_TRY(launch_allpairs_grav(c, c->charge, 1, -c->el_k, c->acc, acc_flag()));
         } else {
             NBX_TRY(cells_plan(c, c->el_R, c->n, &c->cl_el.grid));
             if (c->cl_el.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->n, c->npad, c->water ? 3 : 1));
-                NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, true));
+                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->gid, c->n, c->npad, c->water ? 3 : 1));
+                NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, acc_flag()));
             } else {
-                NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, true));
+                NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, acc_flag()));
             }
         }
     }
-    if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, true));
-    if (c->has_grav) NBX_TRY(launch_allpairs_grav(c, c->mass, 0, c->G, c->acc, true));
-    if (c->has_spcfw) NBX_TRY(launch_spcfw_bonded(c, c->acc));
+    if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, acc_flag()));
+    if (c->has_grav) NBX_TRY(launch_allpairs_grav(c, c->mass, 0, c->G, c->acc, acc_flag()));
+    if (c->has_spcfw) {
+        NBX_TRY(ensure_zero());
+        NBX_TRY(launch_spcfw_bonded(c, c->acc));
+    }
+    NBX_TRY(ensure_zero()); // no potential at all
     return NBX_OK;
 }
 
@@ -581,8 +593,7 @@ int nbx_vv_finish(nbx_ctx *c, double dt)
         NBX_TRY(compute_pairs(c));
     }
     c->forces_done = false;
-    NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel)); // RHS thermostats use v(t) and the temperature of v(t)
-    NBX_TRY(launch_vv_vel(c, dt));
+    NBX_TRY(launch_vv_vel(c, dt, true)); // RHS thermostats use v(t) and the temperature of v(t)
     if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
     return NBX_OK;
 }
@@ -593,13 +604,15 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     NBX_TRY(need_resident(c, "nbx_step_vv"));
     if (c->tgt_lo != 0 || c->tgt_hi != c->n)
         return fail(c, NBX_ERR_INVALID, "nbx_step_vv: sharded context; drive nbx_vv_begin / all-gather / nbx_vv_finish");
+    if (c->pair_nranks > 1)
+        return fail(c, NBX_ERR_INVALID, "nbx_step_vv: pair-sharded context; drive nbx_vv_forces / reduce / nbx_vv_finish");
     if (c->thermo == NBX_THERMO_LANGEVIN)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
     for (int64_t s = 0; s < nsteps; ++s) {
         NBX_TRY(launch_vv_pos(c, dt));
         double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
-        NBX_TRY(compute_accel(c));
-        NBX_TRY(launch_vv_vel(c, dt));
+        NBX_TRY(compute_pairs(c));
+        NBX_TRY(launch_vv_vel(c, dt, true));
         if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
     }
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -10,8 +10,8 @@
 // surrounding cells; binning uses its own wrapped copy x - L floor(x/L)
 // (cf. src/nbody_simulation_result.jl:571), whose rounding (<= 1e-13 L) is far inside the margin.
 //
-// Rebuild: cell id + histogram (atomics) -> exclusive scan -> scatter -> per-cell sort by particle
-// index (makes the order, hence every sum, deterministic) -> gather positions into cell order.
+// Rebuild: cell id + histogram (atomics) -> exclusive scan -> scatter -> rank inside the cell by particle id
+// (makes the order, hence every sum, deterministic) fused with the gather of the records into cell order.
 //
 // Pair kernel (cell_pairs2_kernel): one lane per target.  Phase 1 scans the 27 surrounding cells
 // (9 x-rows, each one contiguous slot range plus at most one periodic wrap-around cell) with an fp32
@@ -70,14 +70,14 @@ __device__ __forceinline__ int cell_coord(double x, double L, int nc)
 }
 
 __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n, double L, int nc,
-                               int *__restrict__ cell_of, int *__restrict__ count)
+                               int *__restrict__ cell_of, int *__restrict__ arrival, int *__restrict__ count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = cell_coord(px[i], L, nc), cy = cell_coord(px[ld + i], L, nc), cz = cell_coord(px[2 * ld + i], L, nc);
     const int cid = (cz * nc + cy) * nc + cx; // x fastest: the three x-neighbours of a cell are contiguous
     cell_of[i] = cid;
-    atomicAdd(&count[cid], 1);
+    arrival[i] = atomicAdd(&count[cid], 1);  // arbitrary but unique slot inside the cell (ordered later)
 }
 
 constexpr int kScanBlock = 1024;
@@ -150,59 +150,54 @@ __global__ void scan_sums_kernel(int *__restrict__ sums, int nb)
     if (threadIdx.x == 0) sums[nb] = carry;
 }
 
-__global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restrict__ sums)
+__global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restrict__ sums, int nb)
 {
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
     if (i < n) out[i] += sums[blockIdx.x];
-    if (i == n - 1 || (n == 0 && i == 0)) { /* total written by the caller kernel below */ }
+    if (i == 0) out[n] = sums[nb]; // grand total closes the CSR
 }
 
-__global__ void scan_total_kernel(int *__restrict__ out, int n, const int *__restrict__ sums, int nb)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) out[n] = sums[nb];
-}
-
-__global__ void scatter_kernel(const int *__restrict__ cell_of, int n, const int *__restrict__ start,
-                               int *__restrict__ fill, int *__restrict__ sorted_idx)
+// slot = cell start + arrival rank (no atomics); the ordering key travels with the index
+__global__ void scatter_kernel(const int *__restrict__ cell_of, const int *__restrict__ arrival,
+                               const int *__restrict__ gid, int n, const int *__restrict__ start,
+                               int *__restrict__ tmp_idx, int *__restrict__ tmp_key)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int cid = cell_of[i];
-    const int slot = start[cid] + atomicAdd(&fill[cid], 1);
-    sorted_idx[slot] = i;
+    const int slot = start[cell_of[i]] + arrival[i];
+    tmp_idx[slot] = i;
+    if (gid) tmp_key[slot] = gid[i];
 }
 
-// one thread per cell: insertion sort of the cell's particle indices (ascending)
-__global__ void cell_sort_kernel(const int *__restrict__ start, int ncell, int *__restrict__ sorted_idx)
-{
-    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cid >= ncell) return;
-    const int b = start[cid], e = start[cid + 1];
-    for (int k = b + 1; k < e; ++k) {
-        const int v = sorted_idx[k];
-        int m = k - 1;
-        while (m >= b && sorted_idx[m] > v) { sorted_idx[m + 1] = sorted_idx[m]; --m; }
-        sorted_idx[m + 1] = v;
-    }
-}
-
-// particle data into cell order: exact coordinates + weight (one 32-byte record per slot), and the fp32
-// prefilter record: wrapped coordinates in cell units [0, nc) + the exclusion key (particle index, or
-// molecule index = i / 3 for the own-molecule exclusion of src/nbody_to_ode.jl:331-351)
-__global__ void gather_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ w,
-                              const int *__restrict__ sorted_idx, const int *__restrict__ cell_of, int n, double L,
-                              int nc, int key_div, double4 *__restrict__ sp4, float4 *__restrict__ sl4,
-                              int *__restrict__ scell)
+// Final slot of a particle = cell start + its rank among the cell's members by key (global particle id, or
+// the local index when the context holds the whole system): the cell order, hence every force sum, is
+// deterministic and independent of how a decomposition numbers its local particles.  The same thread then
+// writes the particle's records in cell order: the exact coordinates + weight (one 32-byte record), and the
+// fp32 prefilter record: wrapped coordinates in cell units [0, nc) + the exclusion key (particle id, or
+// molecule id = id / 3 for the own-molecule exclusion of src/nbody_to_ode.jl:331-351).
+__global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ w,
+                                   const int *__restrict__ tmp_idx, const int *__restrict__ tmp_key,
+                                   const int *__restrict__ cell_of, const int *__restrict__ start, int n, double L,
+                                   int nc, int key_div, int *__restrict__ sorted_idx, double4 *__restrict__ sp4,
+                                   float4 *__restrict__ sl4, int *__restrict__ scell)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const int i = sorted_idx[k];
+    const int i = tmp_idx[k];
+    const int cid = cell_of[i];
+    const int b = start[cid], e = start[cid + 1];
+    const int *keys = tmp_key ? tmp_key : tmp_idx;
+    const int mine = keys[k];
+    int rank = 0;
+    for (int m = b; m < e; ++m) rank += keys[m] < mine ? 1 : 0;
+    const int dst = b + rank;
     const double x = px[i], y = px[ld + i], z = px[2 * ld + i];
-    sp4[k] = make_double4(x, y, z, w ? w[i] : 0.0);
+    sorted_idx[dst] = i;
+    sp4[dst] = make_double4(x, y, z, w ? w[i] : 0.0);
     const double s = (double)nc / L;
-    sl4[k] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
-                         (float)(wrapped_coord(z, L) * s), __int_as_float(i / key_div));
-    scell[k] = cell_of[i];
+    sl4[dst] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
+                           (float)(wrapped_coord(z, L) * s), __int_as_float(mine / key_div));
+    scell[dst] = cid;
 }
 
 static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
@@ -210,6 +205,9 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
     if (n > cl->cap_n) {
         const int64_t np = ((n + kPad - 1) / kPad) * kPad;
         NBX_TRY(dev_alloc(c, &cl->cell_of, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->arrival, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->tmp_idx, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->tmp_key, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sorted_idx, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->scell, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sp4, (size_t)np));
@@ -220,7 +218,6 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
         const int64_t nb = (ncell + kScanBlock - 1) / kScanBlock;
         NBX_TRY(dev_alloc(c, &cl->count, (size_t)ncell + 1));
         NBX_TRY(dev_alloc(c, &cl->start, (size_t)ncell + 1));
-        NBX_TRY(dev_alloc(c, &cl->fill, (size_t)ncell + 1));
         NBX_TRY(dev_alloc(c, &cl->sums, (size_t)nb + 1));
         cl->cap_cells = ncell;
     }
@@ -229,7 +226,8 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
 
 // Rebuild cl for the n particles of the SoA rows px (stride ld); w = optional per-particle weight
 // (charge) carried into cell order.
-int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld, int key_div)
+int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, const int *gid, int64_t n, int64_t ld,
+                int key_div)
 {
     const CellGrid &g = cl->grid;
     if (!g.valid) return fail(c, NBX_ERR_INVALID, "cells_build without a valid grid");
@@ -238,16 +236,16 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int
     const int nb = (ncell + kScanBlock - 1) / kScanBlock;
     timer_begin(c, NBX_T_CELL_BUILD);
     cudaMemsetAsync(cl->count, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
-    cudaMemsetAsync(cl->fill, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
-    cell_id_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->count);
+    cell_id_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
+                                                           cl->count);
     scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums);
     scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb);
-    scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums);
-    scan_total_kernel<<<1, 32, 0, c->stream>>>(cl->start, ncell, cl->sums, nb);
-    scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, ni, cl->start, cl->fill, cl->sorted_idx);
-    cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, c->stream>>>(cl->start, ncell, cl->sorted_idx);
-    gather_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, cl->cell_of, ni, g.len[0],
-                                                          g.nc[0], key_div, cl->sp4, cl->sl4, cl->scell);
+    scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb);
+    scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
+                                                           cl->tmp_key);
+    rank_gather_kernel<<<(ni + 127) / 128, 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
+                                                               cl->cell_of, cl->start, ni, g.len[0], g.nc[0], key_div,
+                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell);
     timer_end(c, NBX_T_CELL_BUILD);
     NBX_CUDA(c, cudaGetLastError());
     cl->n = n;
@@ -386,11 +384,20 @@ __device__ __forceinline__ double rcp_fast(double x)
     return fma(y0, p, y0);
 }
 
+// one 32-byte cell-order record with a single 256-bit load (LDG.E.ENL2.256): half the L1 sector traffic of
+// a 128 + 64 bit pair when every lane gathers a different record
+__device__ __forceinline__ double4 load_rec(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 // MODE 0: accelerations; 1: in-cutoff partner counts; 2: partner lists (CSR via offsets)
 // POT 0: Lennard-Jones (src/basic_potentials.jl:253-266); 1: Coulomb (:288-297).  The exclusion (self, or own
 // molecule) is the key stored in sl4[].w.
 template <int POT, int MODE>
-__global__ void __launch_bounds__(128) cell_pairs2_kernel(const CellPairArgs a, double scale,
+__global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs a, double scale,
                                                           const double *__restrict__ mass, int mstride,
                                                           const double *__restrict__ charge, int lo, int hi,
                                                           double *__restrict__ acc, int64_t ld, int accumulate,
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(128) cell_pairs2_kernel(const CellPairArgs a, 
         for (int s = 0; s < wmax; s += 2) { // two gathers in flight per lane
             const bool v0 = s < cnt, v1 = s + 1 < cnt;
             const int m0 = v0 ? q[s * 128 + tid] : kk, m1 = v1 ? q[(s + 1) * 128 + tid] : kk;
-            const double4 p0 = a.sp4[m0], p1 = a.sp4[m1];
+            const double4 p0 = load_rec(a.sp4 + m0), p1 = load_rec(a.sp4 + m1);
             if (v0) pair(p0, m0);
             if (v1) pair(p1, m1);
         }
@@ -637,7 +644,7 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
     double b[6] = {c->bc[0], c->bc[1], c->bc[2], c->bc[3], c->bc[4], c->bc[5]};
     if (c->bc_kind == NBX_BC_CUBIC) b[1] = 0.5 * c->bc[0];
     if (use_cells) {
-        int rc = cells_build(c, cl, px, nullptr, n, ld, 1);
+        int rc = cells_build(c, cl, px, nullptr, nullptr, n, ld, 1);
         if (rc != NBX_OK) { cudaFree(d_counts); return rc; }
         a = make_args(c, cl, R2);
         if (c->opt_prefilter)
@@ -687,7 +694,8 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
 
 void cells_free(CellList *cl)
 {
-    cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->fill); cudaFree(cl->sums);
+    cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->sums);
+    cudaFree(cl->arrival); cudaFree(cl->tmp_idx); cudaFree(cl->tmp_key);
     cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->sp4); cudaFree(cl->sl4);
     *cl = CellList{};
 }

@@ -232,18 +232,33 @@ __global__ void vv_pos_kernel(double *__restrict__ pos, const double *__restrict
     if (nose && blockIdx.x == 0 && threadIdx.x == 0) scal[1] = fma(dt, scal[2], scal[1]);
 }
 
-// v+ = v + dt/2 (a_old + a_new), and the block partials of sum m v+^2 for the next temperature
-__global__ void vv_vel_kernel(double *__restrict__ vel, const double *__restrict__ a_old,
-                              const double *__restrict__ a_new, const double *__restrict__ mass, int64_t ld,
-                              int64_t lo, int64_t hi, double hdt, double *__restrict__ partial)
+// v+ = v + dt/2 (a_old + a_new), and the block partials of sum m v+^2 for the next temperature.
+// BEREND: the Berendsen RHS term (src/thermostats.jl:76-83) a_new += gamma (T0/T - 1) v(t) is applied on the
+// fly (T from scal[0] = sum m v(t)^2, which only final_sum_kernel overwrites, after this kernel).
+template <bool BEREND>
+__global__ void vv_vel_kernel(double *__restrict__ vel, const double *__restrict__ a_old, double *__restrict__ a_new,
+                              const double *__restrict__ mass, int64_t ld, int64_t lo, int64_t hi, double hdt,
+                              double *__restrict__ partial, const double *__restrict__ scal, double kB, double ndf,
+                              double T0, double gamma)
 {
+    double sc = 0.0;
+    if (BEREND) {
+        const double T = scal[0] / (kB * ndf);
+        sc = (1.0 / T == INFINITY) ? gamma : gamma * (T0 / T - 1.0);
+    }
     double s = 0.0;
     for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
         double v2 = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const int64_t k = d * ld + i;
-            const double v = fma(hdt, a_old[k] + a_new[k], vel[k]);
+            const double v0 = vel[k];
+            double an = a_new[k];
+            if (BEREND) {
+                an += sc * v0; // same expression as berendsen_kernel
+                a_new[k] = an;
+            }
+            const double v = fma(hdt, a_old[k] + an, v0);
             vel[k] = v;
             v2 = fma(v, v, v2);
         }
@@ -265,15 +280,26 @@ int launch_vv_pos(nbx_ctx *c, double dt)
     return NBX_OK;
 }
 
-// acc_old = a(t), acc = a(t+dt) on entry
-int launch_vv_vel(nbx_ctx *c, double dt)
+// acc_old = a(t), acc = a(t+dt) on entry; with_thermostat: the RHS thermostat term is still to be added to acc
+int launch_vv_vel(nbx_ctx *c, double dt, bool with_thermostat)
 {
     NBX_TRY(ensure_red(c));
     const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
     const int nb = red_blocks(c, hi - lo);
+    const double ndf = (double)(3 * c->thN - c->thNc);
+    bool fused = false;
+    if (with_thermostat) {
+        if (c->thermo == NBX_THERMO_BERENDSEN) fused = true;
+        else NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel));
+    }
     timer_begin(c, NBX_T_INTEGRATE);
-    vv_vel_kernel<<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi, 0.5 * dt,
-                                                    c->d_red);
+    if (fused)
+        vv_vel_kernel<true><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
+                                                              0.5 * dt, c->d_red, c->d_scal, c->kB, ndf, c->T0,
+                                                              0.5 / c->tparam);
+    else
+        vv_vel_kernel<false><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
+                                                               0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0);
     final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());

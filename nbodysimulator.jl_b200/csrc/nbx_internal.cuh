@@ -38,7 +38,9 @@ struct CellList {
     int *cell_of = nullptr;     // [n] cell id per particle
     int *count = nullptr;       // [ncell+1] histogram
     int *start = nullptr;       // [ncell+1] exclusive scan of count
-    int *fill = nullptr;        // [ncell+1] scatter cursors
+    int *arrival = nullptr;     // [n] arrival rank of a particle inside its cell (histogram atomics)
+    int *tmp_idx = nullptr;     // [n] particle index per slot before the in-cell ordering
+    int *tmp_key = nullptr;     // [n] ordering key (global id) per slot, only when the context has ids
     int *sums = nullptr;        // scan block totals
     int *sorted_idx = nullptr;  // [n] particle index of the k-th slot in cell order
     int *scell = nullptr;       // [n] cell id of the k-th slot
@@ -91,6 +93,7 @@ struct nbx_ctx {
 
     // ---- sharding -----------------------------------------------------------------------
     int64_t tgt_lo = 0, tgt_hi = 0;
+    int *gid = nullptr;        // slab decomposition: global particle id per local column (nullptr: identity)
 
     // ---- all-pairs scratch ----------------------------------------------------------------
     double *part = nullptr; // [nchunk][3][ntgt_pad] partial sums
@@ -166,7 +169,8 @@ int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_
                         int mstride, double *acc_out, int64_t ld_out, bool accumulate);
 // nbx_cells.cu
 int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g);
-int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, int64_t n, int64_t ld, int key_div);
+int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, const int *gid, int64_t n, int64_t ld,
+                int key_div);
 int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi, int mstride, double *acc_out,
                        int64_t ld_out, bool accumulate);
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
@@ -181,7 +185,7 @@ int launch_fill(nbx_ctx *c, double *p, double v, int64_t count);
 int launch_sum_mv2(nbx_ctx *c, const double *vel, int64_t lo, int64_t hi); // -> d_scal[0]
 int launch_thermostat_rhs(nbx_ctx *c, double *acc, const double *vel);
 int launch_vv_pos(nbx_ctx *c, double dt);
-int launch_vv_vel(nbx_ctx *c, double dt);
+int launch_vv_vel(nbx_ctx *c, double dt, bool with_thermostat);
 int launch_em_step(nbx_ctx *c, double dt);
 int launch_andersen(nbx_ctx *c, double dt);
 int check_finite(nbx_ctx *c, const double *soa, int64_t n);
