@@ -167,6 +167,31 @@ NBX_API int nbx_energy(nbx_ctx *ctx, double *ekin, double *epot, double *tempera
  * cap = capacity of list in entries; NBX_ERR_CAPACITY if too small (offsets still valid). */
 NBX_API int nbx_neighbors(nbx_ctx *ctx, int64_t *offsets, int32_t *list, int64_t cap);
 
+/* ---- slab decomposition (multi-GPU, cutoff potentials in a cubic periodic box) ---------- */
+/* No reference equivalent (the reference is serial): the target loop of soode_system!
+ * (src/nbody_to_ode.jl:474-488) for cutoff Lennard-Jones (src/basic_potentials.jl:240-272) and
+ * cutoff Coulomb (:274-304) under CubicPeriodicBoundaryConditions (src/boundary_conditions.jl:138-165),
+ * cut along x into slabs of whole cell layers, one context per slab.
+ *
+ * nbx_slab_init: every rank has described and uploaded the FULL system (nbx_system, nbx_upload).
+ * Rank `rank` of `nranks` keeps the particles of its layers (with their a(0)), records their global
+ * ids (= column numbers of the upload), and fills its two send buffers with the halo of the boundary
+ * layers.  The host then exchanges the buffers and calls nbx_slab_unpack.  Needs >= 2 layers per slab.
+ * One velocity-Verlet step:  nbx_vv_begin; nbx_slab_pack; exchange; nbx_slab_unpack; nbx_vv_forces;
+ * nbx_vv_finish; all-reduce of the scalar block's [0] (sum m v^2) when a thermostat is set.
+ * Exchange: buffer 0 (send-to-left) -> buffer 3 (recv-from-right) of the left neighbour,
+ *           buffer 1 (send-to-right) -> buffer 2 (recv-from-left) of the right neighbour; periodic.
+ * nbx_slab_unpack synchronises the stream; counts[6] = own, ghosts, migrated out left/right, in from left/right. */
+NBX_API int nbx_slab_init(nbx_ctx *ctx, int rank, int nranks);
+NBX_API int nbx_slab_pack(nbx_ctx *ctx);
+NBX_API int nbx_slab_unpack(nbx_ctx *ctx, int64_t *counts);
+/* which = 0 send-to-left, 1 send-to-right, 2 recv-from-left, 3 recv-from-right; device memory of
+ * *ndoubles doubles each, owned by the context. */
+NBX_API int nbx_slab_buffer(nbx_ctx *ctx, int which, void **ptr, int64_t *ndoubles);
+/* The own particles of the slab: their global ids and state as 3 x n_own column-major host arrays
+ * (any pointer may be NULL; capacity: the full system's column count). */
+NBX_API int nbx_slab_download(nbx_ctx *ctx, int64_t *n_own, int32_t *gid, double *u, double *v, double *dv);
+
 /* ---- plumbing for the host layer ------------------------------------------------------- */
 /* CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on; NULL = the context's own
  * non-blocking stream (the default).  To share the legacy default stream pass cudaStreamLegacy

@@ -53,6 +53,11 @@ SIGNATURES = {
     "nbx_eval_resident": (C.c_int, [_vp]),
     "nbx_energy": (C.c_int, [_vp, _dp, _dp, _dp]),
     "nbx_neighbors": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), _i64]),
+    "nbx_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "nbx_slab_pack": (C.c_int, [_vp]),
+    "nbx_slab_unpack": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "nbx_slab_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "nbx_slab_download": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), _dp, _dp, _dp]),
     "nbx_set_stream": (C.c_int, [_vp, _vp]),
     "nbx_synchronize": (C.c_int, [_vp]),
     "nbx_device_ptr": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
@@ -240,6 +245,34 @@ class Context:
         self._ck(self.lib.nbx_neighbors(self.h, offsets.ctypes.data_as(C.POINTER(_i64)),
                                         lst.ctypes.data_as(C.POINTER(C.c_int32)), cap))
         return offsets, lst[: offsets[-1]]
+
+    # -- slab decomposition ------------------------------------------------------------------------
+    def slab_init(self, rank, nranks):
+        self._ck(self.lib.nbx_slab_init(self.h, int(rank), int(nranks)))
+
+    def slab_pack(self):
+        self._ck(self.lib.nbx_slab_pack(self.h))
+
+    def slab_unpack(self):
+        counts = (_i64 * 6)()
+        self._ck(self.lib.nbx_slab_unpack(self.h, counts))
+        return [int(x) for x in counts]
+
+    def slab_buffer(self, which):
+        p, nd = _vp(), _i64()
+        self._ck(self.lib.nbx_slab_buffer(self.h, int(which), C.byref(p), C.byref(nd)))
+        return int(p.value), int(nd.value)
+
+    def slab_download(self):
+        """(gid, u, v, dv) of the own particles of this slab."""
+        cap = self.n
+        m = _i64()
+        gid = np.zeros(cap, dtype=np.int32)
+        u, v, dv = (np.zeros((3, cap), order="F") for _ in range(3))
+        self._ck(self.lib.nbx_slab_download(self.h, C.byref(m), gid.ctypes.data_as(C.POINTER(C.c_int32)), _p(u), _p(v),
+                                            _p(dv)))
+        k = int(m.value)
+        return gid[:k].copy(), np.asfortranarray(u[:, :k]), np.asfortranarray(v[:, :k]), np.asfortranarray(dv[:, :k])
 
     # -- plumbing ----------------------------------------------------------------------------------
     def set_stream(self, stream_ptr):

@@ -136,7 +136,7 @@ int compute_pairs(nbx_ctx *c)
                 NBX_CUDA(c, cudaGetLastError());
             }
         } else {
-            NBX_TRY(cells_plan(c, c->lj_R, c->n, &c->cl_lj.grid));
+            NBX_TRY(cells_plan(c, c->lj_R, c->slab.on ? c->slab.n_total : c->n, &c->cl_lj.grid));
             if (c->cl_lj.grid.valid) {
                 NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->gid, c->n, c->npad, 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, acc_flag()));
@@ -151,7 +151,7 @@ int compute_pairs(nbx_ctx *c)
             // F += q_j (ri - rj)/r^3, dv += k q_i / m_i F  ==  -k q_i/m_i * sum q_j (rj - ri)/r^3
             NBX_TRY(launch_allpairs_grav(c, c->charge, 1, -c->el_k, c->acc, acc_flag()));
         } else {
-            NBX_TRY(cells_plan(c, c->el_R, c->n, &c->cl_el.grid));
+            NBX_TRY(cells_plan(c, c->el_R, c->slab.on ? c->slab.n_total : c->n, &c->cl_el.grid));
             if (c->cl_el.grid.valid) {
                 NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->gid, c->n, c->npad, c->water ? 3 : 1));
                 NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, acc_flag()));
@@ -189,6 +189,7 @@ static void free_system(nbx_ctx *c)
     c->aos_u = c->aos_v = c->aos_dv = c->opos = c->oacc = nullptr;
     cells_free(&c->cl_lj);
     cells_free(&c->cl_el);
+    slab_free(c);
     c->resident = false;
 }
 
@@ -214,6 +215,22 @@ static int guard(nbx_ctx *c)
 static int need_system(nbx_ctx *c, const char *who)
 {
     if (c->n <= 0) return fail(c, NBX_ERR_INVALID, "%s: call nbx_system first", who);
+    return NBX_OK;
+}
+
+// entry points that assume the context holds the whole system
+static int no_slab(nbx_ctx *c, const char *who)
+{
+    if (c->slab.on)
+        return fail(c, NBX_ERR_INVALID, "%s: the context is slab-decomposed (drive nbx_vv_begin / nbx_slab_pack / exchange / "
+                    "nbx_slab_unpack / nbx_vv_forces / nbx_vv_finish; nbx_system starts over)", who);
+    return NBX_OK;
+}
+
+static int need_resident(nbx_ctx *c, const char *who)
+{
+    NBX_TRY(need_system(c, who));
+    if (!c->resident) return fail(c, NBX_ERR_INVALID, "%s: no resident state (call nbx_upload)", who);
     return NBX_OK;
 }
 
@@ -447,6 +464,7 @@ int nbx_shard_pairs(nbx_ctx *c, int rank, int nranks)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_shard_pairs"));
+    NBX_TRY(no_slab(c, "nbx_shard_pairs"));
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, NBX_ERR_INVALID, "nbx_shard_pairs: rank %d of %d", rank, nranks);
     c->pair_rank = rank; c->pair_nranks = nranks;
     return NBX_OK;
@@ -456,9 +474,61 @@ int nbx_shard(nbx_ctx *c, int64_t lo, int64_t hi)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_shard"));
+    NBX_TRY(no_slab(c, "nbx_shard"));
     if (lo < 0 || hi > c->n || lo > hi) return fail(c, NBX_ERR_INVALID, "nbx_shard: [%lld,%lld) outside [0,%lld)", (long long)lo, (long long)hi, (long long)c->n);
     if (c->water && (lo % 3 || hi % 3)) return fail(c, NBX_ERR_INVALID, "nbx_shard: water shards must hold whole molecules");
     c->tgt_lo = lo; c->tgt_hi = hi;
+    return NBX_OK;
+}
+
+int nbx_slab_init(nbx_ctx *c, int rank, int nranks)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_init"));
+    return slab_init(c, rank, nranks);
+}
+
+int nbx_slab_pack(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_pack"));
+    return slab_pack(c);
+}
+
+int nbx_slab_unpack(nbx_ctx *c, int64_t *counts)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_unpack"));
+    return slab_unpack(c, counts);
+}
+
+int nbx_slab_buffer(nbx_ctx *c, int which, void **ptr, int64_t *ndoubles)
+{
+    NBX_TRY(guard(c));
+    if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_buffer: call nbx_slab_init first");
+    if (which < 0 || which > 3 || !ptr) return fail(c, NBX_ERR_INVALID, "nbx_slab_buffer: which = %d", which);
+    *ptr = c->slab.msg[which];
+    if (ndoubles) *ndoubles = c->slab.msg_doubles;
+    return NBX_OK;
+}
+
+int nbx_slab_download(nbx_ctx *c, int64_t *n_own, int32_t *gid, double *u, double *v, double *dv)
+{
+    NBX_TRY(guard(c));
+    if (!c->slab.on || c->slab.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_download: no complete slab state");
+    const int64_t m = c->slab.n_own;
+    const size_t bytes = sizeof(double) * 3 * (size_t)m;
+    if (n_own) *n_own = m;
+    if (gid && m) NBX_CUDA(c, cudaMemcpyAsync(gid, c->gid, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+    double *const rows[3] = {c->pos, c->vel, c->acc};
+    double *const stage[3] = {c->aos_u, c->aos_v, c->aos_dv};
+    double *const host[3] = {u, v, dv};
+    for (int k = 0; k < 3; ++k) {
+        if (!host[k] || m == 0) continue;
+        NBX_TRY(launch_soa_to_aos(c, rows[k], stage[k], m, m, 0, m));
+        NBX_CUDA(c, cudaMemcpyAsync(host[k], stage[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     return NBX_OK;
 }
 
@@ -491,6 +561,7 @@ int nbx_accel(nbx_ctx *c, const double *u, double *v, double t, double *dv)
     (void)t;
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_accel"));
+    NBX_TRY(no_slab(c, "nbx_accel"));
     if (!u || !dv) return fail(c, NBX_ERR_INVALID, "nbx_accel: u and dv are required");
     const bool have_v = needs_velocity(c);
     if (have_v && !v) return fail(c, NBX_ERR_INVALID, "nbx_accel: this thermostat needs v");
@@ -509,6 +580,7 @@ int nbx_accel_device(nbx_ctx *c, const double *u_dev, double *v_dev, double t, d
     (void)t;
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_accel_device"));
+    NBX_TRY(no_slab(c, "nbx_accel_device"));
     if (!u_dev || !dv_dev) return fail(c, NBX_ERR_INVALID, "nbx_accel_device: u and dv are required");
     const bool have_v = needs_velocity(c);
     if (have_v && !v_dev) return fail(c, NBX_ERR_INVALID, "nbx_accel_device: this thermostat needs v");
@@ -526,6 +598,7 @@ int nbx_upload(nbx_ctx *c, const double *u, const double *v)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_upload"));
+    NBX_TRY(no_slab(c, "nbx_upload"));
     if (!u || !v) return fail(c, NBX_ERR_INVALID, "nbx_upload: u and v are required");
     const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
     NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -551,17 +624,11 @@ int nbx_upload(nbx_ctx *c, const double *u, const double *v)
     return finish_and_check(c);
 }
 
-static int need_resident(nbx_ctx *c, const char *who)
-{
-    NBX_TRY(need_system(c, who));
-    if (!c->resident) return fail(c, NBX_ERR_INVALID, "%s: no resident state (call nbx_upload)", who);
-    return NBX_OK;
-}
-
 int nbx_eval_resident(nbx_ctx *c)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_eval_resident"));
+    NBX_TRY(no_slab(c, "nbx_eval_resident"));
     return compute_accel(c);
 }
 
@@ -602,6 +669,7 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_step_vv"));
+    NBX_TRY(no_slab(c, "nbx_step_vv"));
     if (c->tgt_lo != 0 || c->tgt_hi != c->n)
         return fail(c, NBX_ERR_INVALID, "nbx_step_vv: sharded context; drive nbx_vv_begin / all-gather / nbx_vv_finish");
     if (c->pair_nranks > 1)
@@ -630,6 +698,7 @@ int nbx_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_step_em"));
+    NBX_TRY(no_slab(c, "nbx_step_em"));
     if (c->thermo != NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_step_em: needs the Langevin thermostat");
     if (c->water) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_em: the water SDE variant (src/nbody_to_ode.jl:600-680) is not built");
     if (seed) c->seed = seed;
@@ -646,6 +715,7 @@ int nbx_download(nbx_ctx *c, double *u, double *v, double *dv)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_download"));
+    NBX_TRY(no_slab(c, "nbx_download"));
     const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
     const bool nose = c->thermo == NBX_THERMO_NOSEHOOVER;
     if (u) {
@@ -670,6 +740,7 @@ int nbx_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_energy"));
+    NBX_TRY(no_slab(c, "nbx_energy"));
     if (ekin || temperature) NBX_TRY(reduce_kinetic(c, ekin, temperature));
     if (epot) NBX_TRY(reduce_potential(c, epot));
     return NBX_OK;
@@ -679,6 +750,7 @@ int nbx_neighbors(nbx_ctx *c, int64_t *offsets, int32_t *list, int64_t cap)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_neighbors"));
+    NBX_TRY(no_slab(c, "nbx_neighbors"));
     if (!c->has_lj) return fail(c, NBX_ERR_INVALID, "nbx_neighbors: no Lennard-Jones potential (the cutoff predicate) configured");
     if (!offsets || (!list && cap > 0)) return fail(c, NBX_ERR_INVALID, "nbx_neighbors: NULL output");
     if (c->water) {
@@ -755,6 +827,11 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "ncols")) *value = c->ncols;
     else if (!strcmp(key, "water")) *value = c->water;
     else if (!strcmp(key, "sm_count")) *value = c->sm_count;
+    else if (!strcmp(key, "slab_own")) *value = c->slab.on ? c->slab.n_own : c->n;
+    else if (!strcmp(key, "slab_ghost")) *value = c->slab.on ? c->slab.n_ghost : 0;
+    else if (!strcmp(key, "slab_layer_lo")) *value = c->slab.c0;
+    else if (!strcmp(key, "slab_layer_hi")) *value = c->slab.c1;
+    else if (!strcmp(key, "slab_layers")) *value = c->slab.nc;
     else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;
     else if (!strcmp(key, "cells_el")) *value = c->cl_el.grid.valid ? c->cl_el.grid.ncell : 0;
     else if (!strcmp(key, "allpairs_grid")) *value = c->last_grid;

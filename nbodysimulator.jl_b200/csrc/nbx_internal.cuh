@@ -49,6 +49,19 @@ struct CellList {
     int64_t cap_n = 0, cap_cells = 0;
 };
 
+// slab decomposition state (nbx_slab.cu)
+struct SlabState {
+    bool on = false, packed = false;
+    int rank = 0, nranks = 1;
+    int nc = 0, c0 = 0, c1 = 0, wL = 0, wR = 0; // layers of the slab grid; own layers [c0, c1); neighbour widths
+    int64_t n_total = 0, n_own = 0, n_ghost = 0;
+    int64_t capM = 0, capH = 0, msg_doubles = 0; // message capacities (migrants, halo records) and size
+    double *msg[4] = {nullptr, nullptr, nullptr, nullptr}; // send-left, send-right, recv-from-left, recv-from-right
+    double *pos2 = nullptr, *vel2 = nullptr, *acc2 = nullptr, *mass2 = nullptr, *charge2 = nullptr; // compaction targets
+    int *gid_a = nullptr, *gid_b = nullptr;
+    int *blockcnt = nullptr, *blockoff = nullptr, *d_counts = nullptr, *h_counts = nullptr;
+};
+
 } // namespace nbx
 
 struct nbx_ctx {
@@ -94,6 +107,7 @@ struct nbx_ctx {
     // ---- sharding -----------------------------------------------------------------------
     int64_t tgt_lo = 0, tgt_hi = 0;
     int *gid = nullptr;        // slab decomposition: global particle id per local column (nullptr: identity)
+    nbx::SlabState slab;
 
     // ---- all-pairs scratch ----------------------------------------------------------------
     double *part = nullptr; // [nchunk][3][ntgt_pad] partial sums
@@ -176,6 +190,11 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
                     int32_t *list, int64_t cap);
 void cells_free(CellList *cl);
+// nbx_slab.cu
+int slab_init(nbx_ctx *c, int rank, int nranks);
+int slab_pack(nbx_ctx *c);
+int slab_unpack(nbx_ctx *c, int64_t *counts);
+void slab_free(nbx_ctx *c);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);
 // nbx_integrate.cu

@@ -1,0 +1,371 @@
+// nbx_slab.cu -- slab decomposition of cutoff systems over one process per GPU (sm_100a).
+//
+// The reference is serial; this is the multi-GPU form of the target loop of soode_system!
+// (src/nbody_to_ode.jl:474-488) for short-range potentials in a CubicPeriodicBoundaryConditions box
+// (src/boundary_conditions.jl:101-103).  The box is cut along x into slabs of whole cell layers (the
+// cells of the binning grid, edge >= cutoff).  A rank OWNS the particles whose wrapped x lies in its
+// layers [c0, c1) and keeps, as GHOSTS, copies of the positions of the two adjacent layers.  Per step:
+//
+//   nbx_vv_begin         x += dt v + dt^2/2 a on the own particles
+//   nbx_slab_pack        classify the own particles; stayers are compacted (stable) into the alternate
+//                        state arrays, leavers go with their full state into the send buffer of the
+//                        neighbour they moved to, the own boundary layers go as halo records
+//   (host)               send-to-left/right <-> recv-from-right/left, one message per neighbour
+//   nbx_slab_unpack      arrivals are appended to the own particles, then the ghost set is laid down:
+//                        the leavers just sent (they sit in the neighbour's boundary layer now) and the
+//                        two received halos
+//   nbx_vv_forces/finish cell list over own + ghosts in the GLOBAL grid, pair kernel on the own targets
+//
+// Every local particle carries its global id; the cell order is ranked by that id (nbx_cells.cu), so the
+// force sums are bit-identical to the single-GPU result whatever the local numbering.
+// A slab needs >= 2 layers so that one exchange per step suffices (an arrival from the left lands in the
+// leftmost layer and is a ghost of the left neighbour only, which kept it).
+#include "nbx_internal.cuh"
+
+namespace nbx {
+
+constexpr int kHdr = 8;    // message header doubles: [0] migrants, [1] halo records
+constexpr int kMigW = 12;  // gid, x y z, vx vy vz, ax ay az, m, q
+constexpr int kHaloW = 5;  // gid, x y z, q
+constexpr int kSlabBlock = 256;
+
+enum { CAT_STAY = 0, CAT_MIGL = 1, CAT_MIGR = 2, CAT_HALOL = 3, CAT_HALOR = 4, CAT_N = 5 };
+// device counters
+enum { CNT_ERR_LOST = 5, CNT_ERR_CAP = 6, CNT_OWN = 7, CNT_GHOST = 8, CNT_ARRL = 9, CNT_ARRR = 10, CNT_N = 16 };
+
+struct SlabGeom {
+    double L;
+    int nc, c0, width, wL, wR; // own layers [c0, c0 + width), neighbour widths
+    int init;                  // 1: particles outside the own layers are dropped, not migrated
+};
+
+__device__ __forceinline__ int slab_layer(double x, double L, int nc)
+{
+    double w = x - L * floor(x / L);
+    if (w < 0.0) w += L;
+    if (w >= L) w -= L;
+    int cx = (int)(w * ((double)nc / L));
+    return cx < 0 ? 0 : (cx >= nc ? nc - 1 : cx); // same expression as the binning of nbx_cells.cu
+}
+
+// bit c set: the particle counts in category c;  bit 8: lost (moved past the neighbouring slab)
+__device__ __forceinline__ unsigned slab_classify(double x, const SlabGeom &g)
+{
+    const int layer = slab_layer(x, g.L, g.nc);
+    int rel = layer - g.c0;
+    if (rel < 0) rel += g.nc;
+    if (rel < g.width) {
+        unsigned f = 1u << CAT_STAY;
+        if (rel == 0) f |= 1u << CAT_HALOL;
+        if (rel == g.width - 1) f |= 1u << CAT_HALOR;
+        return f;
+    }
+    if (g.init) return 0u;
+    const int dl = g.nc - rel, dr = rel - g.width + 1; // layers beyond the left / right face
+    if (dl <= dr) return (1u << CAT_MIGL) | (dl > g.wL ? 256u : 0u);
+    return (1u << CAT_MIGR) | (dr > g.wR ? 256u : 0u);
+}
+
+__global__ void __launch_bounds__(kSlabBlock) slab_count_kernel(const double *__restrict__ px, int n, SlabGeom g,
+                                                                int *__restrict__ blockcnt, int *__restrict__ counts)
+{
+    __shared__ int cnt[CAT_N];
+    if (threadIdx.x < CAT_N) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * kSlabBlock + threadIdx.x;
+    const unsigned f = i < n ? slab_classify(px[i], g) : 0u;
+#pragma unroll
+    for (int c = 0; c < CAT_N; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, (f >> c) & 1u);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
+    }
+    if (f & 256u) atomicAdd(&counts[CNT_ERR_LOST], 1);
+    __syncthreads();
+    if (threadIdx.x < CAT_N) blockcnt[blockIdx.x * CAT_N + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// exclusive scan over the blocks, one warp per category; totals -> counts[0..4]
+__global__ void slab_scan_kernel(const int *__restrict__ blockcnt, int *__restrict__ blockoff, int nb,
+                                 int *__restrict__ counts)
+{
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= CAT_N) return;
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = b < nb ? blockcnt[b * CAT_N + c] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (b < nb) blockoff[b * CAT_N + c] = carry + s - v;
+        carry += __shfl_sync(0xffffffffu, s, 31);
+    }
+    if (lane == 0) counts[c] = carry;
+}
+
+struct SlabArrays {
+    double *pos, *vel, *acc, *mass, *charge; // SoA rows of stride ld (charge may be null)
+    int *gid;                                // may be null: identity
+};
+
+__global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, SlabArrays dst, int64_t ld, int n,
+                                                               SlabGeom g, const int *__restrict__ blockoff,
+                                                               int *__restrict__ counts, double *__restrict__ sendL,
+                                                               double *__restrict__ sendR, int capM, int capH)
+{
+    __shared__ int wcnt[kSlabBlock / 32][CAT_N];
+    const int i = blockIdx.x * kSlabBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned f = i < n ? slab_classify(src.pos[i], g) : 0u;
+    int rank[CAT_N];
+#pragma unroll
+    for (int c = 0; c < CAT_N; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, (f >> c) & 1u);
+        rank[c] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) wcnt[warp][c] = __popc(m);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CAT_N; ++c) {
+        int base = blockoff[blockIdx.x * CAT_N + c];
+        for (int w = 0; w < warp; ++w) base += wcnt[w][c];
+        rank[c] += base;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sendL[0] = (double)min(counts[CAT_MIGL], capM); sendL[1] = (double)min(counts[CAT_HALOL], capH);
+        sendR[0] = (double)min(counts[CAT_MIGR], capM); sendR[1] = (double)min(counts[CAT_HALOR], capH);
+        if (counts[CAT_MIGL] > capM || counts[CAT_MIGR] > capM || counts[CAT_HALOL] > capH || counts[CAT_HALOR] > capH)
+            counts[CNT_ERR_CAP] = 1;
+    }
+    if (i >= n || f == 0u) return;
+    const double x = src.pos[i], y = src.pos[ld + i], z = src.pos[2 * ld + i];
+    const int id = src.gid ? src.gid[i] : i;
+    const double q = src.charge ? src.charge[i] : 0.0;
+    if (f & (1u << CAT_STAY)) {
+        const int d = rank[CAT_STAY];
+        dst.pos[d] = x; dst.pos[ld + d] = y; dst.pos[2 * ld + d] = z;
+        dst.vel[d] = src.vel[i]; dst.vel[ld + d] = src.vel[ld + i]; dst.vel[2 * ld + d] = src.vel[2 * ld + i];
+        dst.acc[d] = src.acc[i]; dst.acc[ld + d] = src.acc[ld + i]; dst.acc[2 * ld + d] = src.acc[2 * ld + i];
+        dst.mass[d] = src.mass[i];
+        if (dst.charge) dst.charge[d] = q;
+        dst.gid[d] = id;
+        for (int side = 0; side < 2; ++side) {
+            const int cat = side == 0 ? CAT_HALOL : CAT_HALOR;
+            if (!(f & (1u << cat)) || rank[cat] >= capH) continue;
+            double *rec = (side == 0 ? sendL : sendR) + kHdr + (size_t)capM * kMigW + (size_t)rank[cat] * kHaloW;
+            rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z; rec[4] = q;
+        }
+    } else {
+        const int cat = (f & (1u << CAT_MIGL)) ? CAT_MIGL : CAT_MIGR;
+        if (rank[cat] >= capM) return;
+        double *rec = (cat == CAT_MIGL ? sendL : sendR) + kHdr + (size_t)rank[cat] * kMigW;
+        rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z;
+        rec[4] = src.vel[i]; rec[5] = src.vel[ld + i]; rec[6] = src.vel[2 * ld + i];
+        rec[7] = src.acc[i]; rec[8] = src.acc[ld + i]; rec[9] = src.acc[2 * ld + i];
+        rec[10] = src.mass[i]; rec[11] = q;
+    }
+}
+
+// segments, in the order they are laid down: arrivals (left, right) extend the own particles; the ghosts are
+// the migrants just sent (left, right) and the received halos (left, right)
+__global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
+                                   const double *__restrict__ sendL, const double *__restrict__ sendR,
+                                   const double *__restrict__ recvL, const double *__restrict__ recvR, int capM, int capH)
+{
+    const int nstay = counts[CAT_STAY];
+    const int arrL = min((int)recvL[0], capM), arrR = min((int)recvR[0], capM);
+    const int keptL = min((int)sendL[0], capM), keptR = min((int)sendR[0], capM);
+    const int haloL = min((int)recvL[1], capH), haloR = min((int)recvR[1], capH);
+    const int n_own = nstay + arrL + arrR;
+    const int n_ghost = keptL + keptR + haloL + haloR;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counts[CNT_OWN] = n_own; counts[CNT_GHOST] = n_ghost; counts[CNT_ARRL] = arrL; counts[CNT_ARRR] = arrR;
+        if ((int64_t)n_own + n_ghost > cap_cols) counts[CNT_ERR_CAP] = 1;
+    }
+    if ((int64_t)n_own + n_ghost > cap_cols) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int seg, idx;
+    if (t < 2 * capM) { seg = t / capM; idx = t - seg * capM; }                 // 0,1: arrivals
+    else if (t < 4 * capM) { seg = 2 + (t - 2 * capM) / capM; idx = (t - 2 * capM) % capM; } // 2,3: kept
+    else { const int u = t - 4 * capM; if (u >= 2 * capH) return; seg = 4 + u / capH; idx = u % capH; } // 4,5: halos
+    const int cnt = seg == 0 ? arrL : seg == 1 ? arrR : seg == 2 ? keptL : seg == 3 ? keptR : seg == 4 ? haloL : haloR;
+    if (idx >= cnt) return;
+    const double *buf = seg == 0 ? recvL : seg == 1 ? recvR : seg == 2 ? sendL : seg == 3 ? sendR : seg == 4 ? recvL : recvR;
+    if (seg < 4) {
+        const double *rec = buf + kHdr + (size_t)idx * kMigW;
+        int d;
+        if (seg == 0) d = nstay + idx;
+        else if (seg == 1) d = nstay + arrL + idx;
+        else if (seg == 2) d = n_own + idx;
+        else d = n_own + keptL + idx;
+        dst.gid[d] = (int)rec[0];
+        dst.pos[d] = rec[1]; dst.pos[ld + d] = rec[2]; dst.pos[2 * ld + d] = rec[3];
+        if (seg < 2) { // full state
+            dst.vel[d] = rec[4]; dst.vel[ld + d] = rec[5]; dst.vel[2 * ld + d] = rec[6];
+            dst.acc[d] = rec[7]; dst.acc[ld + d] = rec[8]; dst.acc[2 * ld + d] = rec[9];
+            dst.mass[d] = rec[10];
+        } else {
+            dst.mass[d] = 1.0;
+        }
+        if (dst.charge) dst.charge[d] = rec[11];
+    } else {
+        const double *rec = buf + kHdr + (size_t)capM * kMigW + (size_t)idx * kHaloW;
+        const int d = n_own + keptL + keptR + (seg == 4 ? 0 : haloL) + idx;
+        dst.gid[d] = (int)rec[0];
+        dst.pos[d] = rec[1]; dst.pos[ld + d] = rec[2]; dst.pos[2 * ld + d] = rec[3];
+        dst.mass[d] = 1.0;
+        if (dst.charge) dst.charge[d] = rec[4];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+void slab_free(nbx_ctx *c)
+{
+    SlabState &s = c->slab;
+    for (double *&p : s.msg) { cudaFree(p); p = nullptr; }
+    cudaFree(s.pos2); cudaFree(s.vel2); cudaFree(s.acc2); cudaFree(s.mass2); cudaFree(s.charge2);
+    cudaFree(s.gid_a); cudaFree(s.gid_b); cudaFree(s.blockcnt); cudaFree(s.blockoff); cudaFree(s.d_counts);
+    if (s.h_counts) cudaFreeHost(s.h_counts);
+    s = SlabState{};
+    c->gid = nullptr;
+}
+
+static SlabGeom geom(const nbx_ctx *c, int init)
+{
+    const SlabState &s = c->slab;
+    SlabGeom g{};
+    g.L = c->bc[0]; g.nc = s.nc; g.c0 = s.c0; g.width = s.c1 - s.c0; g.wL = s.wL; g.wR = s.wR; g.init = init;
+    return g;
+}
+
+static SlabArrays arrays(double *pos, double *vel, double *acc, double *mass, double *charge, int *gid)
+{
+    SlabArrays a{};
+    a.pos = pos; a.vel = vel; a.acc = acc; a.mass = mass; a.charge = charge; a.gid = gid;
+    return a;
+}
+
+static int run_pack(nbx_ctx *c, int init)
+{
+    SlabState &s = c->slab;
+    const int n = (int)(init ? s.n_total : s.n_own);
+    const int nb = (n + kSlabBlock - 1) / kSlabBlock;
+    const SlabGeom g = geom(c, init);
+    NBX_CUDA(c, cudaMemsetAsync(s.d_counts, 0, sizeof(int) * CNT_N, c->stream));
+    int *gid_dst = c->gid == s.gid_a ? s.gid_b : s.gid_a;
+    const SlabArrays src = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
+    const SlabArrays dst = arrays(s.pos2, s.vel2, s.acc2, s.mass2, c->charge ? s.charge2 : nullptr, gid_dst);
+    if (nb > 0) {
+        slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_counts);
+        slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
+        slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0],
+                                                          s.msg[1], (int)s.capM, (int)s.capH);
+    } else {
+        NBX_CUDA(c, cudaMemsetAsync(s.msg[0], 0, sizeof(double) * kHdr, c->stream));
+        NBX_CUDA(c, cudaMemsetAsync(s.msg[1], 0, sizeof(double) * kHdr, c->stream));
+    }
+    NBX_CUDA(c, cudaGetLastError());
+    // the compacted state is the state from here on (stream-ordered: later kernels see the new pointers)
+    std::swap(c->pos, s.pos2); std::swap(c->vel, s.vel2); std::swap(c->acc, s.acc2); std::swap(c->mass, s.mass2);
+    if (c->charge) std::swap(c->charge, s.charge2);
+    c->gid = gid_dst;
+    s.packed = true;
+    return NBX_OK;
+}
+
+int slab_init(nbx_ctx *c, int rank, int nranks)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: rank %d of %d", rank, nranks);
+    if (c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: already decomposed (nbx_upload resets)");
+    if (c->bc_kind != NBX_BC_CUBIC) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: slabs need CubicPeriodicBoundaryConditions");
+    if (c->water || c->has_grav || c->has_dip || c->has_spcfw || c->thermo == NBX_THERMO_NOSEHOOVER)
+        return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: slabs cover atomic systems with cutoff Lennard-Jones / Coulomb terms");
+    const bool coul_cut = c->has_coul && isfinite(c->el_R);
+    if (c->has_coul && !coul_cut) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: unbounded Coulomb is an all-pairs problem (use nbx_shard)");
+    if (!c->has_lj && !coul_cut) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: no cutoff potential configured");
+    if (c->tgt_lo != 0 || c->tgt_hi != c->n || c->pair_nranks > 1) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: context is already sharded");
+    const double R = fmax(c->has_lj ? c->lj_R : 0.0, coul_cut ? c->el_R : 0.0);
+    CellGrid grid;
+    NBX_TRY(cells_plan(c, R, c->n, &grid));
+    if (!grid.valid) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: the cutoff does not allow a cell grid (R >= L/3)");
+    const int nc = grid.nc[0];
+    if (nranks > 1 && nc < 2 * nranks)
+        return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: %d cell layers cannot give %d slabs of >= 2 layers", nc, nranks);
+    SlabState &s = c->slab;
+    s.rank = rank; s.nranks = nranks; s.nc = nc;
+    auto lo_of = [&](int r) { return (int)((int64_t)r * nc / nranks); };
+    s.c0 = lo_of(rank); s.c1 = lo_of(rank + 1);
+    const int left = (rank + nranks - 1) % nranks, right = (rank + 1) % nranks;
+    s.wL = lo_of(left + 1) - lo_of(left); s.wR = lo_of(right + 1) - lo_of(right);
+    s.n_total = c->n;
+    const int64_t layer = (c->n + nc - 1) / nc;
+    s.capH = std::min<int64_t>(c->n, 2 * layer + 1024);
+    s.capM = std::min<int64_t>(c->n, layer / 2 + 1024);
+    s.msg_doubles = kHdr + s.capM * kMigW + s.capH * kHaloW;
+    const size_t np = (size_t)c->npad;
+    for (double *&p : s.msg) {
+        NBX_TRY(dev_alloc(c, &p, (size_t)s.msg_doubles));
+        NBX_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)s.msg_doubles, c->stream));
+    }
+    NBX_TRY(dev_alloc(c, &s.pos2, 3 * np)); NBX_TRY(dev_alloc(c, &s.vel2, 3 * np)); NBX_TRY(dev_alloc(c, &s.acc2, 3 * np));
+    NBX_TRY(dev_alloc(c, &s.mass2, np));
+    if (c->charge) NBX_TRY(dev_alloc(c, &s.charge2, np));
+    NBX_TRY(dev_alloc(c, &s.gid_a, np)); NBX_TRY(dev_alloc(c, &s.gid_b, np));
+    const size_t nbmax = (size_t)((c->n + kSlabBlock - 1) / kSlabBlock) + 1;
+    NBX_TRY(dev_alloc(c, &s.blockcnt, nbmax * CAT_N)); NBX_TRY(dev_alloc(c, &s.blockoff, nbmax * CAT_N));
+    NBX_TRY(dev_alloc(c, &s.d_counts, (size_t)CNT_N));
+    NBX_CUDA(c, cudaMallocHost((void **)&s.h_counts, sizeof(int) * CNT_N));
+    // padding of the alternate rows as in nbx_system
+    NBX_TRY(launch_fill(c, s.pos2, kFarAway, 3 * c->npad));
+    NBX_CUDA(c, cudaMemsetAsync(s.vel2, 0, sizeof(double) * 3 * np, c->stream));
+    NBX_CUDA(c, cudaMemsetAsync(s.acc2, 0, sizeof(double) * 3 * np, c->stream));
+    NBX_CUDA(c, cudaMemsetAsync(s.mass2, 0, sizeof(double) * np, c->stream));
+    s.on = true;
+    s.n_own = s.n_total; // the pack below reads the full uploaded state (ids = column numbers)
+    c->gid = nullptr;
+    return run_pack(c, 1);
+}
+
+int slab_pack(nbx_ctx *c)
+{
+    if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: call nbx_slab_init first");
+    if (c->slab.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: the previous pack was not completed by nbx_slab_unpack");
+    return run_pack(c, 0);
+}
+
+int slab_unpack(nbx_ctx *c, int64_t *out)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_unpack: nothing was packed");
+    const int64_t threads = 4 * s.capM + 2 * s.capH;
+    const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
+    slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.n_total, s.d_counts, s.msg[0],
+                                                                              s.msg[1], s.msg[2], s.msg[3], (int)s.capM,
+                                                                              (int)s.capH);
+    NBX_CUDA(c, cudaGetLastError());
+    NBX_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, c->stream));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.packed = false;
+    const int *h = s.h_counts;
+    if (h[CNT_ERR_LOST] > 0)
+        return fail(c, NBX_ERR_INVALID, "slab exchange: %d particle(s) moved past the neighbouring slab in one step", h[CNT_ERR_LOST]);
+    if (h[CNT_ERR_CAP] != 0)
+        return fail(c, NBX_ERR_CAPACITY, "slab exchange: message or state capacity exceeded (migrants %d/%d, halo %d/%d of %lld/%lld)",
+                    h[CAT_MIGL], h[CAT_MIGR], h[CAT_HALOL], h[CAT_HALOR], (long long)s.capM, (long long)s.capH);
+    s.n_own = h[CNT_OWN];
+    s.n_ghost = h[CNT_GHOST];
+    c->n = s.n_own + s.n_ghost;
+    c->tgt_lo = 0;
+    c->tgt_hi = s.n_own;
+    if (out) {
+        out[0] = s.n_own; out[1] = s.n_ghost; out[2] = h[CAT_MIGL]; out[3] = h[CAT_MIGR]; out[4] = h[CNT_ARRL]; out[5] = h[CNT_ARRR];
+    }
+    return NBX_OK;
+}
+
+} // namespace nbx

@@ -11,7 +11,13 @@ index ``i`` of ``soode_system!`` (src/nbody_to_ode.jl:475).  Two decompositions:
   acceleration of ALL particles, and a reduce-scatter of the acceleration rows (24 B per particle)
   completes the own block.  Two exchanges per step, 1.6x less arithmetic.
 
-Both add an 8-byte all-reduce of sum m v^2 when a thermostat needs the global temperature.
+* ``SlabStepper`` (cutoff Lennard-Jones / Coulomb in a cubic periodic box): spatial decomposition
+  along x into slabs of whole cell layers.  A rank owns the particles of its layers and keeps ghost
+  copies of the two adjacent layers; per step ONE message to each neighbour carries the particles
+  that crossed the face (full state) and the boundary layer's positions (halo).  No collective on the
+  data path; the state never leaves the devices (csrc/nbx_slab.cu).
+
+All add an 8-byte all-reduce of sum m v^2 when a thermostat needs the global temperature.
 
 The plumbing works on an *engine* (duck-typed):
     engine.n                       particle columns
@@ -93,6 +99,32 @@ class CudaEngine:
     def vv_finish(self, dt):
         self.ctx.vv_finish(dt)
 
+    # -- slab decomposition (SlabStepper) -----------------------------------------------------------
+    def _raw(self, ptr, count):
+        import torch
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                        "strides": None}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def slab_init(self, rank, world):
+        self.ctx.slab_init(rank, world)
+
+    def slab_buffers(self):
+        """[send-to-left, send-to-right, recv-from-left, recv-from-right] as flat float64 device tensors."""
+        return [self._raw(*self.ctx.slab_buffer(k)) for k in range(4)]
+
+    def slab_pack(self):
+        self.ctx.slab_pack()
+
+    def slab_unpack(self):
+        return self.ctx.slab_unpack()
+
+    def slab_download(self):
+        return self.ctx.slab_download()
+
 
 class ShardedStepper:
     """Velocity Verlet over a process group (see the module docstring for the two modes)."""
@@ -168,6 +200,80 @@ class ShardedStepper:
             if self.engine.needs_temperature and self.world > 1:
                 s = self.engine.scalars()
                 self.dist.all_reduce(s[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class SlabStepper:
+    """Velocity Verlet of a cutoff system over x-slabs, one rank per slab (see the module docstring).
+
+    Every rank must have described and uploaded the FULL system on its engine before construction; the
+    engine then keeps its slab.  Engine duck type, on top of ShardedStepper's: slab_init(rank, world),
+    slab_buffers() -> 4 flat tensors, slab_pack(), slab_unpack() -> counts, slab_download().
+    """
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
+        self.left = (self.rank - 1) % self.world
+        self.right = (self.rank + 1) % self.world
+        engine.slab_init(self.rank, self.world)
+        self.bufs = engine.slab_buffers()
+        self._exchange()
+        self.counts = engine.slab_unpack()
+
+    def _peer(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def _exchange(self):
+        """send-to-left -> the left neighbour's recv-from-right, send-to-right -> the right neighbour's
+        recv-from-left.  Posting order (sends: left, right; receives: from right, from left) keeps the two
+        messages of a 2-rank ring, where both neighbours are the same peer, matched."""
+        if self.world == 1:
+            return  # one slab: the cell list's own periodic wrap does everything, no ghosts
+        dist = self.dist
+        send_l, send_r, recv_l, recv_r = self.bufs
+        ops = [dist.P2POp(dist.isend, send_l, self._peer(self.left), self.group),
+               dist.P2POp(dist.isend, send_r, self._peer(self.right), self.group),
+               dist.P2POp(dist.irecv, recv_r, self._peer(self.right), self.group),
+               dist.P2POp(dist.irecv, recv_l, self._peer(self.left), self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def step(self, dt: float, nsteps: int = 1):
+        e = self.engine
+        for _ in range(nsteps):
+            e.vv_begin(dt)
+            e.slab_pack()
+            self._exchange()
+            self.counts = e.slab_unpack()
+            e.vv_forces()
+            e.vv_finish(dt)
+            if e.needs_temperature and self.world > 1:
+                self.dist.all_reduce(e.scalars()[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def gather(self, n_total: int):
+        """(u, v, dv) of the whole system in the original column order, on every rank (host arrays;
+        diagnostics and tests, not the hot path)."""
+        gid, u, v, dv = self.engine.slab_download()
+        parts = [(gid, u, v, dv)]
+        if self.world > 1:
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, (gid, u, v, dv), group=self.group)
+        out = [np.zeros((3, n_total), order="F") for _ in range(3)]
+        seen = np.zeros(n_total, dtype=np.int64)
+        for g, uu, vv, aa in parts:
+            seen[g] += 1
+            for dst, src in zip(out, (uu, vv, aa)):
+                dst[:, g] = src
+        if not (seen == 1).all():
+            raise RuntimeError(f"slab ownership is not a partition: {int((seen == 0).sum())} particles lost, "
+                               f"{int((seen > 1).sum())} duplicated")
+        return out
 
 
 def numpy_reference_partition_check(n, world, multiple=1):
