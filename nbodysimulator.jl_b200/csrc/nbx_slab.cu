@@ -304,8 +304,9 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     s.wL = lo_of(left + 1) - lo_of(left); s.wR = lo_of(right + 1) - lo_of(right);
     s.n_total = c->n;
     const int64_t layer = (c->n + nc - 1) / nc;
-    s.capH = std::min<int64_t>(c->n, 2 * layer + 1024);
-    s.capM = std::min<int64_t>(c->n, layer / 2 + 1024);
+    // a boundary layer's population with 50 % head room; a step moves a small fraction of a layer across a face
+    s.capH = std::min<int64_t>(c->n, layer + layer / 2 + 1024);
+    s.capM = std::min<int64_t>(c->n, layer / 8 + 1024);
     s.msg_doubles = kHdr + s.capM * kMigW + s.capH * kHaloW;
     const size_t np = (size_t)c->npad;
     for (double *&p : s.msg) {

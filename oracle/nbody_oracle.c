@@ -230,8 +230,18 @@ static void bond_i(double *dv, const double *rs, int64_t i, const double *ms, do
 /* valence_angle_potential_acceleration! -- src/basic_potentials.jl:395-433
  * (a=H1, b=O, c=H2; src/nbody_to_ode.jl:255-260).  normalize(v) = inv(norm(v))*v
  * [upstream StaticArrays, unverified]. Adds into three columns of the full dv. */
+static void angle_abc_to(double *da, double *db, double *dc, const double *rs, int64_t a, int64_t b, int64_t c,
+                         const double *ms, double ka, double aHOH0);
+
 static void angle_abc(double *dv, const double *rs, int64_t a, int64_t b, int64_t c,
                       const double *ms, double ka, double aHOH0)
+{
+    angle_abc_to(dv + 3 * a, dv + 3 * b, dv + 3 * c, rs, a, b, c, ms, ka, aHOH0);
+}
+
+/* same arithmetic, the three columns it adds into given explicitly (for target subsets) */
+static void angle_abc_to(double *da, double *db, double *dc, const double *rs, int64_t a, int64_t b, int64_t c,
+                         const double *ms, double ka, double aHOH0)
 {
     const double *ra = rs + 3 * a, *rb = rs + 3 * b, *rc = rs + 3 * c;
     double rba[3], rbc[3], rcb[3], X[3], pa[3], pc[3];
@@ -250,9 +260,9 @@ static void angle_abc(double *dv, const double *rs, int64_t a, int64_t b, int64_
         const double fa = pa[k] * force / nba;
         const double fc = pc[k] * force / nbc;
         const double fb = -(fa + fc);
-        dv[3 * a + k] += fa / ms[a];
-        dv[3 * b + k] += fb / ms[b];
-        dv[3 * c + k] += fc / ms[c];
+        da[k] += fa / ms[a];
+        db[k] += fb / ms[b];
+        dc[k] += fc / ms[c];
     }
 }
 
@@ -332,6 +342,25 @@ ORC_API void orc_accel_targets(const orc_system *s, const double *u, const int64
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
 #endif
     for (int64_t t = 0; t < nt; ++t) accel_column(s, u, targets[t], out + 3 * t);
+    (void)nthreads;
+}
+
+/* Water: full accelerations (pair terms, bonds AND the per-molecule angle term, src/nbody_to_ode.jl:502-532)
+ * of a list of whole molecules.  out is 3 x (3 nm): columns O, H1, H2 of each listed molecule. */
+ORC_API void orc_accel_molecules(const orc_system *s, const double *u, const int64_t *mols, int64_t nm,
+                                 double *out, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 2) num_threads(nthreads)
+#endif
+    for (int64_t t = 0; t < nm; ++t) {
+        const int64_t o = 3 * mols[t];
+        double *a = out + 9 * t;
+        for (int k = 0; k < 3; ++k) accel_column(s, u, o + k, a + 3 * k);
+        if (s->water && s->has_spcfw)
+            angle_abc_to(a + 3, a, a + 6, u, o + 1, o, o + 2, s->ms, s->k_angle, s->aHOH);
+    }
     (void)nthreads;
 }
 

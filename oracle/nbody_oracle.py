@@ -57,6 +57,8 @@ def lib():
         sp = C.POINTER(OrcSystem)
         L.orc_accel_targets.argtypes = [sp, dp, ip64, C.c_int64, dp, C.c_int]
         L.orc_accel_targets.restype = None
+        L.orc_accel_molecules.argtypes = [sp, dp, ip64, C.c_int64, dp, C.c_int]
+        L.orc_accel_molecules.restype = None
         L.orc_rhs.argtypes = [sp, dp, dp, dp, C.c_int]
         L.orc_rhs.restype = None
         L.orc_gravity_targets_ld.argtypes = [dp, dp, C.c_int64, C.c_double, ip64, C.c_int64, dp, C.c_int]
@@ -169,6 +171,15 @@ class System:
         out = np.zeros((3, t.shape[0]), order="F")
         lib().orc_accel_targets(C.byref(self.c), _dp(u), t.ctypes.data_as(C.POINTER(C.c_int64)),
                                 t.shape[0], _dp(out), int(nthreads))
+        return out
+
+    def accel_molecules(self, u, mols, nthreads=1):
+        """Water: full accelerations (incl. the angle term) of whole molecules; 3 x (3 len(mols))."""
+        u = _f(u)
+        t = np.ascontiguousarray(mols, dtype=np.int64)
+        out = np.zeros((3, 3 * t.shape[0]), order="F")
+        lib().orc_accel_molecules(C.byref(self.c), _dp(u), t.ctypes.data_as(C.POINTER(C.c_int64)), t.shape[0], _dp(out),
+                                  int(nthreads))
         return out
 
     def rhs(self, u, v, nthreads=1):

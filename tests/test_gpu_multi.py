@@ -22,3 +22,16 @@ def test_sharded_stepper_matches_single_gpu(n):
            "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "tests", "mgpu_worker.py"), str(n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_slab_stepper_matches_single_gpu():
+    import torch
+
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if ng < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29643", os.path.join(ROOT, "tests", "mgpu_worker.py"), "slab", "16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -348,6 +348,43 @@ def test_water_cell_list_cutoffs(oracle):
     _check(a, ref)
 
 
+def test_lj_config3_full_size_subsample(oracle):
+    """BASELINE config 3 at full size (1,048,576 argon atoms, 48^3 cells): 768 targets against all atoms through
+    the reference's O(N) loop, neighbour counts of the same targets, and Newton's third law over the box."""
+    w = wl.fcc_argon_reduced(64)
+    rng = np.random.Generator(np.random.Philox(2))
+    u = F(w["u"] + 0.05 * rng.standard_normal(w["u"].shape))
+    n = u.shape[1]
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert ctx.info("cells_lj") == 48 ** 3
+    targets = np.sort(np.random.Generator(np.random.Philox(9)).choice(n, 768, replace=False))
+    s = make_oracle(oracle, spec)
+    ref = s.accel_targets(u, targets, NT)
+    err = rel_err_per_body(a[:, targets], ref)
+    assert err.max() <= TOL, err.max()
+    p = (a * w["ms"]).sum(axis=1)
+    assert (np.abs(p) <= 1e-11 * np.abs(a * w["ms"]).sum(axis=1)).all()
+    ctx.upload(u, w["v"])
+    off, lst = ctx.neighbors(cap=64 * n)
+    for i in targets[::16]:
+        assert np.array_equal(lst[off[i]:off[i + 1]], s.neighbors(u, int(i), w["lj"]["R"]))
+
+
+def test_water_config4_full_size_subsample(oracle):
+    """BASELINE config 4 at full size (32,768 SPC/Fw molecules = 98,304 atoms), variant B (Rel = 0.9162 nm,
+    cell lists for both pair terms): 300 target atoms (100 whole molecules) against the oracle."""
+    w, u, spec = _water(32, 4, Rel=0.9162)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert ctx.info("cells_lj") > 0 and ctx.info("cells_el") > 0
+    mols = np.sort(np.random.Generator(np.random.Philox(3)).choice(w["nmol"], 100, replace=False))
+    targets = (3 * mols[:, None] + np.arange(3)[None, :]).ravel()
+    ref = make_oracle(oracle, spec).accel_molecules(u, mols, NT)
+    _check(a[:, targets], ref)
+
+
 # ------------------------------------------------------------------------------------------
 # RHS thermostats (src/thermostats.jl:76-91, :121-128)
 # ------------------------------------------------------------------------------------------

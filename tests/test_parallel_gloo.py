@@ -146,3 +146,176 @@ def test_two_rank_velocity_verlet_matches_serial(tmp_path, n, mode):
     mv2 = float(np.dot(ms, (vr ** 2).sum(axis=0)))
     for r in range(world):                              # all-reduced sum m v^2 = the global value on every rank
         assert np.load(tmp_path / f"scal{r}.npy")[0] == pytest.approx(mv2, rel=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# slab decomposition: parallel.SlabStepper over gloo with a NumPy engine (forces from the oracle)
+# ------------------------------------------------------------------------------------------------
+class NumpySlabEngine:
+    """Host restatement of the slab protocol of csrc/nbx_slab.cu behind the SlabStepper duck type:
+    own particles of the x-layers [c0, c1) + ghost copies of the adjacent layers; one message per
+    neighbour per step = [n_migrants, n_halo, migrant records (id x v a m), halo records (id x)]."""
+
+    MIG, HALO = 11, 4
+
+    def __init__(self, w, u, v, thermostat=None):
+        import torch
+
+        from oracle import nbody_oracle as orc
+
+        self.torch, self.orc, self.w = torch, orc, w
+        self.n_total = u.shape[1]
+        self.L, self.R = w["L"], w["lj"]["R"]
+        self.nc = int(np.floor(self.L / (self.R * (1 + 1e-6))))
+        self.th = thermostat
+        self.needs_temperature = thermostat is not None
+        full = orc.System(w["ms"], bc=("cubic", self.L), lj=w["lj"])
+        self.gid = np.arange(self.n_total)
+        self.pos, self.vel = np.array(u), np.array(v)
+        self.mass = np.array(w["ms"], dtype=np.float64)
+        self.acc = full.rhs(np.asfortranarray(u), np.asfortranarray(v), 2)
+        self.scal_np = np.zeros(16)
+        self.scal_np[0] = float(np.dot(self.mass, (self.vel ** 2).sum(axis=0)))
+        self._scal = torch.from_numpy(self.scal_np)
+        if thermostat:
+            self.acc += self._berendsen() * self.vel
+        cap = 2 + self.n_total * (self.MIG + self.HALO)
+        self.bufs = [torch.zeros(cap, dtype=torch.float64) for _ in range(4)]
+
+    def _berendsen(self):
+        T = self.scal_np[0] / (self.th["kB"] * 3 * self.n_total)
+        return 0.5 / self.th["tau"] * (self.th["T"] / T - 1.0)
+
+    def _layer(self, x):
+        wv = x - self.L * np.floor(x / self.L)
+        return np.clip((wv * (self.nc / self.L)).astype(int), 0, self.nc - 1)
+
+    def scalars(self):
+        return self._scal
+
+    def slab_buffers(self):
+        return self.bufs
+
+    def slab_init(self, rank, world):
+        lo = lambda r: r * self.nc // world
+        self.c0, self.c1 = lo(rank), lo(rank + 1)
+        self._pack(init=True)
+
+    def slab_pack(self):
+        self._pack(init=False)
+
+    def _pack(self, init):
+        rel = (self._layer(self.pos[0]) - self.c0) % self.nc
+        width = self.c1 - self.c0
+        stay = rel < width
+        left = ~stay & ((self.nc - rel) <= (rel - width + 1)) & (not init)
+        right = ~stay & ~left & (not init)
+        for buf, mig, halo in ((self.bufs[0], left, stay & (rel == 0)), (self.bufs[1], right, stay & (rel == width - 1))):
+            rec = np.concatenate([self.gid[mig][None].astype(float), self.pos[:, mig], self.vel[:, mig], self.acc[:, mig],
+                                  self.mass[mig][None]]).T.ravel()
+            hrec = np.concatenate([self.gid[halo][None].astype(float), self.pos[:, halo]]).T.ravel()
+            out = np.concatenate([[mig.sum(), halo.sum()], rec, hrec])
+            buf.zero_()
+            buf[:out.size] = self.torch.from_numpy(out)
+        self.kept = [np.concatenate([self.gid[m][None].astype(float), self.pos[:, m]]) for m in (left, right)]
+        for name in ("gid", "mass"):
+            setattr(self, name, getattr(self, name)[stay])
+        for name in ("pos", "vel", "acc"):
+            setattr(self, name, getattr(self, name)[:, stay])
+
+    def slab_unpack(self):
+        nstay = self.gid.size
+        ghosts = list(self.kept)
+        arrivals = []
+        for buf in (self.bufs[2], self.bufs[3]):
+            b = buf.numpy()
+            nm, nh = int(b[0]), int(b[1])
+            rec = b[2:2 + nm * self.MIG].reshape(nm, self.MIG).T
+            hrec = b[2 + nm * self.MIG:2 + nm * self.MIG + nh * self.HALO].reshape(nh, self.HALO).T
+            arrivals.append(rec)
+            ghosts.append(hrec)
+        for rec in arrivals:
+            self.gid = np.concatenate([self.gid, rec[0].astype(int)])
+            self.pos = np.concatenate([self.pos, rec[1:4]], axis=1)
+            self.vel = np.concatenate([self.vel, rec[4:7]], axis=1)
+            self.acc = np.concatenate([self.acc, rec[7:10]], axis=1)
+            self.mass = np.concatenate([self.mass, rec[10]])
+        self.ghost_gid = np.concatenate([g[0].astype(int) for g in ghosts])
+        self.ghost_pos = np.concatenate([g[1:4] for g in ghosts], axis=1)
+        return [self.gid.size, self.ghost_gid.size, self.kept[0].shape[1], self.kept[1].shape[1], arrivals[0].shape[1],
+                arrivals[1].shape[1]]
+
+    def vv_begin(self, dt):
+        self.pos = self.pos + dt * self.vel + 0.5 * dt * dt * self.acc
+
+    def vv_forces(self):
+        self.acc_old = self.acc
+        m = self.gid.size
+        x = np.asfortranarray(np.concatenate([self.pos, self.ghost_pos], axis=1))
+        ms = np.concatenate([self.mass, np.ones(self.ghost_gid.size)])
+        local = self.orc.System(ms, bc=("cubic", self.L), lj=self.w["lj"])
+        self.acc = local.accel_targets(x, np.arange(m))
+
+    def vv_finish(self, dt):
+        if self.th:
+            self.acc = self.acc + self._berendsen() * self.vel
+        self.vel = self.vel + 0.5 * dt * (self.acc_old + self.acc)
+        self.scal_np[0] = float(np.dot(self.mass, (self.vel ** 2).sum(axis=0)))
+
+    def slab_download(self):
+        return self.gid.copy(), self.pos.copy(), self.vel.copy(), self.acc.copy()
+
+
+def _slab_setup(thermo):
+    import nbody_b200.workloads as wl
+
+    w = wl.fcc_argon_reduced(5)  # 500 atoms, L = 8.55 sigma
+    w["lj"] = dict(w["lj"], R=1.9)  # 4 cell layers -> 2 slabs of 2
+    rng = np.random.Generator(np.random.Philox(8))
+    u = np.asfortranarray(w["u"] + 0.05 * rng.standard_normal(w["u"].shape))
+    v = np.asfortranarray(4.0 * w["v"])
+    th = dict(kind="berendsen", T=90.0, tau=0.05, kB=w["kB"]) if thermo else None
+    return w, u, v, th, 4e-3, 25
+
+
+def _slab_worker(rank, world, port, out_dir, thermo):
+    import torch.distributed as dist
+
+    from nbody_b200.parallel import SlabStepper
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    w, u, v, th, dt, steps = _slab_setup(thermo)
+    eng = NumpySlabEngine(w, u, v, th)
+    st = SlabStepper(eng)
+    moved = 0
+    for _ in range(steps):
+        st.step(dt, 1)
+        moved += st.counts[2] + st.counts[3]
+    ug, vg, ag = st.gather(u.shape[1])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "u.npy"), ug)
+        np.save(os.path.join(out_dir, "v.npy"), vg)
+    np.save(os.path.join(out_dir, f"moved{rank}.npy"), np.array([moved, st.counts[0], st.counts[1]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("thermo", [False, True])
+def test_two_rank_slab_stepper_matches_serial(tmp_path, thermo):
+    import torch.multiprocessing as mp
+
+    from oracle import nbody_oracle as orc
+    from tests._common import make_oracle
+
+    world = 2
+    mp.spawn(_slab_worker, args=(world, _free_port(), str(tmp_path), thermo), nprocs=world, join=True)
+    w, u, v, th, dt, steps = _slab_setup(thermo)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    if th:
+        spec["thermostat"] = th
+    ur, vr = orc.velocity_verlet(make_oracle(orc, spec), u, v, dt, steps)
+    moved = [np.load(tmp_path / f"moved{r}.npy") for r in range(world)]
+    assert sum(m[0] for m in moved) > 0                      # particles crossed slab faces
+    assert sum(m[1] for m in moved) == u.shape[1]            # ownership stays a partition
+    assert all(m[2] > 0 for m in moved)                      # both slabs hold ghosts
+    assert np.allclose(np.load(tmp_path / "u.npy"), ur, rtol=1e-11, atol=1e-13)
+    assert np.allclose(np.load(tmp_path / "v.npy"), vr, rtol=1e-10, atol=1e-12)
