@@ -181,10 +181,15 @@ NBX_API int nbx_neighbors(nbx_ctx *ctx, int64_t *offsets, int32_t *list, int64_t
  * nbx_vv_finish; all-reduce of the scalar block's [0] (sum m v^2) when a thermostat is set.
  * Exchange: buffer 0 (send-to-left) -> buffer 3 (recv-from-right) of the left neighbour,
  *           buffer 1 (send-to-right) -> buffer 2 (recv-from-left) of the right neighbour; periodic.
- * nbx_slab_unpack synchronises the stream; counts[6] = own, ghosts, migrated out left/right, in from left/right. */
+ * The particle counts stay on the device: a step is a pure stream of launches (capturable in a CUDA graph
+ * with the exchange).  nbx_slab_unpack(counts = NULL) is asynchronous; errors (a particle that jumped past
+ * the neighbouring slab, a full buffer) accumulate and are reported by the next nbx_slab_check, by
+ * nbx_slab_unpack with counts != NULL, or by nbx_slab_download -- all three synchronise the stream.
+ * counts[6] = own, ghosts, migrated out left/right, in from left/right (of the last step). */
 NBX_API int nbx_slab_init(nbx_ctx *ctx, int rank, int nranks);
 NBX_API int nbx_slab_pack(nbx_ctx *ctx);
 NBX_API int nbx_slab_unpack(nbx_ctx *ctx, int64_t *counts);
+NBX_API int nbx_slab_check(nbx_ctx *ctx, int64_t *counts);
 /* which = 0 send-to-left, 1 send-to-right, 2 recv-from-left, 3 recv-from-right; device memory of
  * *ndoubles doubles each, owned by the context. */
 NBX_API int nbx_slab_buffer(nbx_ctx *ctx, int which, void **ptr, int64_t *ndoubles);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "nbx_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
     "nbx_slab_pack": (C.c_int, [_vp]),
     "nbx_slab_unpack": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "nbx_slab_check": (C.c_int, [_vp, C.POINTER(_i64)]),
     "nbx_slab_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
     "nbx_slab_download": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), _dp, _dp, _dp]),
     "nbx_set_stream": (C.c_int, [_vp, _vp]),
@@ -253,9 +254,18 @@ class Context:
     def slab_pack(self):
         self._ck(self.lib.nbx_slab_pack(self.h))
 
-    def slab_unpack(self):
+    def slab_unpack(self, sync=True):
+        """sync=False: asynchronous (no host round trip); errors surface at the next slab_check()."""
+        if not sync:
+            self._ck(self.lib.nbx_slab_unpack(self.h, None))
+            return None
         counts = (_i64 * 6)()
         self._ck(self.lib.nbx_slab_unpack(self.h, counts))
+        return [int(x) for x in counts]
+
+    def slab_check(self):
+        counts = (_i64 * 6)()
+        self._ck(self.lib.nbx_slab_check(self.h, counts))
         return [int(x) for x in counts]
 
     def slab_buffer(self, which):

@@ -502,6 +502,12 @@ int nbx_slab_unpack(nbx_ctx *c, int64_t *counts)
     return slab_unpack(c, counts);
 }
 
+int nbx_slab_check(nbx_ctx *c, int64_t *counts)
+{
+    NBX_TRY(guard(c));
+    return slab_check(c, counts);
+}
+
 int nbx_slab_buffer(nbx_ctx *c, int which, void **ptr, int64_t *ndoubles)
 {
     NBX_TRY(guard(c));
@@ -516,6 +522,7 @@ int nbx_slab_download(nbx_ctx *c, int64_t *n_own, int32_t *gid, double *u, doubl
 {
     NBX_TRY(guard(c));
     if (!c->slab.on || c->slab.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_download: no complete slab state");
+    NBX_TRY(slab_check(c, nullptr));
     const int64_t m = c->slab.n_own;
     const size_t bytes = sizeof(double) * 3 * (size_t)m;
     if (n_own) *n_own = m;

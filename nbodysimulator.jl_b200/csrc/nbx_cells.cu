@@ -70,10 +70,11 @@ __device__ __forceinline__ int cell_coord(double x, double L, int nc)
 }
 
 __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n, double L, int nc,
-                               int *__restrict__ cell_of, int *__restrict__ arrival, int *__restrict__ count)
+                               int *__restrict__ cell_of, int *__restrict__ arrival, int *__restrict__ count,
+                               const int *__restrict__ dyn)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= dyn_loc(dyn, n)) return;
     const int cx = cell_coord(px[i], L, nc), cy = cell_coord(px[ld + i], L, nc), cz = cell_coord(px[2 * ld + i], L, nc);
     const int cid = (cz * nc + cy) * nc + cx; // x fastest: the three x-neighbours of a cell are contiguous
     cell_of[i] = cid;
@@ -160,10 +161,10 @@ __global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restr
 // slot = cell start + arrival rank (no atomics); the ordering key travels with the index
 __global__ void scatter_kernel(const int *__restrict__ cell_of, const int *__restrict__ arrival,
                                const int *__restrict__ gid, int n, const int *__restrict__ start,
-                               int *__restrict__ tmp_idx, int *__restrict__ tmp_key)
+                               int *__restrict__ tmp_idx, int *__restrict__ tmp_key, const int *__restrict__ dyn)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= dyn_loc(dyn, n)) return;
     const int slot = start[cell_of[i]] + arrival[i];
     tmp_idx[slot] = i;
     if (gid) tmp_key[slot] = gid[i];
@@ -179,10 +180,10 @@ __global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, co
                                    const int *__restrict__ tmp_idx, const int *__restrict__ tmp_key,
                                    const int *__restrict__ cell_of, const int *__restrict__ start, int n, double L,
                                    int nc, int key_div, int *__restrict__ sorted_idx, double4 *__restrict__ sp4,
-                                   float4 *__restrict__ sl4, int *__restrict__ scell)
+                                   float4 *__restrict__ sl4, int *__restrict__ scell, const int *__restrict__ dyn)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= dyn_loc(dyn, n)) return;
     const int i = tmp_idx[k];
     const int cid = cell_of[i];
     const int b = start[cid], e = start[cid + 1];
@@ -237,15 +238,15 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, con
     timer_begin(c, NBX_T_CELL_BUILD);
     cudaMemsetAsync(cl->count, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
     cell_id_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
-                                                           cl->count);
+                                                           cl->count, c->dyn);
     scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums);
     scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb);
     scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb);
     scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
-                                                           cl->tmp_key);
+                                                           cl->tmp_key, c->dyn);
     rank_gather_kernel<<<(ni + 127) / 128, 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
                                                                cl->cell_of, cl->start, ni, g.len[0], g.nc[0], key_div,
-                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell);
+                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn);
     timer_end(c, NBX_T_CELL_BUILD);
     NBX_CUDA(c, cudaGetLastError());
     cl->n = n;
@@ -325,12 +326,13 @@ template <int POT, int EXCL>
 __global__ void __launch_bounds__(128) cell_force_kernel(const CellPairArgs a, double scale,
                                                          const double *__restrict__ mass, int mstride,
                                                          const double *__restrict__ charge, int lo, int hi,
-                                                         double *__restrict__ acc, int64_t ld, int accumulate)
+                                                         double *__restrict__ acc, int64_t ld, int accumulate,
+                                                         const int *__restrict__ dyn)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
+    if (k >= dyn_loc(dyn, a.n)) return;
     const int i = a.sorted_idx[k];
-    if (i < lo || i >= hi) return;
+    if (i < lo || i >= (dyn ? min(hi, dyn[0]) : hi)) return;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
     int cnt = 0;
     const double4 pi = a.sp4[k];
@@ -402,17 +404,20 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
                                                           const double *__restrict__ charge, int lo, int hi,
                                                           double *__restrict__ acc, int64_t ld, int accumulate,
                                                           int *__restrict__ counts, const int64_t *__restrict__ offsets,
-                                                          int32_t *__restrict__ list)
+                                                          int32_t *__restrict__ list, const int *__restrict__ dyn)
 {
     __shared__ int q[kQCap * 128];
+    const int n_loc = dyn_loc(dyn, a.n);
+    if (blockIdx.x * 128 >= n_loc) return; // launch bound beyond the actual count (whole block)
+    if (dyn) hi = min(hi, dyn[0]);
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
     const int k = blockIdx.x * 128 + tid;
-    const int kk = k < a.n ? k : a.n - 1;
+    const int kk = k < n_loc ? k : n_loc - 1;
     const float4 me = a.sl4[kk];
     const int key = __float_as_int(me.w);
     const int i = a.sorted_idx[kk];
-    const bool live = k < a.n && i >= lo && i < hi;
+    const bool live = k < n_loc && i >= lo && i < hi;
     const double4 pi = a.sp4[kk];
     const int cid = a.scell[kk];
     const int nc = a.nc;
@@ -573,24 +578,24 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
             const CellPairArgs a = make_args(c, cl, c->lj_R2);
             cell_pairs2_kernel<0, 0><<<blocks, 128, 0, c->stream>>>(a, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
                                                                   (int)lo, (int)hi, acc_out, ld_out, acc_flag, nullptr,
-                                                                  nullptr, nullptr);
+                                                                  nullptr, nullptr, c->dyn);
         } else { // the exclusion (self / own molecule) was fixed when the list was built (key_div)
             const CellPairArgs a = make_args(c, cl, c->el_R2);
             cell_pairs2_kernel<1, 0><<<blocks, 128, 0, c->stream>>>(a, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi,
-                                                                  acc_out, ld_out, acc_flag, nullptr, nullptr, nullptr);
+                                                                  acc_out, ld_out, acc_flag, nullptr, nullptr, nullptr, c->dyn);
         }
     } else if (pot == 0) {
         const CellPairArgs a = make_args(c, cl, c->lj_R2);
         cell_force_kernel<0, 0><<<blocks, 128, 0, c->stream>>>(a, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
-                                                             (int)lo, (int)hi, acc_out, ld_out, acc_flag);
+                                                             (int)lo, (int)hi, acc_out, ld_out, acc_flag, c->dyn);
     } else if (pot == 1) {
         const CellPairArgs a = make_args(c, cl, c->el_R2);
         cell_force_kernel<1, 0><<<blocks, 128, 0, c->stream>>>(a, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi,
-                                                             acc_out, ld_out, acc_flag);
+                                                             acc_out, ld_out, acc_flag, c->dyn);
     } else {
         const CellPairArgs a = make_args(c, cl, c->el_R2);
         cell_force_kernel<1, 1><<<blocks, 128, 0, c->stream>>>(a, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi,
-                                                             acc_out, ld_out, acc_flag);
+                                                             acc_out, ld_out, acc_flag, c->dyn);
     }
     timer_end(c, NBX_T_PAIR_CELLS);
     NBX_CUDA(c, cudaGetLastError());
@@ -649,7 +654,7 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
         a = make_args(c, cl, R2);
         if (c->opt_prefilter)
             cell_pairs2_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0, d_counts,
-                                                                  nullptr, nullptr);
+                                                                  nullptr, nullptr, nullptr);
         else
             cell_neigh_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, d_counts, nullptr, nullptr);
     } else {
@@ -675,7 +680,7 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
             cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream);
             if (use_cells && c->opt_prefilter)
                 cell_pairs2_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0,
-                                                                      d_counts, d_off, d_list);
+                                                                      d_counts, d_off, d_list, nullptr);
             else if (use_cells)
                 cell_neigh_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, d_counts, d_off, d_list);
             else

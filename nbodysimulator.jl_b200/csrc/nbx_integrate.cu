@@ -219,8 +219,9 @@ int launch_thermostat_rhs(nbx_ctx *c, double *acc, const double *vel)
 // ------------------------------------------------------------------------------------------------
 __global__ void vv_pos_kernel(double *__restrict__ pos, const double *__restrict__ vel, const double *__restrict__ acc,
                               int64_t ld, int64_t lo, int64_t hi, double dt, double hdt2, double *__restrict__ scal,
-                              int nose)
+                              int nose, const int *__restrict__ dyn)
 {
+    if (dyn) hi = min(hi, lo + (int64_t)dyn[0]);
     for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -239,8 +240,9 @@ template <bool BEREND>
 __global__ void vv_vel_kernel(double *__restrict__ vel, const double *__restrict__ a_old, double *__restrict__ a_new,
                               const double *__restrict__ mass, int64_t ld, int64_t lo, int64_t hi, double hdt,
                               double *__restrict__ partial, const double *__restrict__ scal, double kB, double ndf,
-                              double T0, double gamma)
+                              double T0, double gamma, const int *__restrict__ dyn)
 {
+    if (dyn) hi = min(hi, lo + (int64_t)dyn[0]);
     double sc = 0.0;
     if (BEREND) {
         const double T = scal[0] / (kB * ndf);
@@ -274,7 +276,7 @@ int launch_vv_pos(nbx_ctx *c, double dt)
     const int nb = red_blocks(c, hi - lo);
     timer_begin(c, NBX_T_INTEGRATE);
     vv_pos_kernel<<<nb, kRedThreads, 0, c->stream>>>(c->pos, c->vel, c->acc, c->npad, lo, hi, dt, 0.5 * dt * dt,
-                                                    c->d_scal, c->thermo == NBX_THERMO_NOSEHOOVER ? 1 : 0);
+                                                    c->d_scal, c->thermo == NBX_THERMO_NOSEHOOVER ? 1 : 0, c->dyn);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
@@ -296,10 +298,10 @@ int launch_vv_vel(nbx_ctx *c, double dt, bool with_thermostat)
     if (fused)
         vv_vel_kernel<true><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
                                                               0.5 * dt, c->d_red, c->d_scal, c->kB, ndf, c->T0,
-                                                              0.5 / c->tparam);
+                                                              0.5 / c->tparam, c->dyn);
     else
         vv_vel_kernel<false><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
-                                                               0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0);
+                                                               0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0, c->dyn);
     final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());

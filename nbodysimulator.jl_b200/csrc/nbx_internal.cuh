@@ -54,7 +54,10 @@ struct SlabState {
     bool on = false, packed = false;
     int rank = 0, nranks = 1;
     int nc = 0, c0 = 0, c1 = 0, wL = 0, wR = 0; // layers of the slab grid; own layers [c0, c1); neighbour widths
-    int64_t n_total = 0, n_own = 0, n_ghost = 0;
+    int64_t n_total = 0, n_own = 0, n_ghost = 0; // n_own / n_ghost: as of the last nbx_slab_check
+    int64_t cap_loc = 0;                         // bound on own + ghosts (launch sizes); exceeding it is an error
+    int *d_n = nullptr;                          // device: [0] own, [1] ghosts, [2] lost particles, [3] capacity errors
+    cudaEvent_t ev_counts = nullptr;             // completion of the last asynchronous count read-back
     int64_t capM = 0, capH = 0, msg_doubles = 0; // message capacities (migrants, halo records) and size
     double *msg[4] = {nullptr, nullptr, nullptr, nullptr}; // send-left, send-right, recv-from-left, recv-from-right
     double *pos2 = nullptr, *vel2 = nullptr, *acc2 = nullptr, *mass2 = nullptr, *charge2 = nullptr; // compaction targets
@@ -108,6 +111,9 @@ struct nbx_ctx {
     int64_t tgt_lo = 0, tgt_hi = 0;
     int *gid = nullptr;        // slab decomposition: global particle id per local column (nullptr: identity)
     nbx::SlabState slab;
+    // slab mode: the particle counts live on the device ([0] own, [1] ghosts) so that a step needs no host
+    // round trip; n / tgt_hi then are launch BOUNDS and every kernel clamps to the device counts
+    const int *dyn = nullptr;
 
     // ---- all-pairs scratch ----------------------------------------------------------------
     double *part = nullptr; // [nchunk][3][ntgt_pad] partial sums
@@ -194,6 +200,7 @@ void cells_free(CellList *cl);
 int slab_init(nbx_ctx *c, int rank, int nranks);
 int slab_pack(nbx_ctx *c);
 int slab_unpack(nbx_ctx *c, int64_t *counts);
+int slab_check(nbx_ctx *c, int64_t *counts);
 void slab_free(nbx_ctx *c);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);
@@ -217,6 +224,9 @@ int compute_accel(nbx_ctx *c); // pos, vel -> acc (all potentials + RHS thermost
 
 // ---- device helpers --------------------------------------------------------------------------
 #ifdef __CUDACC__
+// launch bound -> actual count (see nbx_ctx::dyn)
+__device__ __forceinline__ int dyn_own(const int *dyn, int bound) { return dyn ? min(bound, dyn[0]) : bound; }
+__device__ __forceinline__ int dyn_loc(const int *dyn, int bound) { return dyn ? min(bound, dyn[0] + dyn[1]) : bound; }
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -18,6 +18,11 @@
 //
 // Every local particle carries its global id; the cell order is ranked by that id (nbx_cells.cu), so the
 // force sums are bit-identical to the single-GPU result whatever the local numbering.
+// The particle counts never visit the host inside a step: they live in d_n ([0] own, [1] ghosts), every kernel of
+// the step is launched for the capacity bound cap_loc and clamps to d_n (nbx_ctx::dyn), and errors (a particle that
+// jumped past the neighbouring slab, a full message or state buffer) accumulate in d_n[2..3] until
+// nbx_slab_check / nbx_slab_unpack(counts != NULL) reads them.  A step is therefore a pure stream of launches
+// and copies, i.e. capturable in a CUDA graph together with the NCCL send/recv of the host layer.
 // A slab needs >= 2 layers so that one exchange per step suffices (an arrival from the left lands in the
 // leftmost layer and is a ghost of the left neighbour only, which kept it).
 #include "nbx_internal.cuh"
@@ -31,7 +36,9 @@ constexpr int kSlabBlock = 256;
 
 enum { CAT_STAY = 0, CAT_MIGL = 1, CAT_MIGR = 2, CAT_HALOL = 3, CAT_HALOR = 4, CAT_N = 5 };
 // device counters
-enum { CNT_ERR_LOST = 5, CNT_ERR_CAP = 6, CNT_OWN = 7, CNT_GHOST = 8, CNT_ARRL = 9, CNT_ARRR = 10, CNT_N = 16 };
+enum { CNT_ARRL = 5, CNT_ARRR = 6, CNT_N = 8 };
+// persistent counters d_n
+enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_N = 4 };
 
 struct SlabGeom {
     double L;
@@ -67,9 +74,11 @@ __device__ __forceinline__ unsigned slab_classify(double x, const SlabGeom &g)
 }
 
 __global__ void __launch_bounds__(kSlabBlock) slab_count_kernel(const double *__restrict__ px, int n, SlabGeom g,
-                                                                int *__restrict__ blockcnt, int *__restrict__ counts)
+                                                                int *__restrict__ blockcnt, int *__restrict__ dn,
+                                                                const int *__restrict__ dyn)
 {
     __shared__ int cnt[CAT_N];
+    n = dyn_own(dyn, n);
     if (threadIdx.x < CAT_N) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * kSlabBlock + threadIdx.x;
@@ -79,7 +88,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_count_kernel(const double *__
         const unsigned m = __ballot_sync(0xffffffffu, (f >> c) & 1u);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
     }
-    if (f & 256u) atomicAdd(&counts[CNT_ERR_LOST], 1);
+    if (f & 256u) atomicAdd(&dn[DN_LOST], 1);
     __syncthreads();
     if (threadIdx.x < CAT_N) blockcnt[blockIdx.x * CAT_N + threadIdx.x] = cnt[threadIdx.x];
 }
@@ -114,9 +123,11 @@ struct SlabArrays {
 __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, SlabArrays dst, int64_t ld, int n,
                                                                SlabGeom g, const int *__restrict__ blockoff,
                                                                int *__restrict__ counts, double *__restrict__ sendL,
-                                                               double *__restrict__ sendR, int capM, int capH)
+                                                               double *__restrict__ sendR, int capM, int capH,
+                                                               int *__restrict__ dn, const int *__restrict__ dyn)
 {
     __shared__ int wcnt[kSlabBlock / 32][CAT_N];
+    n = dyn_own(dyn, n);
     const int i = blockIdx.x * kSlabBlock + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned f = i < n ? slab_classify(src.pos[i], g) : 0u;
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
         sendL[0] = (double)min(counts[CAT_MIGL], capM); sendL[1] = (double)min(counts[CAT_HALOL], capH);
         sendR[0] = (double)min(counts[CAT_MIGR], capM); sendR[1] = (double)min(counts[CAT_HALOR], capH);
         if (counts[CAT_MIGL] > capM || counts[CAT_MIGR] > capM || counts[CAT_HALOL] > capH || counts[CAT_HALOR] > capH)
-            counts[CNT_ERR_CAP] = 1;
+            dn[DN_CAP] = 1;
     }
     if (i >= n || f == 0u) return;
     const double x = src.pos[i], y = src.pos[ld + i], z = src.pos[2 * ld + i];
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
 // segments, in the order they are laid down: arrivals (left, right) extend the own particles; the ghosts are
 // the migrants just sent (left, right) and the received halos (left, right)
 __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
+                                   int *__restrict__ dn,
                                    const double *__restrict__ sendL, const double *__restrict__ sendR,
                                    const double *__restrict__ recvL, const double *__restrict__ recvR, int capM, int capH)
 {
@@ -181,11 +193,13 @@ __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols,
     const int haloL = min((int)recvL[1], capH), haloR = min((int)recvR[1], capH);
     const int n_own = nstay + arrL + arrR;
     const int n_ghost = keptL + keptR + haloL + haloR;
+    const bool fits = (int64_t)n_own + n_ghost <= cap_cols;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        counts[CNT_OWN] = n_own; counts[CNT_GHOST] = n_ghost; counts[CNT_ARRL] = arrL; counts[CNT_ARRR] = arrR;
-        if ((int64_t)n_own + n_ghost > cap_cols) counts[CNT_ERR_CAP] = 1;
+        counts[CNT_ARRL] = arrL; counts[CNT_ARRR] = arrR;
+        dn[DN_OWN] = fits ? n_own : 0; dn[DN_GHOST] = fits ? n_ghost : 0;
+        if (!fits) dn[DN_CAP] = 1;
     }
-    if ((int64_t)n_own + n_ghost > cap_cols) return;
+    if (!fits) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int seg, idx;
     if (t < 2 * capM) { seg = t / capM; idx = t - seg * capM; }                 // 0,1: arrivals
@@ -230,9 +244,12 @@ void slab_free(nbx_ctx *c)
     for (double *&p : s.msg) { cudaFree(p); p = nullptr; }
     cudaFree(s.pos2); cudaFree(s.vel2); cudaFree(s.acc2); cudaFree(s.mass2); cudaFree(s.charge2);
     cudaFree(s.gid_a); cudaFree(s.gid_b); cudaFree(s.blockcnt); cudaFree(s.blockoff); cudaFree(s.d_counts);
+    cudaFree(s.d_n);
     if (s.h_counts) cudaFreeHost(s.h_counts);
+    if (s.ev_counts) cudaEventDestroy(s.ev_counts);
     s = SlabState{};
     c->gid = nullptr;
+    c->dyn = nullptr;
 }
 
 static SlabGeom geom(const nbx_ctx *c, int init)
@@ -253,22 +270,18 @@ static SlabArrays arrays(double *pos, double *vel, double *acc, double *mass, do
 static int run_pack(nbx_ctx *c, int init)
 {
     SlabState &s = c->slab;
-    const int n = (int)(init ? s.n_total : s.n_own);
+    const int n = (int)(init ? s.n_total : s.cap_loc); // launch bound; the kernels clamp to d_n[0] after the init
     const int nb = (n + kSlabBlock - 1) / kSlabBlock;
     const SlabGeom g = geom(c, init);
+    const int *dyn = init ? nullptr : s.d_n;
     NBX_CUDA(c, cudaMemsetAsync(s.d_counts, 0, sizeof(int) * CNT_N, c->stream));
     int *gid_dst = c->gid == s.gid_a ? s.gid_b : s.gid_a;
     const SlabArrays src = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     const SlabArrays dst = arrays(s.pos2, s.vel2, s.acc2, s.mass2, c->charge ? s.charge2 : nullptr, gid_dst);
-    if (nb > 0) {
-        slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_counts);
-        slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
-        slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0],
-                                                          s.msg[1], (int)s.capM, (int)s.capH);
-    } else {
-        NBX_CUDA(c, cudaMemsetAsync(s.msg[0], 0, sizeof(double) * kHdr, c->stream));
-        NBX_CUDA(c, cudaMemsetAsync(s.msg[1], 0, sizeof(double) * kHdr, c->stream));
-    }
+    slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_n, dyn);
+    slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
+    slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0], s.msg[1],
+                                                      (int)s.capM, (int)s.capH, s.d_n, dyn);
     NBX_CUDA(c, cudaGetLastError());
     // the compacted state is the state from here on (stream-ordered: later kernels see the new pointers)
     std::swap(c->pos, s.pos2); std::swap(c->vel, s.vel2); std::swap(c->acc, s.acc2); std::swap(c->mass, s.mass2);
@@ -281,7 +294,7 @@ static int run_pack(nbx_ctx *c, int init)
 int slab_init(nbx_ctx *c, int rank, int nranks)
 {
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: rank %d of %d", rank, nranks);
-    if (c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: already decomposed (nbx_upload resets)");
+    if (c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: already decomposed (nbx_system starts over)");
     if (c->bc_kind != NBX_BC_CUBIC) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: slabs need CubicPeriodicBoundaryConditions");
     if (c->water || c->has_grav || c->has_dip || c->has_spcfw || c->thermo == NBX_THERMO_NOSEHOOVER)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: slabs cover atomic systems with cutoff Lennard-Jones / Coulomb terms");
@@ -308,6 +321,8 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     s.capH = std::min<int64_t>(c->n, layer + layer / 2 + 1024);
     s.capM = std::min<int64_t>(c->n, layer / 8 + 1024);
     s.msg_doubles = kHdr + s.capM * kMigW + s.capH * kHaloW;
+    // own + ghosts: twice the slab's share of a uniform box (+ the ghost layers); all of it for one slab
+    s.cap_loc = nranks == 1 ? c->n : std::min<int64_t>(c->n, 2 * layer * (s.c1 - s.c0) + 2 * s.capH + 4096);
     const size_t np = (size_t)c->npad;
     for (double *&p : s.msg) {
         NBX_TRY(dev_alloc(c, &p, (size_t)s.msg_doubles));
@@ -320,16 +335,24 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     const size_t nbmax = (size_t)((c->n + kSlabBlock - 1) / kSlabBlock) + 1;
     NBX_TRY(dev_alloc(c, &s.blockcnt, nbmax * CAT_N)); NBX_TRY(dev_alloc(c, &s.blockoff, nbmax * CAT_N));
     NBX_TRY(dev_alloc(c, &s.d_counts, (size_t)CNT_N));
-    NBX_CUDA(c, cudaMallocHost((void **)&s.h_counts, sizeof(int) * CNT_N));
+    NBX_TRY(dev_alloc(c, &s.d_n, (size_t)DN_N));
+    NBX_CUDA(c, cudaMemsetAsync(s.d_n, 0, sizeof(int) * DN_N, c->stream));
+    NBX_CUDA(c, cudaMallocHost((void **)&s.h_counts, sizeof(int) * (CNT_N + DN_N)));
+    NBX_CUDA(c, cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
     // padding of the alternate rows as in nbx_system
     NBX_TRY(launch_fill(c, s.pos2, kFarAway, 3 * c->npad));
     NBX_CUDA(c, cudaMemsetAsync(s.vel2, 0, sizeof(double) * 3 * np, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(s.acc2, 0, sizeof(double) * 3 * np, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(s.mass2, 0, sizeof(double) * np, c->stream));
     s.on = true;
-    s.n_own = s.n_total; // the pack below reads the full uploaded state (ids = column numbers)
-    c->gid = nullptr;
-    return run_pack(c, 1);
+    c->gid = nullptr; // the pack below reads the full uploaded state (ids = column numbers)
+    NBX_TRY(run_pack(c, 1));
+    // from here on the counts are device-side and the host sizes are bounds
+    c->dyn = s.d_n;
+    c->n = s.cap_loc;
+    c->tgt_lo = 0;
+    c->tgt_hi = s.cap_loc;
+    return NBX_OK;
 }
 
 int slab_pack(nbx_ctx *c)
@@ -339,34 +362,43 @@ int slab_pack(nbx_ctx *c)
     return run_pack(c, 0);
 }
 
+// waits for the last asynchronous read-back and reports accumulated errors
+int slab_check(nbx_ctx *c, int64_t *out)
+{
+    SlabState &s = c->slab;
+    if (!s.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_check: call nbx_slab_init first");
+    if (s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_check: a pack is waiting for nbx_slab_unpack");
+    NBX_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, c->stream));
+    NBX_CUDA(c, cudaMemcpyAsync(s.h_counts + CNT_N, s.d_n, sizeof(int) * DN_N, cudaMemcpyDeviceToHost, c->stream));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int *h = s.h_counts, *hn = s.h_counts + CNT_N;
+    if (hn[DN_LOST] > 0)
+        return fail(c, NBX_ERR_INVALID, "slab exchange: %d particle(s) moved past the neighbouring slab in one step", hn[DN_LOST]);
+    if (hn[DN_CAP] != 0)
+        return fail(c, NBX_ERR_CAPACITY, "slab exchange: message or state capacity exceeded (last step: migrants %d/%d of %lld, "
+                    "halo %d/%d of %lld; own + ghosts bound %lld)", h[CAT_MIGL], h[CAT_MIGR], (long long)s.capM, h[CAT_HALOL],
+                    h[CAT_HALOR], (long long)s.capH, (long long)s.cap_loc);
+    s.n_own = hn[DN_OWN];
+    s.n_ghost = hn[DN_GHOST];
+    if (out) {
+        out[0] = s.n_own; out[1] = s.n_ghost; out[2] = h[CAT_MIGL]; out[3] = h[CAT_MIGR]; out[4] = h[CNT_ARRL]; out[5] = h[CNT_ARRR];
+    }
+    return NBX_OK;
+}
+
+// counts == NULL: asynchronous (errors surface at the next nbx_slab_check); else also synchronise and report
 int slab_unpack(nbx_ctx *c, int64_t *out)
 {
     SlabState &s = c->slab;
     if (!s.on || !s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_unpack: nothing was packed");
     const int64_t threads = 4 * s.capM + 2 * s.capH;
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
-    slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.n_total, s.d_counts, s.msg[0],
-                                                                              s.msg[1], s.msg[2], s.msg[3], (int)s.capM,
-                                                                              (int)s.capH);
+    slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.cap_loc, s.d_counts, s.d_n,
+                                                                              s.msg[0], s.msg[1], s.msg[2], s.msg[3],
+                                                                              (int)s.capM, (int)s.capH);
     NBX_CUDA(c, cudaGetLastError());
-    NBX_CUDA(c, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, c->stream));
-    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     s.packed = false;
-    const int *h = s.h_counts;
-    if (h[CNT_ERR_LOST] > 0)
-        return fail(c, NBX_ERR_INVALID, "slab exchange: %d particle(s) moved past the neighbouring slab in one step", h[CNT_ERR_LOST]);
-    if (h[CNT_ERR_CAP] != 0)
-        return fail(c, NBX_ERR_CAPACITY, "slab exchange: message or state capacity exceeded (migrants %d/%d, halo %d/%d of %lld/%lld)",
-                    h[CAT_MIGL], h[CAT_MIGR], h[CAT_HALOL], h[CAT_HALOR], (long long)s.capM, (long long)s.capH);
-    s.n_own = h[CNT_OWN];
-    s.n_ghost = h[CNT_GHOST];
-    c->n = s.n_own + s.n_ghost;
-    c->tgt_lo = 0;
-    c->tgt_hi = s.n_own;
-    if (out) {
-        out[0] = s.n_own; out[1] = s.n_ghost; out[2] = h[CAT_MIGL]; out[3] = h[CAT_MIGR]; out[4] = h[CNT_ARRL]; out[5] = h[CNT_ARRR];
-    }
-    return NBX_OK;
+    return out ? slab_check(c, out) : NBX_OK;
 }
 
 } // namespace nbx

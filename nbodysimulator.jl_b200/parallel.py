@@ -119,8 +119,11 @@ class CudaEngine:
     def slab_pack(self):
         self.ctx.slab_pack()
 
-    def slab_unpack(self):
-        return self.ctx.slab_unpack()
+    def slab_unpack(self, sync=True):
+        return self.ctx.slab_unpack(sync)
+
+    def slab_check(self):
+        return self.ctx.slab_check()
 
     def slab_download(self):
         return self.ctx.slab_download()
@@ -244,17 +247,24 @@ class SlabStepper:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
-    def step(self, dt: float, nsteps: int = 1):
+    def _one_step(self, dt):
         e = self.engine
+        e.vv_begin(dt)
+        e.slab_pack()
+        self._exchange()
+        e.slab_unpack(sync=False)  # counts stay on the device: no host round trip inside a step
+        e.vv_forces()
+        e.vv_finish(dt)
+        if e.needs_temperature and self.world > 1:
+            self.dist.all_reduce(e.scalars()[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, dt: float, nsteps: int = 1, check: bool = True):
+        """nsteps velocity-Verlet steps, enqueued without host synchronisation; ``check`` then waits and raises
+        if any step lost a particle or overflowed a buffer (``self.counts`` = counts of the last step)."""
         for _ in range(nsteps):
-            e.vv_begin(dt)
-            e.slab_pack()
-            self._exchange()
-            self.counts = e.slab_unpack()
-            e.vv_forces()
-            e.vv_finish(dt)
-            if e.needs_temperature and self.world > 1:
-                self.dist.all_reduce(e.scalars()[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
+            self._one_step(dt)
+        if check:
+            self.counts = self.engine.slab_check()
 
     def gather(self, n_total: int):
         """(u, v, dv) of the whole system in the original column order, on every rank (host arrays;

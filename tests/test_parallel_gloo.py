@@ -223,7 +223,10 @@ class NumpySlabEngine:
         for name in ("pos", "vel", "acc"):
             setattr(self, name, getattr(self, name)[:, stay])
 
-    def slab_unpack(self):
+    def slab_check(self):
+        return self._counts
+
+    def slab_unpack(self, sync=True):
         nstay = self.gid.size
         ghosts = list(self.kept)
         arrivals = []
@@ -242,8 +245,9 @@ class NumpySlabEngine:
             self.mass = np.concatenate([self.mass, rec[10]])
         self.ghost_gid = np.concatenate([g[0].astype(int) for g in ghosts])
         self.ghost_pos = np.concatenate([g[1:4] for g in ghosts], axis=1)
-        return [self.gid.size, self.ghost_gid.size, self.kept[0].shape[1], self.kept[1].shape[1], arrivals[0].shape[1],
-                arrivals[1].shape[1]]
+        self._counts = [self.gid.size, self.ghost_gid.size, self.kept[0].shape[1], self.kept[1].shape[1],
+                        arrivals[0].shape[1], arrivals[1].shape[1]]
+        return self._counts
 
     def vv_begin(self, dt):
         self.pos = self.pos + dt * self.vel + 0.5 * dt * dt * self.acc
