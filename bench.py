@@ -234,6 +234,8 @@ def lj_secondary(local, world, steps, warmup, cells=LJ_CELLS):
     }
     if stepper is not None:
         out["rank0_own"], out["rank0_ghosts"] = stepper.counts[0], stepper.counts[1]
+        out["exchange"] = ("direct: the pack kernel stores migrants + halo into the neighbours' receive areas over NVLink "
+                           "(CUDA IPC peer memory) and raises their flags" if stepper.direct else "NCCL send/recv of the message buffers")
     ctx.close()
     return out
 

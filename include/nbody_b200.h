@@ -175,8 +175,9 @@ NBX_API int nbx_neighbors(nbx_ctx *ctx, int64_t *offsets, int32_t *list, int64_t
  *
  * nbx_slab_init: every rank has described and uploaded the FULL system (nbx_system, nbx_upload).
  * Rank `rank` of `nranks` keeps the particles of its layers (with their a(0)), records their global
- * ids (= column numbers of the upload), and fills its two send buffers with the halo of the boundary
- * layers.  The host then exchanges the buffers and calls nbx_slab_unpack.  Needs >= 2 layers per slab.
+ * ids (= column numbers of the upload); the first nbx_slab_pack then selects the own particles and
+ * fills the two send buffers with the halo of the boundary layers, the host exchanges the buffers and
+ * calls nbx_slab_unpack.  Needs >= 2 layers per slab.
  * One velocity-Verlet step:  nbx_vv_begin; nbx_slab_pack; exchange; nbx_slab_unpack; nbx_vv_forces;
  * nbx_vv_finish; all-reduce of the scalar block's [0] (sum m v^2) when a thermostat is set.
  * Exchange: buffer 0 (send-to-left) -> buffer 3 (recv-from-right) of the left neighbour,
@@ -190,8 +191,17 @@ NBX_API int nbx_slab_init(nbx_ctx *ctx, int rank, int nranks);
 NBX_API int nbx_slab_pack(nbx_ctx *ctx);
 NBX_API int nbx_slab_unpack(nbx_ctx *ctx, int64_t *counts);
 NBX_API int nbx_slab_check(nbx_ctx *ctx, int64_t *counts);
-/* which = 0 send-to-left, 1 send-to-right, 2 recv-from-left, 3 recv-from-right; device memory of
- * *ndoubles doubles each, owned by the context. */
+/* Direct exchange over NVLink peer memory (optional, between nbx_slab_init and the first nbx_slab_pack):
+ * nbx_slab_rx returns this rank's receive area (device pointer, size, and -- if ipc_handle64 != NULL -- its
+ * 64-byte CUDA IPC handle for another process).  nbx_slab_connect maps the neighbours' receive areas, given
+ * as IPC handles or, inside one process, as device pointers (pointer wins when both are set).  From then on
+ * nbx_slab_pack stores its messages straight into the neighbours' memory and raises their flags, and
+ * nbx_slab_unpack waits on its own flags on the device: no host-side exchange. */
+NBX_API int nbx_slab_rx(nbx_ctx *ctx, void **ptr, int64_t *ndoubles, void *ipc_handle64);
+NBX_API int nbx_slab_connect(nbx_ctx *ctx, const void *left_handle64, const void *right_handle64,
+                             void *left_ptr, void *right_ptr);
+/* Host-driven exchange: which = 0 send-to-left, 1 send-to-right, 2 recv-from-left, 3 recv-from-right; device
+ * memory of *ndoubles doubles each, owned by the context. */
 NBX_API int nbx_slab_buffer(nbx_ctx *ctx, int which, void **ptr, int64_t *ndoubles);
 /* The own particles of the slab: their global ids and state as 3 x n_own column-major host arrays
  * (any pointer may be NULL; capacity: the full system's column count). */

@@ -56,6 +56,8 @@ SIGNATURES = {
     "nbx_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
     "nbx_slab_pack": (C.c_int, [_vp]),
     "nbx_slab_unpack": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "nbx_slab_rx": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _vp]),
+    "nbx_slab_connect": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "nbx_slab_check": (C.c_int, [_vp, C.POINTER(_i64)]),
     "nbx_slab_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]),
     "nbx_slab_download": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), _dp, _dp, _dp]),
@@ -267,6 +269,17 @@ class Context:
         counts = (_i64 * 6)()
         self._ck(self.lib.nbx_slab_check(self.h, counts))
         return [int(x) for x in counts]
+
+    def slab_rx(self, want_handle=False):
+        """(device pointer, doubles, 64-byte CUDA IPC handle or None) of this slab's receive area."""
+        p, nd = _vp(), _i64()
+        h = C.create_string_buffer(64) if want_handle else None
+        self._ck(self.lib.nbx_slab_rx(self.h, C.byref(p), C.byref(nd), h))
+        return int(p.value), int(nd.value), (h.raw if want_handle else None)
+
+    def slab_connect(self, left_handle=None, right_handle=None, left_ptr=None, right_ptr=None):
+        self._ck(self.lib.nbx_slab_connect(self.h, left_handle, right_handle, _vp(left_ptr) if left_ptr else None,
+                                           _vp(right_ptr) if right_ptr else None))
 
     def slab_buffer(self, which):
         p, nd = _vp(), _i64()

@@ -502,6 +502,27 @@ int nbx_slab_unpack(nbx_ctx *c, int64_t *counts)
     return slab_unpack(c, counts);
 }
 
+int nbx_slab_rx(nbx_ctx *c, void **ptr, int64_t *ndoubles, void *ipc_handle64)
+{
+    NBX_TRY(guard(c));
+    if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_rx: call nbx_slab_init first");
+    if (ptr) *ptr = c->slab.rx;
+    if (ndoubles) *ndoubles = c->slab.rx_doubles;
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t h;
+        NBX_CUDA(c, cudaIpcGetMemHandle(&h, c->slab.rx));
+        static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+        memcpy(ipc_handle64, &h, sizeof h);
+    }
+    return NBX_OK;
+}
+
+int nbx_slab_connect(nbx_ctx *c, const void *left_handle64, const void *right_handle64, void *left_ptr, void *right_ptr)
+{
+    NBX_TRY(guard(c));
+    return slab_connect(c, left_handle64, right_handle64, left_ptr, right_ptr);
+}
+
 int nbx_slab_check(nbx_ctx *c, int64_t *counts)
 {
     NBX_TRY(guard(c));
@@ -513,6 +534,7 @@ int nbx_slab_buffer(nbx_ctx *c, int which, void **ptr, int64_t *ndoubles)
     NBX_TRY(guard(c));
     if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_buffer: call nbx_slab_init first");
     if (which < 0 || which > 3 || !ptr) return fail(c, NBX_ERR_INVALID, "nbx_slab_buffer: which = %d", which);
+    if (c->slab.direct) return fail(c, NBX_ERR_INVALID, "nbx_slab_buffer: the exchange is direct (nbx_slab_connect), nothing for the host to move");
     *ptr = c->slab.msg[which];
     if (ndoubles) *ndoubles = c->slab.msg_doubles;
     return NBX_OK;

@@ -51,7 +51,12 @@ struct CellList {
 
 // slab decomposition state (nbx_slab.cu)
 struct SlabState {
-    bool on = false, packed = false;
+    bool on = false, packed = false, first = false; // first: the next pack selects the slab from the full upload
+    bool direct = false;                            // neighbours' receive areas are mapped: the pack kernel stores into them
+    double *rx = nullptr;                           // receive area: flags + 4 message buffers (2 sides x 2 parities)
+    int64_t rx_doubles = 0;
+    double *peer[2] = {nullptr, nullptr};           // receive areas of the left / right neighbour (direct mode)
+    std::vector<void *> ipc_opened;
     int rank = 0, nranks = 1;
     int nc = 0, c0 = 0, c1 = 0, wL = 0, wR = 0; // layers of the slab grid; own layers [c0, c1); neighbour widths
     int64_t n_total = 0, n_own = 0, n_ghost = 0; // n_own / n_ghost: as of the last nbx_slab_check
@@ -201,6 +206,7 @@ int slab_init(nbx_ctx *c, int rank, int nranks);
 int slab_pack(nbx_ctx *c);
 int slab_unpack(nbx_ctx *c, int64_t *counts);
 int slab_check(nbx_ctx *c, int64_t *counts);
+int slab_connect(nbx_ctx *c, const void *left_handle, const void *right_handle, void *left_ptr, void *right_ptr);
 void slab_free(nbx_ctx *c);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);

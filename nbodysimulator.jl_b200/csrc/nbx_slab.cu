@@ -23,9 +23,17 @@
 // jumped past the neighbouring slab, a full message or state buffer) accumulate in d_n[2..3] until
 // nbx_slab_check / nbx_slab_unpack(counts != NULL) reads them.  A step is therefore a pure stream of launches
 // and copies, i.e. capturable in a CUDA graph together with the NCCL send/recv of the host layer.
+// Exchange, direct mode (nbx_slab_connect): the receive area of a rank (flags + 2 x 2 message buffers, double
+// buffered by message parity) is mapped into its neighbours (CUDA IPC over NVLink, or plain pointers inside one
+// process).  The pack kernel then stores its records straight into the neighbours' memory; the last block to
+// finish fences and raises the neighbours' flags, and the unpack kernel of the neighbour spins on its flags.
+// Compute and transfer are one kernel, nothing is staged, no collective library and no host in the loop.
+// Without a connection the host moves the send buffers (NCCL / gloo send-recv, or a copy) -- same layout.
 // A slab needs >= 2 layers so that one exchange per step suffices (an arrival from the left lands in the
 // leftmost layer and is a ghost of the left neighbour only, which kept it).
 #include "nbx_internal.cuh"
+
+#include <cstring>
 
 namespace nbx {
 
@@ -38,7 +46,9 @@ enum { CAT_STAY = 0, CAT_MIGL = 1, CAT_MIGR = 2, CAT_HALOL = 3, CAT_HALOR = 4, C
 // device counters
 enum { CNT_ARRL = 5, CNT_ARRR = 6, CNT_N = 8 };
 // persistent counters d_n
-enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_N = 4 };
+enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_MSG = 4, DN_TICKET = 5, DN_TIMEOUT = 6, DN_N = 8 };
+constexpr int kRxHdr = 16; // doubles in front of the receive area: [0] 'message m from the left is complete', [1] same from the right
+
 
 struct SlabGeom {
     double L;
@@ -120,14 +130,26 @@ struct SlabArrays {
     int *gid;                                // may be null: identity
 };
 
+__device__ __forceinline__ double *rx_msg(double *rx, int which, int parity, int64_t msg_doubles)
+{
+    return rx + kRxHdr + (size_t)(which * 2 + parity) * (size_t)msg_doubles; // which: 0 from-left, 1 from-right
+}
+
+// peerL / peerR: receive areas of the left / right neighbour (direct mode), else null.  A message to the left
+// lands in the left neighbour's "from-right" buffer and vice versa.
 __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, SlabArrays dst, int64_t ld, int n,
                                                                SlabGeom g, const int *__restrict__ blockoff,
                                                                int *__restrict__ counts, double *__restrict__ sendL,
                                                                double *__restrict__ sendR, int capM, int capH,
-                                                               int *__restrict__ dn, const int *__restrict__ dyn)
+                                                               int *__restrict__ dn, const int *__restrict__ dyn,
+                                                               double *peerL, double *peerR, int64_t msg_doubles)
 {
     __shared__ int wcnt[kSlabBlock / 32][CAT_N];
+    __shared__ int last_block;
     n = dyn_own(dyn, n);
+    const int msg = dn[DN_MSG] + 1; // number of the message this kernel produces (the last block publishes it)
+    double *remL = peerL ? rx_msg(peerL, 1, msg & 1, msg_doubles) : nullptr;
+    double *remR = peerR ? rx_msg(peerR, 0, msg & 1, msg_doubles) : nullptr;
     const int i = blockIdx.x * kSlabBlock + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned f = i < n ? slab_classify(src.pos[i], g) : 0u;
@@ -146,47 +168,97 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
         rank[c] += base;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sendL[0] = (double)min(counts[CAT_MIGL], capM); sendL[1] = (double)min(counts[CAT_HALOL], capH);
-        sendR[0] = (double)min(counts[CAT_MIGR], capM); sendR[1] = (double)min(counts[CAT_HALOR], capH);
+        const double hl0 = (double)min(counts[CAT_MIGL], capM), hl1 = (double)min(counts[CAT_HALOL], capH);
+        const double hr0 = (double)min(counts[CAT_MIGR], capM), hr1 = (double)min(counts[CAT_HALOR], capH);
+        sendL[0] = hl0; sendL[1] = hl1; sendR[0] = hr0; sendR[1] = hr1;
+        if (remL) { remL[0] = hl0; remL[1] = hl1; }
+        if (remR) { remR[0] = hr0; remR[1] = hr1; }
         if (counts[CAT_MIGL] > capM || counts[CAT_MIGR] > capM || counts[CAT_HALOL] > capH || counts[CAT_HALOR] > capH)
             dn[DN_CAP] = 1;
     }
-    if (i >= n || f == 0u) return;
-    const double x = src.pos[i], y = src.pos[ld + i], z = src.pos[2 * ld + i];
-    const int id = src.gid ? src.gid[i] : i;
-    const double q = src.charge ? src.charge[i] : 0.0;
-    if (f & (1u << CAT_STAY)) {
-        const int d = rank[CAT_STAY];
-        dst.pos[d] = x; dst.pos[ld + d] = y; dst.pos[2 * ld + d] = z;
-        dst.vel[d] = src.vel[i]; dst.vel[ld + d] = src.vel[ld + i]; dst.vel[2 * ld + d] = src.vel[2 * ld + i];
-        dst.acc[d] = src.acc[i]; dst.acc[ld + d] = src.acc[ld + i]; dst.acc[2 * ld + d] = src.acc[2 * ld + i];
-        dst.mass[d] = src.mass[i];
-        if (dst.charge) dst.charge[d] = q;
-        dst.gid[d] = id;
-        for (int side = 0; side < 2; ++side) {
-            const int cat = side == 0 ? CAT_HALOL : CAT_HALOR;
-            if (!(f & (1u << cat)) || rank[cat] >= capH) continue;
-            double *rec = (side == 0 ? sendL : sendR) + kHdr + (size_t)capM * kMigW + (size_t)rank[cat] * kHaloW;
-            rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z; rec[4] = q;
+    if (i < n && f != 0u) {
+        const double x = src.pos[i], y = src.pos[ld + i], z = src.pos[2 * ld + i];
+        const int id = src.gid ? src.gid[i] : i;
+        const double q = src.charge ? src.charge[i] : 0.0;
+        if (f & (1u << CAT_STAY)) {
+            const int d = rank[CAT_STAY];
+            dst.pos[d] = x; dst.pos[ld + d] = y; dst.pos[2 * ld + d] = z;
+            dst.vel[d] = src.vel[i]; dst.vel[ld + d] = src.vel[ld + i]; dst.vel[2 * ld + d] = src.vel[2 * ld + i];
+            dst.acc[d] = src.acc[i]; dst.acc[ld + d] = src.acc[ld + i]; dst.acc[2 * ld + d] = src.acc[2 * ld + i];
+            dst.mass[d] = src.mass[i];
+            if (dst.charge) dst.charge[d] = q;
+            dst.gid[d] = id;
+            for (int side = 0; side < 2; ++side) {
+                const int cat = side == 0 ? CAT_HALOL : CAT_HALOR;
+                if (!(f & (1u << cat)) || rank[cat] >= capH) continue;
+                // halo records go to the neighbour directly when connected, else into the send buffer
+                double *out = side == 0 ? (remL ? remL : sendL) : (remR ? remR : sendR);
+                double *rec = out + kHdr + (size_t)capM * kMigW + (size_t)rank[cat] * kHaloW;
+                rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z; rec[4] = q;
+            }
+        } else {
+            const int cat = (f & (1u << CAT_MIGL)) ? CAT_MIGL : CAT_MIGR;
+            if (rank[cat] < capM) {
+                const double v0 = src.vel[i], v1 = src.vel[ld + i], v2 = src.vel[2 * ld + i];
+                const double a0 = src.acc[i], a1 = src.acc[ld + i], a2 = src.acc[2 * ld + i];
+                const double m = src.mass[i];
+                double *rem = cat == CAT_MIGL ? remL : remR;
+                // the local copy stays: the migrant is a ghost here from now on (unpack reads it back)
+                for (int copy = 0; copy < 2; ++copy) {
+                    double *out = copy == 0 ? (cat == CAT_MIGL ? sendL : sendR) : rem;
+                    if (!out) continue;
+                    double *rec = out + kHdr + (size_t)rank[cat] * kMigW;
+                    rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z;
+                    rec[4] = v0; rec[5] = v1; rec[6] = v2; rec[7] = a0; rec[8] = a1; rec[9] = a2;
+                    rec[10] = m; rec[11] = q;
+                }
+            }
         }
-    } else {
-        const int cat = (f & (1u << CAT_MIGL)) ? CAT_MIGL : CAT_MIGR;
-        if (rank[cat] >= capM) return;
-        double *rec = (cat == CAT_MIGL ? sendL : sendR) + kHdr + (size_t)rank[cat] * kMigW;
-        rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z;
-        rec[4] = src.vel[i]; rec[5] = src.vel[ld + i]; rec[6] = src.vel[2 * ld + i];
-        rec[7] = src.acc[i]; rec[8] = src.acc[ld + i]; rec[9] = src.acc[2 * ld + i];
-        rec[10] = src.mass[i]; rec[11] = q;
+    }
+    // completion: every block fences its (remote) stores and takes a ticket; the last one publishes the message
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_block = atomicAdd(&dn[DN_TICKET], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last_block && threadIdx.x == 0) {
+        __threadfence_system();
+        if (peerL) *reinterpret_cast<volatile long long *>(peerL + 1) = (long long)msg; // left's "from the right"
+        if (peerR) *reinterpret_cast<volatile long long *>(peerR + 0) = (long long)msg; // right's "from the left"
+        dn[DN_TICKET] = 0;
+        dn[DN_MSG] = msg;
     }
 }
 
 // segments, in the order they are laid down: arrivals (left, right) extend the own particles; the ghosts are
 // the migrants just sent (left, right) and the received halos (left, right)
 __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
-                                   int *__restrict__ dn,
-                                   const double *__restrict__ sendL, const double *__restrict__ sendR,
-                                   const double *__restrict__ recvL, const double *__restrict__ recvR, int capM, int capH)
+                                   int *__restrict__ dn, const double *__restrict__ sendL,
+                                   const double *__restrict__ sendR, double *rx, int64_t msg_doubles, int direct,
+                                   int capM, int capH)
 {
+    // direct mode: the neighbours store into this rank's receive area and raise its flags (message number)
+    const int msg = dn[DN_MSG];
+    if (direct) {
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) {
+            timed_out = 0;
+            const volatile long long *flag = reinterpret_cast<const volatile long long *>(rx);
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (flag[0] < msg || flag[1] < msg) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 10000000000ull) { timed_out = 1; break; } // 10 s: a neighbour died; do not hang the GPU
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (timed_out) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { dn[DN_TIMEOUT] = 1; dn[DN_OWN] = 0; dn[DN_GHOST] = 0; }
+            return;
+        }
+    }
+    const double *recvL = rx_msg(rx, 0, direct ? (msg & 1) : 0, msg_doubles);
+    const double *recvR = rx_msg(rx, 1, direct ? (msg & 1) : 0, msg_doubles);
     const int nstay = counts[CAT_STAY];
     const int arrL = min((int)recvL[0], capM), arrR = min((int)recvR[0], capM);
     const int keptL = min((int)sendL[0], capM), keptR = min((int)sendR[0], capM);
@@ -241,7 +313,8 @@ __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols,
 void slab_free(nbx_ctx *c)
 {
     SlabState &s = c->slab;
-    for (double *&p : s.msg) { cudaFree(p); p = nullptr; }
+    for (void *p : s.ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(s.msg[0]); cudaFree(s.msg[1]); cudaFree(s.rx);
     cudaFree(s.pos2); cudaFree(s.vel2); cudaFree(s.acc2); cudaFree(s.mass2); cudaFree(s.charge2);
     cudaFree(s.gid_a); cudaFree(s.gid_b); cudaFree(s.blockcnt); cudaFree(s.blockoff); cudaFree(s.d_counts);
     cudaFree(s.d_n);
@@ -281,7 +354,8 @@ static int run_pack(nbx_ctx *c, int init)
     slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_n, dyn);
     slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
     slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0], s.msg[1],
-                                                      (int)s.capM, (int)s.capH, s.d_n, dyn);
+                                                      (int)s.capM, (int)s.capH, s.d_n, dyn, s.direct ? s.peer[0] : nullptr,
+                                                      s.direct ? s.peer[1] : nullptr, s.msg_doubles);
     NBX_CUDA(c, cudaGetLastError());
     // the compacted state is the state from here on (stream-ordered: later kernels see the new pointers)
     std::swap(c->pos, s.pos2); std::swap(c->vel, s.vel2); std::swap(c->acc, s.acc2); std::swap(c->mass, s.mass2);
@@ -324,10 +398,16 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     // own + ghosts: twice the slab's share of a uniform box (+ the ghost layers); all of it for one slab
     s.cap_loc = nranks == 1 ? c->n : std::min<int64_t>(c->n, 2 * layer * (s.c1 - s.c0) + 2 * s.capH + 4096);
     const size_t np = (size_t)c->npad;
-    for (double *&p : s.msg) {
-        NBX_TRY(dev_alloc(c, &p, (size_t)s.msg_doubles));
-        NBX_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)s.msg_doubles, c->stream));
+    for (int k = 0; k < 2; ++k) {
+        NBX_TRY(dev_alloc(c, &s.msg[k], (size_t)s.msg_doubles));
+        NBX_CUDA(c, cudaMemsetAsync(s.msg[k], 0, sizeof(double) * (size_t)s.msg_doubles, c->stream));
     }
+    // receive area: flags + {from-left, from-right} x {parity 0, 1}; host-driven exchanges use parity 0
+    s.rx_doubles = kRxHdr + 4 * s.msg_doubles;
+    NBX_TRY(dev_alloc(c, &s.rx, (size_t)s.rx_doubles));
+    NBX_CUDA(c, cudaMemsetAsync(s.rx, 0, sizeof(double) * (size_t)s.rx_doubles, c->stream));
+    s.msg[2] = s.rx + kRxHdr;
+    s.msg[3] = s.rx + kRxHdr + 2 * s.msg_doubles;
     NBX_TRY(dev_alloc(c, &s.pos2, 3 * np)); NBX_TRY(dev_alloc(c, &s.vel2, 3 * np)); NBX_TRY(dev_alloc(c, &s.acc2, 3 * np));
     NBX_TRY(dev_alloc(c, &s.mass2, np));
     if (c->charge) NBX_TRY(dev_alloc(c, &s.charge2, np));
@@ -344,21 +424,57 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     NBX_CUDA(c, cudaMemsetAsync(s.vel2, 0, sizeof(double) * 3 * np, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(s.acc2, 0, sizeof(double) * 3 * np, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(s.mass2, 0, sizeof(double) * np, c->stream));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream)); // the receive area is zeroed before a neighbour may write to it
     s.on = true;
-    c->gid = nullptr; // the pack below reads the full uploaded state (ids = column numbers)
-    NBX_TRY(run_pack(c, 1));
-    // from here on the counts are device-side and the host sizes are bounds
-    c->dyn = s.d_n;
-    c->n = s.cap_loc;
-    c->tgt_lo = 0;
-    c->tgt_hi = s.cap_loc;
+    s.first = true;
+    c->gid = nullptr; // the first pack reads the full uploaded state (ids = column numbers)
+    return NBX_OK;
+}
+
+// Direct exchange: the neighbours' receive areas, either as device pointers valid in this process or as CUDA IPC
+// handles of another process (64 bytes each, from nbx_slab_ipc_handle).
+int slab_connect(nbx_ctx *c, const void *left_handle, const void *right_handle, void *left_ptr, void *right_ptr)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.first) return fail(c, NBX_ERR_INVALID, "nbx_slab_connect: call it between nbx_slab_init and the first nbx_slab_pack");
+    if (!left_handle && !right_handle && !left_ptr && !right_ptr) { // back to the host-driven exchange
+        s.direct = false;
+        return NBX_OK;
+    }
+    if (s.nranks == 1) return NBX_OK;
+    void *ptr[2] = {left_ptr, right_ptr};
+    const void *hdl[2] = {left_handle, right_handle};
+    for (int k = 0; k < 2; ++k) {
+        if (ptr[k]) continue;
+        if (!hdl[k]) return fail(c, NBX_ERR_INVALID, "nbx_slab_connect: neither a pointer nor a handle for side %d", k);
+        if (k == 1 && hdl[0] && !left_ptr && !memcmp(hdl[0], hdl[1], sizeof(cudaIpcMemHandle_t))) { ptr[1] = ptr[0]; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hdl[k], sizeof h);
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaIpcOpenMemHandle (neighbour receive area)");
+        s.ipc_opened.push_back(ptr[k]);
+    }
+    s.peer[0] = static_cast<double *>(ptr[0]);
+    s.peer[1] = static_cast<double *>(ptr[1]);
+    s.direct = true;
     return NBX_OK;
 }
 
 int slab_pack(nbx_ctx *c)
 {
-    if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: call nbx_slab_init first");
-    if (c->slab.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: the previous pack was not completed by nbx_slab_unpack");
+    SlabState &s = c->slab;
+    if (!s.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: call nbx_slab_init first");
+    if (s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_pack: the previous pack was not completed by nbx_slab_unpack");
+    if (s.first) {
+        NBX_TRY(run_pack(c, 1));
+        s.first = false;
+        // from here on the counts are device-side and the host sizes are bounds
+        c->dyn = s.d_n;
+        c->n = s.cap_loc;
+        c->tgt_lo = 0;
+        c->tgt_hi = s.cap_loc;
+        return NBX_OK;
+    }
     return run_pack(c, 0);
 }
 
@@ -374,6 +490,8 @@ int slab_check(nbx_ctx *c, int64_t *out)
     const int *h = s.h_counts, *hn = s.h_counts + CNT_N;
     if (hn[DN_LOST] > 0)
         return fail(c, NBX_ERR_INVALID, "slab exchange: %d particle(s) moved past the neighbouring slab in one step", hn[DN_LOST]);
+    if (hn[DN_TIMEOUT] != 0)
+        return fail(c, NBX_ERR_CUDA, "slab exchange: timed out waiting for a neighbour's message (direct mode)");
     if (hn[DN_CAP] != 0)
         return fail(c, NBX_ERR_CAPACITY, "slab exchange: message or state capacity exceeded (last step: migrants %d/%d of %lld, "
                     "halo %d/%d of %lld; own + ghosts bound %lld)", h[CAT_MIGL], h[CAT_MIGR], (long long)s.capM, h[CAT_HALOL],
@@ -394,8 +512,8 @@ int slab_unpack(nbx_ctx *c, int64_t *out)
     const int64_t threads = 4 * s.capM + 2 * s.capH;
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.cap_loc, s.d_counts, s.d_n,
-                                                                              s.msg[0], s.msg[1], s.msg[2], s.msg[3],
-                                                                              (int)s.capM, (int)s.capH);
+                                                                              s.msg[0], s.msg[1], s.rx, s.msg_doubles,
+                                                                              s.direct ? 1 : 0, (int)s.capM, (int)s.capH);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return out ? slab_check(c, out) : NBX_OK;

@@ -112,6 +112,39 @@ class CudaEngine:
     def slab_init(self, rank, world):
         self.ctx.slab_init(rank, world)
 
+    def slab_connect(self, stepper):
+        """Try to map the neighbours' receive areas (CUDA IPC over NVLink) so that the pack kernel stores its
+        messages straight into them.  Collective over the stepper's group; returns True when EVERY rank
+        connected (otherwise all ranks stay on the host-driven send/recv exchange)."""
+        import torch
+
+        dist = stepper.dist
+        if stepper.world == 1:
+            return True
+        if dist.get_backend(stepper.group) != "nccl":
+            return False
+        ok = 1
+        try:
+            _, _, handle = self.ctx.slab_rx(want_handle=True)
+        except Exception:
+            handle, ok = None, 0
+        handles = [None] * stepper.world
+        dist.all_gather_object(handles, handle, group=stepper.group)
+        if ok and all(h is not None for h in handles):
+            try:
+                self.ctx.slab_connect(handles[stepper.left], handles[stepper.right])
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=stepper.group)
+        if int(t.item()) == 0:
+            self.ctx.slab_connect()  # disconnect: every rank must use the same exchange
+            return False
+        dist.barrier(group=stepper.group)  # every receive area is mapped before anyone stores into one
+        return True
+
     def slab_buffers(self):
         """[send-to-left, send-to-right, recv-from-left, recv-from-right] as flat float64 device tensors."""
         return [self._raw(*self.ctx.slab_buffer(k)) for k in range(4)]
@@ -213,7 +246,7 @@ class SlabStepper:
     slab_buffers() -> 4 flat tensors, slab_pack(), slab_unpack() -> counts, slab_download().
     """
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, direct=True):
         import torch.distributed as dist
 
         self.dist = dist
@@ -225,7 +258,10 @@ class SlabStepper:
         self.left = (self.rank - 1) % self.world
         self.right = (self.rank + 1) % self.world
         engine.slab_init(self.rank, self.world)
-        self.bufs = engine.slab_buffers()
+        # direct = the neighbours' receive areas are mapped and the pack kernel writes into them (no host exchange)
+        self.direct = bool(direct and self.world > 1 and hasattr(engine, "slab_connect") and engine.slab_connect(self))
+        self.bufs = None if self.direct else engine.slab_buffers()
+        engine.slab_pack()  # the first pack selects the own particles out of the full upload
         self._exchange()
         self.counts = engine.slab_unpack()
 
@@ -236,8 +272,8 @@ class SlabStepper:
         """send-to-left -> the left neighbour's recv-from-right, send-to-right -> the right neighbour's
         recv-from-left.  Posting order (sends: left, right; receives: from right, from left) keeps the two
         messages of a 2-rank ring, where both neighbours are the same peer, matched."""
-        if self.world == 1:
-            return  # one slab: the cell list's own periodic wrap does everything, no ghosts
+        if self.world == 1 or self.direct:
+            return  # one slab: no ghosts at all; direct: the pack kernel already stored into the neighbours
         dist = self.dist
         send_l, send_r, recv_l, recv_r = self.bufs
         ops = [dist.P2POp(dist.isend, send_l, self._peer(self.left), self.group),

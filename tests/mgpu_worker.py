@@ -28,7 +28,7 @@ def slab_main(cells):
     v = np.asfortranarray(3.0 * w["v"])
     dt, steps = 2e-3, 40
     ok = True
-    for thermo in (False, True):
+    for thermo, direct in ((False, True), (True, True), (False, False)):
         def make():
             ctx = _lib.Context(local)
             ctx.system(w["ms"])
@@ -47,7 +47,7 @@ def slab_main(cells):
         eng = CudaEngine(ctx, local)
         eng.needs_temperature = thermo
         ctx.upload(u, v)
-        st = SlabStepper(eng)
+        st = SlabStepper(eng, direct=direct)
         moved = 0
         for _ in range(steps):
             st.step(dt, 1)
@@ -62,9 +62,9 @@ def slab_main(cells):
             else:  # cell order is ranked by global id: bit-identical to the single-GPU sums
                 err = 0.0 if (np.array_equal(ug, ur) and np.array_equal(vg, vr) and np.array_equal(ag, ar)) else 1.0
                 good = err == 0.0
-            print(f"slab thermo={thermo} world={world} n={n} own={st.counts[0]} ghosts={st.counts[1]} "
+            print(f"slab thermo={thermo} direct={st.direct} world={world} n={n} own={st.counts[0]} ghosts={st.counts[1]} "
                   f"migrations={int(t.item())} err={err:.2e}")
-            ok = ok and good and t.item() > 0
+            ok = ok and good and t.item() > 0 and (st.direct or not direct)
         ctx.close()
     if rank == 0:
         print("MGPU_OK" if ok else "MGPU_FAIL")

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 class LocalRing:
     """K slab contexts on one device; neighbour exchange by tensor copies."""
 
-    def __init__(self, make_ctx, u, v, world, thermostat):
+    def __init__(self, make_ctx, u, v, world, thermostat, direct=False):
         import torch
 
         from nbody_b200.parallel import CudaEngine
@@ -34,12 +34,20 @@ class LocalRing:
             ctx.upload(u, v)
             eng.slab_init(r, world)
             self.engines.append(eng)
-        self.bufs = [e.slab_buffers() for e in self.engines]
+        self.direct = direct and world > 1
+        if self.direct:  # same process: the neighbours' receive areas as plain device pointers
+            rx = [e.ctx.slab_rx()[0] for e in self.engines]
+            for r, e in enumerate(self.engines):
+                e.ctx.slab_connect(left_ptr=rx[(r - 1) % world], right_ptr=rx[(r + 1) % world])
+        else:
+            self.bufs = [e.slab_buffers() for e in self.engines]
+        for e in self.engines:
+            e.slab_pack()
         self._exchange()
         self.counts = [e.slab_unpack() for e in self.engines]
 
     def _exchange(self):
-        if self.world == 1:
+        if self.world == 1 or self.direct:
             return
         for r in range(self.world):
             left, right = (r - 1) % self.world, (r + 1) % self.world
@@ -88,9 +96,10 @@ def _argon(cells, seed, hot=3.0):
     return w, u, v
 
 
+@pytest.mark.parametrize("direct", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("thermostat", [False, True])
-def test_slabs_reproduce_the_single_context_trajectory(world, thermostat):
+def test_slabs_reproduce_the_single_context_trajectory(world, thermostat, direct):
     w, u, v = _argon(12, 5)  # 6,912 atoms, 9 cell layers
     n = u.shape[1]
     dt, steps = 2e-3, 60
@@ -110,7 +119,7 @@ def test_slabs_reproduce_the_single_context_trajectory(world, thermostat):
     ur, vr, ar = ref.download(want_dv=True)
     ref.close()
 
-    ring = LocalRing(make_ctx, u, v, world, thermostat)
+    ring = LocalRing(make_ctx, u, v, world, thermostat, direct)
     assert sum(c[0] for c in ring.counts) == n
     if world > 1:
         assert all(c[1] > 0 for c in ring.counts)  # ghosts
@@ -140,6 +149,9 @@ def test_slab_errors_are_reported():
     with pytest.raises(_lib.NbxError):
         ctx.slab_pack()
     ctx.slab_init(1, 2)
+    ctx.slab_pack()
+    with pytest.raises(_lib.NbxError):
+        ctx.slab_pack()  # the previous pack was not completed
     with pytest.raises(_lib.NbxError):
         ctx.step_vv(1e-3, 1)  # whole-system entry points are closed on a slab context
     with pytest.raises(_lib.NbxError):

@@ -199,10 +199,11 @@ class NumpySlabEngine:
     def slab_init(self, rank, world):
         lo = lambda r: r * self.nc // world
         self.c0, self.c1 = lo(rank), lo(rank + 1)
-        self._pack(init=True)
+        self.first = True
 
     def slab_pack(self):
-        self._pack(init=False)
+        self._pack(init=self.first)
+        self.first = False
 
     def _pack(self, init):
         rel = (self._layer(self.pos[0]) - self.c0) % self.nc
