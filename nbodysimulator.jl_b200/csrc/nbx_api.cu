@@ -123,26 +123,21 @@ int compute_pairs(nbx_ctx *c)
             gather_oxygen_kernel<<<(unsigned)((c->opad + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, nmol, c->opos,
                                                                                          c->opad, kFarAway);
             NBX_CUDA(c, cudaGetLastError());
-            NBX_TRY(cells_plan(c, c->lj_R, nmol, &c->cl_lj.grid));
-            if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->opos, nullptr, nullptr, nmol, c->opad, 1));
-                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, mlo, mhi, 3, c->oacc, c->opad, false));
-            } else {
-                NBX_TRY(launch_allpairs_pbc(c, 0, c->opos, nmol, c->opad, mlo, mhi, 3, c->oacc, c->opad, false));
-            }
+            bool used = false;
+            NBX_TRY(cells_pairs(c, &c->cl_lj, c->lj_R, 0, c->opos, nullptr, nullptr, nmol, nmol, c->opad, 1, mlo, mhi, 3, c->oacc,
+                                c->opad, false, &used));
+            if (!used) NBX_TRY(launch_allpairs_pbc(c, 0, c->opos, nmol, c->opad, mlo, mhi, 3, c->oacc, c->opad, false));
             if (mhi > mlo) {
                 scatter_oxygen_kernel<<<(unsigned)((mhi - mlo + 255) / 256), 256, 0, c->stream>>>(c->oacc, c->opad, mlo, mhi,
                                                                                                 c->acc, c->npad);
                 NBX_CUDA(c, cudaGetLastError());
             }
         } else {
-            NBX_TRY(cells_plan(c, c->lj_R, c->slab.on ? c->slab.n_total : c->n, &c->cl_lj.grid));
-            if (c->cl_lj.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_lj, c->pos, nullptr, c->gid, c->n, c->npad, 1));
-                NBX_TRY(launch_cells_force(c, &c->cl_lj, 0, lo, hi, 1, c->acc, c->npad, acc_flag()));
-            } else {
-                NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, acc_flag()));
-            }
+            bool used = false;
+            const bool accum = acc_flag();
+            NBX_TRY(cells_pairs(c, &c->cl_lj, c->lj_R, 0, c->pos, nullptr, c->gid, c->n, c->slab.on ? c->slab.n_total : c->n,
+                                c->npad, 1, lo, hi, 1, c->acc, c->npad, accum, &used));
+            if (!used) NBX_TRY(launch_allpairs_pbc(c, 0, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, accum));
         }
     }
     if (c->has_coul) {
@@ -151,13 +146,11 @@ int compute_pairs(nbx_ctx *c)
             // F += q_j (ri - rj)/r^3, dv += k q_i / m_i F  ==  -k q_i/m_i * sum q_j (rj - ri)/r^3
             NBX_TRY(launch_allpairs_grav(c, c->charge, 1, -c->el_k, c->acc, acc_flag()));
         } else {
-            NBX_TRY(cells_plan(c, c->el_R, c->slab.on ? c->slab.n_total : c->n, &c->cl_el.grid));
-            if (c->cl_el.grid.valid) {
-                NBX_TRY(cells_build(c, &c->cl_el, c->pos, c->charge, c->gid, c->n, c->npad, c->water ? 3 : 1));
-                NBX_TRY(launch_cells_force(c, &c->cl_el, pot, lo, hi, 1, c->acc, c->npad, acc_flag()));
-            } else {
-                NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, acc_flag()));
-            }
+            bool used = false;
+            const bool accum = acc_flag();
+            NBX_TRY(cells_pairs(c, &c->cl_el, c->el_R, pot, c->pos, c->charge, c->gid, c->n, c->slab.on ? c->slab.n_total : c->n,
+                                c->npad, c->water ? 3 : 1, lo, hi, 1, c->acc, c->npad, accum, &used));
+            if (!used) NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, accum));
         }
     }
     if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, acc_flag()));
@@ -838,6 +831,10 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     if (!key) return fail(c, NBX_ERR_INVALID, "nbx_set_option: key is NULL");
     if (!strcmp(key, "cell_list")) c->opt_cell_list = (int)value;
     else if (!strcmp(key, "prefilter")) c->opt_prefilter = (int)value;
+    else if (!strcmp(key, "verlet_skin_permille")) {
+        if (value < 0 || value > 1000) return fail(c, NBX_ERR_INVALID, "verlet_skin_permille: 0 .. 1000 (thousandths of the cutoff)");
+        c->opt_verlet_permille = (int)value;
+    }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
@@ -861,6 +858,17 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "slab_layer_lo")) *value = c->slab.c0;
     else if (!strcmp(key, "slab_layer_hi")) *value = c->slab.c1;
     else if (!strcmp(key, "slab_layers")) *value = c->slab.nc;
+    else if (!strcmp(key, "verlet_overflow") || !strcmp(key, "verlet_rebuilds")) {
+        // device flags of the LJ list (synchronises): [1] sticky overflow, [2] rebuilds so far
+        int h[4] = {0, 0, 0, 0};
+        if (c->cl_lj.v_valid && c->cl_lj.v_flags) {
+            NBX_CUDA(c, cudaMemcpyAsync(h, c->cl_lj.v_flags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+            NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2];
+    }
+    else if (!strcmp(key, "verlet_lj")) *value = c->cl_lj.v_valid ? c->cl_lj.v_cap : 0;
+    else if (!strcmp(key, "verlet_el")) *value = c->cl_el.v_valid ? c->cl_el.v_cap : 0;
     else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;
     else if (!strcmp(key, "cells_el")) *value = c->cl_el.grid.valid ? c->cl_el.grid.ncell : 0;
     else if (!strcmp(key, "allpairs_grid")) *value = c->last_grid;

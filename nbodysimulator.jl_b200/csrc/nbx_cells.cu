@@ -71,8 +71,9 @@ __device__ __forceinline__ int cell_coord(double x, double L, int nc)
 
 __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n, double L, int nc,
                                int *__restrict__ cell_of, int *__restrict__ arrival, int *__restrict__ count,
-                               const int *__restrict__ dyn)
+                               const int *__restrict__ dyn, const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return; // Verlet mode: the list is still valid, nothing to rebuild
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dyn_loc(dyn, n)) return;
     const int cx = cell_coord(px[i], L, nc), cy = cell_coord(px[ld + i], L, nc), cz = cell_coord(px[2 * ld + i], L, nc);
@@ -84,9 +85,11 @@ __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n,
 constexpr int kScanBlock = 1024;
 
 // exclusive scan of in[0..n) by blocks of 1024; block totals to sums[]
-__global__ void scan_block_kernel(const int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ sums)
+__global__ void scan_block_kernel(const int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ sums,
+                                  const int *__restrict__ cond)
 {
     __shared__ int wsum[32];
+    if (cond && !cond[0]) return;
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
     const int v = i < n ? in[i] : 0;
     int s = v;
@@ -114,10 +117,11 @@ __global__ void scan_block_kernel(const int *__restrict__ in, int *__restrict__ 
 }
 
 // serial-by-chunks exclusive scan of the block totals (single block), total -> sums[nb]
-__global__ void scan_sums_kernel(int *__restrict__ sums, int nb)
+__global__ void scan_sums_kernel(int *__restrict__ sums, int nb, const int *__restrict__ cond)
 {
     __shared__ int wsum[32];
     __shared__ int carry;
+    if (cond && !cond[0]) return;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base0 = 0; base0 < nb; base0 += kScanBlock) {
@@ -151,8 +155,10 @@ __global__ void scan_sums_kernel(int *__restrict__ sums, int nb)
     if (threadIdx.x == 0) sums[nb] = carry;
 }
 
-__global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restrict__ sums, int nb)
+__global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restrict__ sums, int nb,
+                                const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return;
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
     if (i < n) out[i] += sums[blockIdx.x];
     if (i == 0) out[n] = sums[nb]; // grand total closes the CSR
@@ -161,8 +167,10 @@ __global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restr
 // slot = cell start + arrival rank (no atomics); the ordering key travels with the index
 __global__ void scatter_kernel(const int *__restrict__ cell_of, const int *__restrict__ arrival,
                                const int *__restrict__ gid, int n, const int *__restrict__ start,
-                               int *__restrict__ tmp_idx, int *__restrict__ tmp_key, const int *__restrict__ dyn)
+                               int *__restrict__ tmp_idx, int *__restrict__ tmp_key, const int *__restrict__ dyn,
+                               const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dyn_loc(dyn, n)) return;
     const int slot = start[cell_of[i]] + arrival[i];
@@ -180,8 +188,10 @@ __global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, co
                                    const int *__restrict__ tmp_idx, const int *__restrict__ tmp_key,
                                    const int *__restrict__ cell_of, const int *__restrict__ start, int n, double L,
                                    int nc, int key_div, int *__restrict__ sorted_idx, double4 *__restrict__ sp4,
-                                   float4 *__restrict__ sl4, int *__restrict__ scell, const int *__restrict__ dyn)
+                                   float4 *__restrict__ sl4, int *__restrict__ scell, const int *__restrict__ dyn,
+                                   const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= dyn_loc(dyn, n)) return;
     const int i = tmp_idx[k];
@@ -228,7 +238,7 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
 // Rebuild cl for the n particles of the SoA rows px (stride ld); w = optional per-particle weight
 // (charge) carried into cell order.
 int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, const int *gid, int64_t n, int64_t ld,
-                int key_div)
+                int key_div, const int *cond)
 {
     const CellGrid &g = cl->grid;
     if (!g.valid) return fail(c, NBX_ERR_INVALID, "cells_build without a valid grid");
@@ -238,15 +248,15 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, con
     timer_begin(c, NBX_T_CELL_BUILD);
     cudaMemsetAsync(cl->count, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
     cell_id_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
-                                                           cl->count, c->dyn);
-    scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums);
-    scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb);
-    scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb);
+                                                           cl->count, c->dyn, cond);
+    scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums, cond);
+    scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb, cond);
+    scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb, cond);
     scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
-                                                           cl->tmp_key, c->dyn);
+                                                           cl->tmp_key, c->dyn, cond);
     rank_gather_kernel<<<(ni + 127) / 128, 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
                                                                cl->cell_of, cl->start, ni, g.len[0], g.nc[0], key_div,
-                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn);
+                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn, cond);
     timer_end(c, NBX_T_CELL_BUILD);
     NBX_CUDA(c, cudaGetLastError());
     cl->n = n;
@@ -404,9 +414,11 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
                                                           const double *__restrict__ charge, int lo, int hi,
                                                           double *__restrict__ acc, int64_t ld, int accumulate,
                                                           int *__restrict__ counts, const int64_t *__restrict__ offsets,
-                                                          int32_t *__restrict__ list, const int *__restrict__ dyn)
+                                                          int32_t *__restrict__ list, const int *__restrict__ dyn,
+                                                          const int *__restrict__ cond)
 {
     __shared__ int q[kQCap * 128];
+    if (cond && !cond[0]) return; // Verlet mode: runs only as the fallback when a list overflowed
     const int n_loc = dyn_loc(dyn, a.n);
     if (blockIdx.x * 128 >= n_loc) return; // launch bound beyond the actual count (whole block)
     if (dyn) hi = min(hi, dyn[0]);
@@ -545,6 +557,160 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Verlet lists: the survivor set of the fp32 scan, kept across steps
+// ------------------------------------------------------------------------------------------------
+// The scan of cell_pairs2_kernel with the threshold widened to R + skin produces, per slot, the list of slots
+// that can come within R while no particle has moved more than skin/2 since the build (|d(t) - d(build)| <
+// skin).  Every later evaluation applies the reference's exact predicate to the listed pairs only, so the
+// in-cutoff pair set is unchanged; the list is rebuilt -- on the device's own decision, no host round trip --
+// as soon as some particle's displacement from its build-time position exceeds skin/2.
+// flags: [0] rebuild now, [1] a list overflowed its capacity (sticky: from then on every evaluation rebuilds
+// the cells and takes the scan-per-step kernel instead).
+__global__ void verlet_check_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ ref, int64_t rld,
+                                    int n, double lim2, int *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && flags[1]) flags[0] = 1;
+    if (i >= n) return;
+    const double dx = px[i] - ref[i], dy = px[ld + i] - ref[rld + i], dz = px[2 * ld + i] - ref[2 * rld + i];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 <= lim2)) flags[0] = 1; // also catches NaN
+}
+
+struct VerletArgs {
+    int *list;   // [cap][stride]: entry e of slot k at e * stride + k
+    int *nlist;  // [n]
+    int *flags;
+    int cap;
+    int64_t stride;
+};
+
+// one lane per slot: the fp32 scan of cell_pairs2_kernel, survivors appended to the slot's list
+__global__ void __launch_bounds__(128) verlet_build_kernel(const CellPairArgs a, const VerletArgs v)
+{
+    if (!v.flags[0] || v.flags[1]) return;
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= a.n) return;
+    const float4 me = a.sl4[k];
+    const int key = __float_as_int(me.w);
+    const int cid = a.scell[k];
+    const int nc = a.nc;
+    const int cx = cid % nc, cy = (cid / nc) % nc, cz = cid / (nc * nc);
+    const float fnc = (float)nc;
+    int cnt = 0;
+    bool over = false;
+    auto scan = [&](int b, int e, float tx, float ty, float tz) {
+        for (int m = b; m < e; ++m) {
+            const float4 cj = __ldg(&a.sl4[m]);
+            const float dx = tx - cj.x, dy = ty - cj.y, dz = tz - cj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (r2 < a.R2f && __float_as_int(cj.w) != key) {
+                if (cnt < v.cap) v.list[(size_t)cnt * v.stride + k] = m;
+                else over = true;
+                ++cnt;
+            }
+        }
+    };
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int dz = r / 3 - 1, dy = r - (r / 3) * 3 - 1;
+        int z = cz + dz, y = cy + dy;
+        float tz = me.z, ty = me.y;
+        if (z < 0) { z += nc; tz += fnc; } else if (z >= nc) { z -= nc; tz -= fnc; }
+        if (y < 0) { y += nc; ty += fnc; } else if (y >= nc) { y -= nc; ty -= fnc; }
+        const int row = (z * nc + y) * nc;
+        const int xa = cx > 0 ? cx - 1 : 0, xb = cx < nc - 1 ? cx + 1 : nc - 1;
+        scan(a.start[row + xa], a.start[row + xb + 1], me.x, ty, tz);
+        if (cx == 0) scan(a.start[row + nc - 1], a.start[row + nc], me.x + fnc, ty, tz);
+        else if (cx == nc - 1) scan(a.start[row], a.start[row + 1], me.x - fnc, ty, tz);
+    }
+    v.nlist[k] = cnt < v.cap ? cnt : v.cap;
+    if (over) v.flags[1] = 1;
+}
+
+// after a rebuild: remember the positions the list was built from
+__global__ void verlet_ref_kernel(const double *__restrict__ px, int64_t ld, double *__restrict__ ref, int64_t rld, int n,
+                                  int *__restrict__ flags)
+{
+    if (!flags[0]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) flags[2] += 1; // rebuild counter (diagnostics)
+    if (i >= n) return;
+    ref[i] = px[i]; ref[rld + i] = px[ld + i]; ref[2 * rld + i] = px[2 * ld + i];
+}
+
+// every evaluation: current exact coordinates into the cell-order records; the rebuild request is consumed here
+// (nothing after this kernel reads flags[0])
+__global__ void verlet_refresh_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ w,
+                                      const int *__restrict__ sorted_idx, int n, double4 *__restrict__ sp4,
+                                      int *__restrict__ flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) flags[0] = 0;
+    if (k >= n) return;
+    const int i = sorted_idx[k];
+    sp4[k] = make_double4(px[i], px[ld + i], px[2 * ld + i], w ? w[i] : 0.0);
+}
+
+template <int POT>
+__global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a, const VerletArgs v, double scale,
+                                                           const double *__restrict__ mass, int mstride,
+                                                           const double *__restrict__ charge, int lo, int hi,
+                                                           double *__restrict__ acc, int64_t ld, int accumulate)
+{
+    if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= a.n) return;
+    const int i = a.sorted_idx[k];
+    if (i < lo || i >= hi) return;
+    const double4 pi = a.sp4[k];
+    const int cnt = v.nlist[k];
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    auto pair = [&](const double4 pj) {
+        double rx = __dsub_rn(pi.x, pj.x), ry = __dsub_rn(pi.y, pj.y), rz = __dsub_rn(pi.z, pj.z);
+        const int hx = __double2hiint(rx) & 0x7fffffff, hy = __double2hiint(ry) & 0x7fffffff,
+                  hz = __double2hiint(rz) & 0x7fffffff;
+        if (max(hx, max(hy, hz)) >= a.hi_radius) {
+            rx = wrap_cubic(rx, a.radius, a.L);
+            ry = wrap_cubic(ry, a.radius, a.L);
+            rz = wrap_cubic(rz, a.radius, a.L);
+        }
+        const double r2 = r2_unfused(rx, ry, rz);
+        if (__double_as_longlong(r2) < __double_as_longlong(a.R2)) {
+            double f;
+            if (POT == 0) {
+                const double inv = rcp_fast(r2);
+                const double qq = a.sigma2 * inv;
+                const double s6 = qq * qq * qq;
+                f = (s6 * inv) * fma(2.0, s6, -1.0);
+            } else {
+                f = w_rinv3(r2, pj.w);
+            }
+            f0 = fma(f, rx, f0);
+            f1 = fma(f, ry, f1);
+            f2 = fma(f, rz, f2);
+        }
+    };
+    const int *lp = v.list + k;
+    int e = 0;
+    for (; e + 4 <= cnt; e += 4) { // four gathers in flight per lane
+        const int m0 = lp[(size_t)e * v.stride], m1 = lp[(size_t)(e + 1) * v.stride], m2 = lp[(size_t)(e + 2) * v.stride],
+                  m3 = lp[(size_t)(e + 3) * v.stride];
+        const double4 p0 = load_rec(a.sp4 + m0), p1 = load_rec(a.sp4 + m1), p2 = load_rec(a.sp4 + m2),
+                      p3 = load_rec(a.sp4 + m3);
+        pair(p0); pair(p1); pair(p2); pair(p3);
+    }
+    for (; e < cnt; ++e) pair(load_rec(a.sp4 + lp[(size_t)e * v.stride]));
+    double coeff = scale / mass[(size_t)i * mstride];
+    if (POT == 1) coeff *= charge[i];
+    if (accumulate) {
+        acc[i] += coeff * f0; acc[ld + i] += coeff * f1; acc[2 * ld + i] += coeff * f2;
+    } else {
+        acc[i] = coeff * f0; acc[ld + i] = coeff * f1; acc[2 * ld + i] = coeff * f2;
+    }
+}
+
 static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
 {
     CellPairArgs a{};
@@ -566,7 +732,7 @@ static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
 
 // pot 0: LJ (self exclusion), 1: Coulomb (self exclusion), 2: Coulomb (own-molecule exclusion)
 int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi, int mstride, double *acc_out,
-                       int64_t ld_out, bool accumulate)
+                       int64_t ld_out, bool accumulate, const int *cond)
 {
     const int n = (int)cl->n;
     if (n == 0) return NBX_OK;
@@ -578,11 +744,11 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
             const CellPairArgs a = make_args(c, cl, c->lj_R2);
             cell_pairs2_kernel<0, 0><<<blocks, 128, 0, c->stream>>>(a, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
                                                                   (int)lo, (int)hi, acc_out, ld_out, acc_flag, nullptr,
-                                                                  nullptr, nullptr, c->dyn);
+                                                                  nullptr, nullptr, c->dyn, cond);
         } else { // the exclusion (self / own molecule) was fixed when the list was built (key_div)
             const CellPairArgs a = make_args(c, cl, c->el_R2);
             cell_pairs2_kernel<1, 0><<<blocks, 128, 0, c->stream>>>(a, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi,
-                                                                  acc_out, ld_out, acc_flag, nullptr, nullptr, nullptr, c->dyn);
+                                                                  acc_out, ld_out, acc_flag, nullptr, nullptr, nullptr, c->dyn, cond);
         }
     } else if (pot == 0) {
         const CellPairArgs a = make_args(c, cl, c->lj_R2);
@@ -600,6 +766,87 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
     timer_end(c, NBX_T_PAIR_CELLS);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one cutoff potential over a cell list: plan -> (re)build -> forces.  *used = false when the box cannot be
+// cell-listed for this cutoff (the caller falls back to the all-pairs kernel).
+// ------------------------------------------------------------------------------------------------
+int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, const double *w, const int *gid, int64_t n,
+                int64_t nplan, int64_t ld, int key_div, int64_t lo, int64_t hi, int mstride, double *acc_out,
+                int64_t ld_out, bool accumulate, bool *used)
+{
+    *used = false;
+    const double R2 = R * R;
+    // Verlet lists need the whole system in one context with stable slots (not the slab decomposition)
+    bool verlet = c->opt_verlet_permille > 0 && c->opt_prefilter && !c->slab.on && c->dyn == nullptr;
+    const double skin = verlet ? R * 1e-3 * (double)c->opt_verlet_permille : 0.0;
+    if (verlet) {
+        NBX_TRY(cells_plan(c, R + skin, nplan, &cl->grid));
+        if (!cl->grid.valid) verlet = false;
+    }
+    if (!verlet) {
+        NBX_TRY(cells_plan(c, R, nplan, &cl->grid));
+        if (!cl->grid.valid) return NBX_OK;
+        *used = true;
+        cl->v_valid = false;
+        NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, nullptr));
+        return launch_cells_force(c, cl, pot, lo, hi, mstride, acc_out, ld_out, accumulate, nullptr);
+    }
+    *used = true;
+    const int ni = (int)n;
+    NBX_TRY(ensure_cells(c, cl, n, cl->grid.ncell));
+    // list capacity from the mean density: 1.5 x the expected partners within R + skin (+ slack)
+    const double L = c->bc[0];
+    const double expect = (double)n / (L * L * L) * 4.18879020478639 * (R + skin) * (R + skin) * (R + skin);
+    int cap = (int)(1.5 * expect) + 24;
+    if (cap > ni - 1) cap = ni > 1 ? ni - 1 : 1;
+    const bool same = cl->v_valid && cl->v_n == n && cl->v_px == px && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
+                      cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap;
+    if (!same) {
+        if (cl->v_cap_alloc < (int64_t)cap * cl->cap_n) {
+            NBX_TRY(dev_alloc(c, &cl->v_list, (size_t)cap * (size_t)cl->cap_n));
+            cl->v_cap_alloc = (int64_t)cap * cl->cap_n;
+        }
+        if (cl->v_ref_n < cl->cap_n) {
+            NBX_TRY(dev_alloc(c, &cl->v_ref, (size_t)3 * (size_t)cl->cap_n));
+            NBX_TRY(dev_alloc(c, &cl->v_nlist, (size_t)cl->cap_n));
+            cl->v_ref_n = cl->cap_n;
+        }
+        if (!cl->v_flags) NBX_TRY(dev_alloc(c, &cl->v_flags, (size_t)4));
+        NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 0, sizeof(int) * 4, c->stream));
+        NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream)); // [0] != 0: build now
+        NBX_CUDA(c, cudaMemsetAsync(cl->v_ref, 0, sizeof(double) * 3 * (size_t)cl->cap_n, c->stream));
+        cl->v_valid = true; cl->v_n = n; cl->v_px = px; cl->v_R = R; cl->v_skin = skin; cl->v_L = L;
+        cl->v_key_div = key_div; cl->v_nc = cl->grid.nc[0]; cl->v_cap = cap;
+    }
+    const int blocks256 = (ni + 255) / 256, blocks128 = (ni + 127) / 128;
+    const double lim = 0.5 * skin * (1.0 - 1e-9);
+    timer_begin(c, NBX_T_CELL_BUILD);
+    verlet_check_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, lim * lim, cl->v_flags);
+    timer_end(c, NBX_T_CELL_BUILD);
+    NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags));
+    CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin)); // scan threshold of the list build
+    VerletArgs v{};
+    v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n;
+    timer_begin(c, NBX_T_CELL_BUILD);
+    verlet_build_kernel<<<blocks128, 128, 0, c->stream>>>(a, v);
+    verlet_ref_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags);
+    verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags);
+    timer_end(c, NBX_T_CELL_BUILD);
+    a = make_args(c, cl, R2);
+    const int acc_flag = accumulate ? 1 : 0;
+    timer_begin(c, NBX_T_PAIR_CELLS);
+    if (pot == 0)
+        verlet_force_kernel<0><<<blocks128, 128, 0, c->stream>>>(a, v, 24.0 * c->lj_eps, c->mass, mstride, c->charge, (int)lo,
+                                                                (int)hi, acc_out, ld_out, acc_flag);
+    else
+        verlet_force_kernel<1><<<blocks128, 128, 0, c->stream>>>(a, v, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi, acc_out,
+                                                                ld_out, acc_flag);
+    timer_end(c, NBX_T_PAIR_CELLS);
+    NBX_CUDA(c, cudaGetLastError());
+    // fallback when a list overflowed (dense clusters): the cells were rebuilt above (flags[1] forces it)
+    return launch_cells_force(c, cl, pot, lo, hi, mstride, acc_out, ld_out, accumulate, cl->v_flags + 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -649,12 +896,13 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
     double b[6] = {c->bc[0], c->bc[1], c->bc[2], c->bc[3], c->bc[4], c->bc[5]};
     if (c->bc_kind == NBX_BC_CUBIC) b[1] = 0.5 * c->bc[0];
     if (use_cells) {
-        int rc = cells_build(c, cl, px, nullptr, nullptr, n, ld, 1);
+        cl->v_valid = false; // the cells are rebuilt on this call's own grid
+        int rc = cells_build(c, cl, px, nullptr, nullptr, n, ld, 1, nullptr);
         if (rc != NBX_OK) { cudaFree(d_counts); return rc; }
         a = make_args(c, cl, R2);
         if (c->opt_prefilter)
             cell_pairs2_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0, d_counts,
-                                                                  nullptr, nullptr, nullptr);
+                                                                  nullptr, nullptr, nullptr, nullptr);
         else
             cell_neigh_kernel<0, 1><<<blocks, 128, 0, c->stream>>>(a, d_counts, nullptr, nullptr);
     } else {
@@ -680,7 +928,7 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
             cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream);
             if (use_cells && c->opt_prefilter)
                 cell_pairs2_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, 0.0, nullptr, 1, nullptr, 0, ni, nullptr, 0, 0,
-                                                                      d_counts, d_off, d_list, nullptr);
+                                                                      d_counts, d_off, d_list, nullptr, nullptr);
             else if (use_cells)
                 cell_neigh_kernel<0, 2><<<blocks, 128, 0, c->stream>>>(a, d_counts, d_off, d_list);
             else
@@ -701,6 +949,7 @@ void cells_free(CellList *cl)
 {
     cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->sums);
     cudaFree(cl->arrival); cudaFree(cl->tmp_idx); cudaFree(cl->tmp_key);
+    cudaFree(cl->v_list); cudaFree(cl->v_nlist); cudaFree(cl->v_ref); cudaFree(cl->v_flags);
     cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->sp4); cudaFree(cl->sl4);
     *cl = CellList{};
 }

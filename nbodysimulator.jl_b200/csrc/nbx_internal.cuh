@@ -47,6 +47,15 @@ struct CellList {
     double4 *sp4 = nullptr;     // [n] cell order: x, y, z unwrapped (as the reference's predicate uses them), w = charge
     float4 *sl4 = nullptr;      // [n] cell order: wrapped coordinates in cell units (fp32 prefilter), w = exclusion key bits
     int64_t cap_n = 0, cap_cells = 0;
+    // Verlet list kept across evaluations (nbx_cells.cu): slots listed per slot, build-time positions, flags
+    int *v_list = nullptr, *v_nlist = nullptr, *v_flags = nullptr;
+    double *v_ref = nullptr;
+    int64_t v_cap_alloc = 0, v_ref_n = 0;
+    bool v_valid = false; // the settings below describe the resident list
+    int64_t v_n = 0;
+    const double *v_px = nullptr;
+    double v_R = 0, v_skin = 0, v_L = 0;
+    int v_key_div = 0, v_nc = 0, v_cap = 0;
 };
 
 // slab decomposition state (nbx_slab.cu)
@@ -134,6 +143,7 @@ struct nbx_ctx {
     nbx::CellList cl_lj, cl_el;
     int opt_cell_list = 1;
     int opt_prefilter = 1;
+    int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
     int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
     int64_t sym_min_n = 8192;
@@ -195,9 +205,12 @@ int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_
 // nbx_cells.cu
 int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g);
 int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, const int *gid, int64_t n, int64_t ld,
-                int key_div);
+                int key_div, const int *cond);
 int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi, int mstride, double *acc_out,
-                       int64_t ld_out, bool accumulate);
+                       int64_t ld_out, bool accumulate, const int *cond);
+int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, const double *w, const int *gid, int64_t n,
+                int64_t nplan, int64_t ld, int key_div, int64_t lo, int64_t hi, int mstride, double *acc_out,
+                int64_t ld_out, bool accumulate, bool *used);
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
                     int32_t *list, int64_t cap);
 void cells_free(CellList *cl);

@@ -223,14 +223,17 @@ def _fcc(cells, jitter, seed, drift=False):
     return w, F(u)
 
 
+@pytest.mark.parametrize("verlet", [0, 100])
 @pytest.mark.parametrize("drift", [False, True])
-def test_lj_cell_list_forces(oracle, drift):
-    w, u = _fcc(12, 0.05, 3, drift)  # 6,912 atoms, 9 cells per dimension
+def test_lj_cell_list_forces(oracle, drift, verlet):
+    w, u = _fcc(12, 0.05, 3, drift)  # 6,912 atoms, 9 cells per dimension (8 with the Verlet skin of 0.1 R)
     spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
     ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
     ctx = make_context(spec)
+    ctx.set_option("verlet_skin_permille", verlet)
     a = ctx.accel(u)
-    assert ctx.info("cells_lj") == 9 ** 3
+    assert ctx.info("cells_lj") == (8 ** 3 if verlet else 9 ** 3)
+    assert (ctx.info("verlet_lj") > 0) == bool(verlet)
     _check(a, ref)
     # the cell list changes the candidate set only: switching it off gives the same pair set
     ctx.set_option("cell_list", 0)
@@ -301,6 +304,64 @@ def test_lj_dense_clusters_overflow_the_survivor_queue(oracle):
     _check(ctx.accel(u), ref, tol=5e-12)  # near-overlapping pairs: r^-14 terms of both signs cancel
 
 
+def test_lj_verlet_list_follows_the_particles(oracle):
+    """The Verlet list (survivors of the fp32 scan within R + skin, rebuilt on the device once a particle has moved
+    skin/2) never changes the pair set: after a hot run with many rebuilds the resident accelerations equal the
+    reference loop evaluated at the resident positions, and the trajectory equals the scan-every-step one."""
+    w, u = _fcc(10, 0.05, 31)  # 4,000 atoms
+    v = F(3.0 * w["v"])
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    dt, steps = 2e-3, 80
+    out = {}
+    for skin in (0, 20, 100):
+        ctx = make_context(spec)
+        ctx.set_option("verlet_skin_permille", skin)
+        ctx.upload(u, v)
+        ctx.step_vv(dt, steps)
+        out[skin] = ctx.download(want_dv=True)
+        assert ctx.info("verlet_overflow") == 0
+        if skin:
+            assert 3 <= ctx.info("verlet_rebuilds") < steps  # rebuilt several times, not on every step
+        ctx.close()
+    s = make_oracle(oracle, spec)
+    for skin in (20, 100):
+        ug, vg, ag = out[skin]
+        _check(ag, s.rhs(ug, vg.copy(order="F"), NT))  # exact at the final state: no pair was missed or added
+        for a, b in zip(out[skin], out[0]):
+            assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()  # only the summation order differs
+
+
+def test_lj_verlet_rhs_dropin_with_arbitrary_positions(oracle):
+    """nbx_accel gets whatever positions the integrator asks for: small moves reuse the list, large ones rebuild."""
+    w, u = _fcc(8, 0.05, 33)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    s = make_oracle(oracle, spec)
+    ctx = make_context(spec)
+    rng = np.random.Generator(np.random.Philox(5))
+    for scale in (0.0, 0.02, 0.05, 0.5, 0.01, 3.0):  # sigma: within skin/2 = 0.11, beyond it, far beyond, box-sized
+        x = F(u + scale * rng.standard_normal(u.shape))
+        _check(ctx.accel(x), s.rhs(x, w["v"], NT), tol=5e-12 if scale >= 0.5 else TOL)
+
+
+def test_lj_verlet_overflow_falls_back_to_the_cell_scan(oracle):
+    """Clusters far denser than the box average overflow the list capacity (sized from the mean density): the
+    context then rescans the cells on every evaluation -- same pair set, same forces."""
+    rng = np.random.Generator(np.random.Philox(77))
+    L, R, n = 24.0, 2.5, 4000
+    centres = rng.random((3, 5)) * L
+    u = centres[:, rng.integers(0, 5, n)] + 1.1 * rng.standard_normal((3, n))
+    u[:, :1000] = rng.random((3, 1000)) * L
+    u = F(u)
+    spec = dict(ms=rng.random(n) + 0.5, bc=("cubic", L), lj=dict(eps=0.3, sigma=0.35, R=R))
+    s = make_oracle(oracle, spec)
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    assert ctx.info("verlet_lj") > 0 and ctx.info("verlet_overflow") == 1
+    _check(a, s.rhs(u, np.zeros_like(u), NT), tol=5e-12)
+    x = F(u + 0.01 * rng.standard_normal(u.shape))
+    _check(ctx.accel(x), s.rhs(x, np.zeros_like(u), NT), tol=5e-12)
+
+
 def test_lj_pairs_on_the_cutoff_boundary(oracle):
     """Pairs within a few ulp of R: the strict `r2 < R2` decision must match the reference's un-fused fp64."""
     L, R = 10.0, 2.5
@@ -358,7 +419,7 @@ def test_lj_config3_full_size_subsample(oracle):
     spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
     ctx = make_context(spec)
     a = ctx.accel(u)
-    assert ctx.info("cells_lj") == 48 ** 3
+    assert ctx.info("cells_lj") == 44 ** 3 and ctx.info("verlet_lj") > 0  # cells of edge >= R + skin, skin = 0.1 R
     targets = np.sort(np.random.Generator(np.random.Philox(9)).choice(n, 768, replace=False))
     s = make_oracle(oracle, spec)
     ref = s.accel_targets(u, targets, NT)
