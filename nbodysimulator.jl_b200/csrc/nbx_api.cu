@@ -698,13 +698,43 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
         return fail(c, NBX_ERR_INVALID, "nbx_step_vv: pair-sharded context; drive nbx_vv_forces / reduce / nbx_vv_finish");
     if (c->thermo == NBX_THERMO_LANGEVIN)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
-    for (int64_t s = 0; s < nsteps; ++s) {
+    auto one_step = [&]() -> int {
         NBX_TRY(launch_vv_pos(c, dt));
         double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
         NBX_TRY(compute_pairs(c));
         NBX_TRY(launch_vv_vel(c, dt, true));
         if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
+        return NBX_OK;
+    };
+    int64_t s = 0;
+    // Long runs replay a CUDA graph of TWO steps (the acc / acc_old swap has period two): every decision inside a
+    // step (Verlet rebuild, overflow fallback) is taken on the device, so the launch sequence is the same for all
+    // steps.  Andersen draws from a host-side step counter and the phase timers record events: both stay eager.
+    const bool graphable = c->opt_graph && !c->timing && c->thermo != NBX_THERMO_ANDERSEN && nsteps >= 32 &&
+                           c->stream != nullptr && c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
+    if (graphable) {
+        for (; s < 2; ++s) NBX_TRY(one_step()); // warm-up: allocations and attribute calls happen outside the capture
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            int rc = one_step();
+            if (rc == NBX_OK) rc = one_step();
+            e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc != NBX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        }
+        if (e == cudaSuccess && exec) {
+            for (; s + 2 <= nsteps; s += 2) {
+                e = cudaGraphLaunch(exec, c->stream);
+                if (e != cudaSuccess) break;
+            }
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(c, e, "CUDA graph of the velocity-Verlet step");
     }
+    for (; s < nsteps; ++s) NBX_TRY(one_step());
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     return NBX_OK;
 }

@@ -74,12 +74,13 @@ __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n,
                                const int *__restrict__ dyn, const int *__restrict__ cond)
 {
     if (cond && !cond[0]) return; // Verlet mode: the list is still valid, nothing to rebuild
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dyn_loc(dyn, n)) return;
-    const int cx = cell_coord(px[i], L, nc), cy = cell_coord(px[ld + i], L, nc), cz = cell_coord(px[2 * ld + i], L, nc);
-    const int cid = (cz * nc + cy) * nc + cx; // x fastest: the three x-neighbours of a cell are contiguous
-    cell_of[i] = cid;
-    arrival[i] = atomicAdd(&count[cid], 1);  // arbitrary but unique slot inside the cell (ordered later)
+    n = dyn_loc(dyn, n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int cx = cell_coord(px[i], L, nc), cy = cell_coord(px[ld + i], L, nc), cz = cell_coord(px[2 * ld + i], L, nc);
+        const int cid = (cz * nc + cy) * nc + cx; // x fastest: the three x-neighbours of a cell are contiguous
+        cell_of[i] = cid;
+        arrival[i] = atomicAdd(&count[cid], 1);  // arbitrary but unique slot inside the cell (ordered later)
+    }
 }
 
 constexpr int kScanBlock = 1024;
@@ -171,11 +172,12 @@ __global__ void scatter_kernel(const int *__restrict__ cell_of, const int *__res
                                const int *__restrict__ cond)
 {
     if (cond && !cond[0]) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dyn_loc(dyn, n)) return;
-    const int slot = start[cell_of[i]] + arrival[i];
-    tmp_idx[slot] = i;
-    if (gid) tmp_key[slot] = gid[i];
+    n = dyn_loc(dyn, n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = start[cell_of[i]] + arrival[i];
+        tmp_idx[slot] = i;
+        if (gid) tmp_key[slot] = gid[i];
+    }
 }
 
 // Final slot of a particle = cell start + its rank among the cell's members by key (global particle id, or
@@ -192,23 +194,33 @@ __global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, co
                                    const int *__restrict__ cond)
 {
     if (cond && !cond[0]) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= dyn_loc(dyn, n)) return;
-    const int i = tmp_idx[k];
-    const int cid = cell_of[i];
-    const int b = start[cid], e = start[cid + 1];
+    n = dyn_loc(dyn, n);
     const int *keys = tmp_key ? tmp_key : tmp_idx;
-    const int mine = keys[k];
-    int rank = 0;
-    for (int m = b; m < e; ++m) rank += keys[m] < mine ? 1 : 0;
-    const int dst = b + rank;
-    const double x = px[i], y = px[ld + i], z = px[2 * ld + i];
-    sorted_idx[dst] = i;
-    sp4[dst] = make_double4(x, y, z, w ? w[i] : 0.0);
     const double s = (double)nc / L;
-    sl4[dst] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
-                           (float)(wrapped_coord(z, L) * s), __int_as_float(mine / key_div));
-    scell[dst] = cid;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int i = tmp_idx[k];
+        const int cid = cell_of[i];
+        const int b = start[cid], e = start[cid + 1];
+        const int mine = keys[k];
+        int rank = 0;
+        for (int m = b; m < e; ++m) rank += keys[m] < mine ? 1 : 0;
+        const int dst = b + rank;
+        const double x = px[i], y = px[ld + i], z = px[2 * ld + i];
+        sorted_idx[dst] = i;
+        sp4[dst] = make_double4(x, y, z, w ? w[i] : 0.0);
+        sl4[dst] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
+                               (float)(wrapped_coord(z, L) * s), __int_as_float(mine / key_div));
+        scell[dst] = cid;
+    }
+}
+
+// grid of an element-wise (grid-stride) kernel: enough blocks to fill the machine, few enough that a launch whose
+// condition is off costs next to nothing
+static unsigned map_grid(const nbx_ctx *c, int n, int threads)
+{
+    const int full = (n + threads - 1) / threads;
+    const int cap = c->sm_count * (2048 / threads);
+    return (unsigned)(full < cap ? (full > 0 ? full : 1) : cap);
 }
 
 static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
@@ -247,14 +259,14 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, con
     const int nb = (ncell + kScanBlock - 1) / kScanBlock;
     timer_begin(c, NBX_T_CELL_BUILD);
     cudaMemsetAsync(cl->count, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
-    cell_id_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
+    cell_id_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
                                                            cl->count, c->dyn, cond);
     scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums, cond);
     scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb, cond);
     scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb, cond);
-    scatter_kernel<<<(ni + 255) / 256, 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
+    scatter_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
                                                            cl->tmp_key, c->dyn, cond);
-    rank_gather_kernel<<<(ni + 127) / 128, 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
+    rank_gather_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
                                                                cl->cell_of, cl->start, ni, g.len[0], g.nc[0], key_div,
                                                                cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn, cond);
     timer_end(c, NBX_T_CELL_BUILD);
@@ -420,11 +432,12 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
     __shared__ int q[kQCap * 128];
     if (cond && !cond[0]) return; // Verlet mode: runs only as the fallback when a list overflowed
     const int n_loc = dyn_loc(dyn, a.n);
-    if (blockIdx.x * 128 >= n_loc) return; // launch bound beyond the actual count (whole block)
     if (dyn) hi = min(hi, dyn[0]);
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
-    const int k = blockIdx.x * 128 + tid;
+    // block-stride over the 128-slot groups (the grid may be a bound, or deliberately small for the fallback launch)
+    for (int blk = blockIdx.x; blk * 128 < n_loc; blk += gridDim.x) {
+    const int k = blk * 128 + tid;
     const int kk = k < n_loc ? k : n_loc - 1;
     const float4 me = a.sl4[kk];
     const int key = __float_as_int(me.w);
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
     }
     flush();
 
-    if (!live) return;
+    if (!live) continue;
     if (MODE == 0) {
         double coeff = scale / mass[(size_t)i * mstride];
         if (POT == 1) coeff *= charge[i];
@@ -555,6 +568,7 @@ __global__ void __launch_bounds__(128, 8) cell_pairs2_kernel(const CellPairArgs 
             mine[m + 1] = v;
         }
     }
+    } // block-stride loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,11 +601,17 @@ struct VerletArgs {
 };
 
 // one lane per slot: the fp32 scan of cell_pairs2_kernel, survivors appended to the slot's list
+__device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const VerletArgs &v, int k);
+
 __global__ void __launch_bounds__(128) verlet_build_kernel(const CellPairArgs a, const VerletArgs v)
 {
     if (!v.flags[0] || v.flags[1]) return;
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= a.n) return;
+    for (int k = blockIdx.x * 128 + threadIdx.x; k < a.n; k += gridDim.x * 128)
+        verlet_build_slot(a, v, k);
+}
+
+__device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const VerletArgs &v, int k)
+{
     const float4 me = a.sl4[k];
     const int key = __float_as_int(me.w);
     const int cid = a.scell[k];
@@ -634,10 +654,10 @@ __global__ void verlet_ref_kernel(const double *__restrict__ px, int64_t ld, dou
                                   int *__restrict__ flags)
 {
     if (!flags[0]) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) flags[2] += 1; // rebuild counter (diagnostics)
-    if (i >= n) return;
-    ref[i] = px[i]; ref[rld + i] = px[ld + i]; ref[2 * rld + i] = px[2 * ld + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[2] += 1; // rebuild counter (diagnostics)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ref[i] = px[i]; ref[rld + i] = px[ld + i]; ref[2 * rld + i] = px[2 * ld + i];
+    }
 }
 
 // every evaluation: current exact coordinates into the cell-order records; the rebuild request is consumed here
@@ -736,7 +756,8 @@ int launch_cells_force(nbx_ctx *c, CellList *cl, int pot, int64_t lo, int64_t hi
 {
     const int n = (int)cl->n;
     if (n == 0) return NBX_OK;
-    const int blocks = (n + 127) / 128;
+    int blocks = (n + 127) / 128;
+    if (cond && blocks > c->sm_count * 8) blocks = c->sm_count * 8; // conditional (fallback) launch: block-stride, cheap when off
     const int acc_flag = accumulate ? 1 : 0;
     timer_begin(c, NBX_T_PAIR_CELLS);
     if (c->opt_prefilter) {
@@ -830,8 +851,8 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     VerletArgs v{};
     v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n;
     timer_begin(c, NBX_T_CELL_BUILD);
-    verlet_build_kernel<<<blocks128, 128, 0, c->stream>>>(a, v);
-    verlet_ref_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags);
+    verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
+    verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags);
     verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags);
     timer_end(c, NBX_T_CELL_BUILD);
     a = make_args(c, cl, R2);
