@@ -46,6 +46,8 @@ def main():
         ctx.boundary(_lib.BC_CUBIC, [w["L"]])
         ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
         ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 10 * dt, w["kB"], u.shape[1], 0)
+        if "PROF_VERLET" in os.environ:
+            ctx.set_option("verlet_skin_permille", int(os.environ["PROF_VERLET"]))
     elif what == "water":
         w = wl.water_omm(arg or 32, Rel=float(os.environ.get("PROF_REL", "0.9162")))
         u, v, dt = w["u"], w["v"], w["dt"]
