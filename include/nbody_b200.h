@@ -232,6 +232,11 @@ NBX_API int nbx_get_info(nbx_ctx *ctx, const char *key, int64_t *value);
 NBX_API int nbx_measure_fp64_peak(nbx_ctx *ctx, double *tflops, double *sm_mhz_effective);
 /* STREAM-style copy bandwidth (GB/s, read+write) of this device, for the HBM roofline. */
 NBX_API int nbx_measure_hbm_peak(nbx_ctx *ctx, double *gbs);
+/* Diagnostics for the tests: copies an internal device array of the fused cutoff step (csrc/nbx_fused.cu) to the
+ * host.  name: "start" (ncell+1 int32 padded cell starts), "pid", "scell", "nlist" (int32 per slot), "list"
+ * (cap_e x cap_slots int32), "x" (4 doubles per slot; which: position buffer 0/1).  *count receives the element
+ * count; dst may be NULL to query it; cap = capacity of dst in elements.  Not part of the reference-facing API. */
+NBX_API int nbx_debug_fetch(nbx_ctx *ctx, const char *name, int which, void *dst, int64_t cap, int64_t *count);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "nbx_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64)]),
     "nbx_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "nbx_measure_hbm_peak": (C.c_int, [_vp, _dp]),
+    "nbx_debug_fetch": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, _i64, C.POINTER(_i64)]),
 }
 
 _lib = None
@@ -335,6 +336,14 @@ class Context:
         tf, mhz = C.c_double(), C.c_double()
         self._ck(self.lib.nbx_measure_fp64_peak(self.h, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
+
+    def debug_fetch(self, name, which=0):
+        """Internal array of the fused cutoff step (diagnostics for the tests)."""
+        cnt = _i64()
+        self._ck(self.lib.nbx_debug_fetch(self.h, name.encode(), int(which), None, 0, C.byref(cnt)))
+        out = np.empty(cnt.value, dtype=np.float64 if name == "x" else np.int32)
+        self._ck(self.lib.nbx_debug_fetch(self.h, name.encode(), int(which), out.ctypes.data_as(_vp), out.size, C.byref(cnt)))
+        return out
 
     def measure_hbm_peak(self):
         g = C.c_double()

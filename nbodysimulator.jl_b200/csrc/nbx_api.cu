@@ -182,6 +182,8 @@ static void free_system(nbx_ctx *c)
     c->aos_u = c->aos_v = c->aos_dv = c->opos = c->oacc = nullptr;
     cells_free(&c->cl_lj);
     cells_free(&c->cl_el);
+    fused_free(c);
+    c->fz = FusedState();
     slab_free(c);
     c->resident = false;
 }
@@ -698,22 +700,32 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
         return fail(c, NBX_ERR_INVALID, "nbx_step_vv: pair-sharded context; drive nbx_vv_forces / reduce / nbx_vv_finish");
     if (c->thermo == NBX_THERMO_LANGEVIN)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
+    int64_t s = 0;
+    bool skip_pos = false;
+    // One cutoff potential in a cubic box: one fused kernel per step over the state in cell order (nbx_fused.cu).
+    // A cluster-list overflow hands the rest of the run back to the kernels below, positions already advanced.
+    if (fused_eligible(c, nsteps)) {
+        NBX_TRY(fused_run(c, dt, nsteps, &s));
+        if (s >= nsteps) return NBX_OK;
+        skip_pos = true;
+    }
     auto one_step = [&]() -> int {
-        NBX_TRY(launch_vv_pos(c, dt));
+        if (!skip_pos) NBX_TRY(launch_vv_pos(c, dt));
+        skip_pos = false;
         double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
         NBX_TRY(compute_pairs(c));
         NBX_TRY(launch_vv_vel(c, dt, true));
         if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
         return NBX_OK;
     };
-    int64_t s = 0;
+    if (skip_pos) { NBX_TRY(one_step()); ++s; }
     // Long runs replay a CUDA graph of TWO steps (the acc / acc_old swap has period two): every decision inside a
     // step (Verlet rebuild, overflow fallback) is taken on the device, so the launch sequence is the same for all
     // steps.  Andersen draws from a host-side step counter and the phase timers record events: both stay eager.
-    const bool graphable = c->opt_graph && !c->timing && c->thermo != NBX_THERMO_ANDERSEN && nsteps >= 32 &&
+    const bool graphable = c->opt_graph && !c->timing && c->thermo != NBX_THERMO_ANDERSEN && nsteps - s >= 32 &&
                            c->stream != nullptr && c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
     if (graphable) {
-        for (; s < 2; ++s) NBX_TRY(one_step()); // warm-up: allocations and attribute calls happen outside the capture
+        for (int w = 0; w < 2; ++w, ++s) NBX_TRY(one_step()); // warm-up: allocations and attribute calls happen outside the capture
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
@@ -866,6 +878,12 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "fused_step")) { c->opt_fused = (int)value; if (value) c->fz.disabled = false; }
+    else if (!strcmp(key, "fused_cluster")) {
+        if (value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "fused_cluster: 1, 2, 4 or 8");
+        c->opt_fused_cluster = (int)value;
+    }
+    else if (!strcmp(key, "fused_min_steps")) c->fused_min_steps = (value < 2 && value != -12345) ? 2 : value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
     else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;
@@ -895,8 +913,11 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
             NBX_CUDA(c, cudaMemcpyAsync(h, c->cl_lj.v_flags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
             NBX_CUDA(c, cudaStreamSynchronize(c->stream));
         }
-        *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2];
+        *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2] + c->fz.rebuilds_total;
     }
+    else if (!strcmp(key, "fused_steps")) *value = c->fz.steps_total;
+    else if (!strcmp(key, "fused_disabled")) *value = c->fz.disabled ? 1 : 0;
+    else if (!strcmp(key, "fused_list_cap")) *value = c->fz.cap_e;
     else if (!strcmp(key, "verlet_lj")) *value = c->cl_lj.v_valid ? c->cl_lj.v_cap : 0;
     else if (!strcmp(key, "verlet_el")) *value = c->cl_el.v_valid ? c->cl_el.v_cap : 0;
     else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;
@@ -917,6 +938,30 @@ int nbx_measure_hbm_peak(nbx_ctx *c, double *gbs)
 {
     NBX_TRY(guard(c));
     return measure_hbm_peak(c, gbs);
+}
+
+int nbx_debug_fetch(nbx_ctx *c, const char *name, int which, void *dst, int64_t cap, int64_t *count)
+{
+    NBX_TRY(guard(c));
+    if (!name || !count) return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: NULL argument");
+    const FusedState &z = c->fz;
+    if (!z.flags) return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: the fused step has not run on this context");
+    const void *src = nullptr;
+    int64_t cnt = 0;
+    size_t elem = sizeof(int);
+    if (!strcmp(name, "start")) { src = z.start; cnt = z.ncell + 1; }
+    else if (!strcmp(name, "pid")) { src = z.pid; cnt = z.cap_slots; }
+    else if (!strcmp(name, "scell")) { src = z.scell; cnt = z.cap_slots; }
+    else if (!strcmp(name, "nlist")) { src = z.nlist; cnt = z.cap_slots; }
+    else if (!strcmp(name, "list")) { src = z.list; cnt = (int64_t)z.cap_e * z.cap_slots; }
+    else if (!strcmp(name, "x")) { src = z.x[which & 1]; cnt = 4 * z.cap_slots; elem = sizeof(double); }
+    else return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: unknown array '%s'", name);
+    *count = cnt;
+    if (!dst) return NBX_OK;
+    if (cap < cnt) return fail(c, NBX_ERR_CAPACITY, "nbx_debug_fetch: %lld elements needed", (long long)cnt);
+    NBX_CUDA(c, cudaMemcpyAsync(dst, src, elem * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream));
+    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
 }
 
 } // extern "C"

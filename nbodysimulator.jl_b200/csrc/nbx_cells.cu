@@ -55,20 +55,6 @@ int cells_plan(nbx_ctx *c, double R, int64_t n, CellGrid *g)
 // ------------------------------------------------------------------------------------------------
 // rebuild kernels
 // ------------------------------------------------------------------------------------------------
-// binning copy of a coordinate, wrapped into [0, L) (cf. src/nbody_simulation_result.jl:571)
-__device__ __forceinline__ double wrapped_coord(double x, double L)
-{
-    double w = x - L * floor(x / L);
-    if (w < 0.0) w += L;
-    if (w >= L) w -= L;
-    return w;
-}
-__device__ __forceinline__ int cell_coord(double x, double L, int nc)
-{
-    int cx = (int)(wrapped_coord(x, L) * ((double)nc / L));
-    return cx < 0 ? 0 : (cx >= nc ? nc - 1 : cx);
-}
-
 __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n, double L, int nc,
                                int *__restrict__ cell_of, int *__restrict__ arrival, int *__restrict__ count,
                                const int *__restrict__ dyn, const int *__restrict__ cond)
@@ -86,13 +72,15 @@ __global__ void cell_id_kernel(const double *__restrict__ px, int64_t ld, int n,
 constexpr int kScanBlock = 1024;
 
 // exclusive scan of in[0..n) by blocks of 1024; block totals to sums[]
+// (round_to > 1: every input is first rounded up to a multiple of it -- padded cell sizes of nbx_fused.cu)
 __global__ void scan_block_kernel(const int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ sums,
-                                  const int *__restrict__ cond)
+                                  const int *__restrict__ cond, int round_to)
 {
     __shared__ int wsum[32];
     if (cond && !cond[0]) return;
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
-    const int v = i < n ? in[i] : 0;
+    int v = i < n ? in[i] : 0;
+    if (round_to > 1) v = (v + round_to - 1) / round_to * round_to;
     int s = v;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -163,6 +151,18 @@ __global__ void scan_add_kernel(int *__restrict__ out, int n, const int *__restr
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
     if (i < n) out[i] += sums[blockIdx.x];
     if (i == 0) out[n] = sums[nb]; // grand total closes the CSR
+}
+
+// exclusive scan out[0..n] of in[0..n) (inputs rounded up to multiples of round_to), out[n] = total; sums: scratch of
+// ceil(n / 1024) + 1 ints.  The three launches return at once when cond && !cond[0].
+int cells_scan(nbx_ctx *c, const int *in, int *out, int n, int *sums, int round_to, const int *cond)
+{
+    const int nb = (n + kScanBlock - 1) / kScanBlock;
+    scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(in, out, n, sums, cond, round_to);
+    scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(sums, nb, cond);
+    scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(out, n, sums, nb, cond);
+    NBX_CUDA(c, cudaGetLastError());
+    return NBX_OK;
 }
 
 // slot = cell start + arrival rank (no atomics); the ordering key travels with the index
@@ -261,7 +261,7 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, con
     cudaMemsetAsync(cl->count, 0, sizeof(int) * (size_t)(ncell + 1), c->stream);
     cell_id_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, ni, g.len[0], g.nc[0], cl->cell_of, cl->arrival,
                                                            cl->count, c->dyn, cond);
-    scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums, cond);
+    scan_block_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->count, cl->start, ncell, cl->sums, cond, 1);
     scan_sums_kernel<<<1, kScanBlock, 0, c->stream>>>(cl->sums, nb, cond);
     scan_add_kernel<<<nb, kScanBlock, 0, c->stream>>>(cl->start, ncell, cl->sums, nb, cond);
     scatter_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(cl->cell_of, cl->arrival, gid, ni, cl->start, cl->tmp_idx,
@@ -397,25 +397,6 @@ __global__ void __launch_bounds__(128) cell_neigh_kernel(const CellPairArgs a, i
 // pair kernel v2: fp32 prefilter -> per-lane survivor queue -> exact fp64 predicate + force
 // ------------------------------------------------------------------------------------------------
 constexpr int kQCap = 32; // survivors a lane can hold before the warp drains its queues
-
-// 1/x to < 1 ulp-ish (error e^3, e = seed error ~2^-22) without the IEEE division's slow path
-__device__ __forceinline__ double rcp_fast(double x)
-{
-    double y0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double e = fma(-x, y0, 1.0);
-    const double p = fma(e, e, e);
-    return fma(y0, p, y0);
-}
-
-// one 32-byte cell-order record with a single 256-bit load (LDG.E.ENL2.256): half the L1 sector traffic of
-// a 128 + 64 bit pair when every lane gathers a different record
-__device__ __forceinline__ double4 load_rec(const double4 *p)
-{
-    double4 r;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
 
 // MODE 0: accelerations; 1: in-cutoff partner counts; 2: partner lists (CSR via offsets)
 // POT 0: Lennard-Jones (src/basic_potentials.jl:253-266); 1: Coulomb (:288-297).  The exclusion (self, or own

@@ -58,6 +58,29 @@ struct CellList {
     int v_key_div = 0, v_nc = 0, v_cap = 0;
 };
 
+// Fused cutoff step (nbx_fused.cu): the state in padded cell order ("slots"), cluster lists, device flags
+struct FusedState {
+    bool disabled = false;     // a list overflowed once: the context stays on the unfused path
+    int C = 0;                 // cluster size the buffers were laid out for
+    int64_t n = 0, ncell = 0;  // system / grid the buffers were sized for
+    int64_t cap_slots = 0;     // bound on the padded slot count (multiple of 128)
+    int cap_e = 0;             // list entries per slot
+    double4 *x[2] = {nullptr, nullptr}; // [cap_slots] x, y, z (unwrapped), w = charge; read/write alternate every step
+    double4 *vm = nullptr;     // [cap_slots] vx, vy, vz, mass
+    double *sa = nullptr;      // [3][cap_slots] acceleration
+    double *ref = nullptr;     // [3][cap_slots] positions the lists were built from
+    float4 *sl = nullptr;      // [cap_slots] wrapped coordinates in cell units + exclusion key (list build prefilter)
+    int *pid = nullptr;        // [cap_slots] particle index of a slot, -1: padding
+    int *scell = nullptr;      // [cap_slots] cell of a slot
+    int *cell_of = nullptr, *arrival = nullptr, *tmp_idx = nullptr; // [n]
+    int *count = nullptr, *start = nullptr, *sums = nullptr;        // [ncell + 1] members / padded starts / scan scratch
+    int *list = nullptr;       // [cap_e][cap_slots]
+    int *nlist = nullptr;      // [cap_slots]
+    int *flags = nullptr;      // [16] device flags (nbx_fused.cu)
+    double *partial = nullptr; // [cap_slots / 128] block partials of sum m v^2
+    int64_t steps_total = 0, rebuilds_total = 0; // diagnostics (nbx_get_info "fused_steps", "verlet_rebuilds")
+};
+
 // slab decomposition state (nbx_slab.cu)
 struct SlabState {
     bool on = false, packed = false, first = false; // first: the next pack selects the slab from the full upload
@@ -145,6 +168,10 @@ struct nbx_ctx {
     int opt_prefilter = 1;
     int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
+    int opt_fused = 1;             // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu)
+    int opt_fused_cluster = 4;     // slots per cluster (1, 2, 4 or 8)
+    int64_t fused_min_steps = 16;  // shorter runs stay on the unfused path (every fused run starts with a list build)
+    nbx::FusedState fz;
     int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
     int64_t sym_min_n = 8192;
     int opt_sym_variant = 0;
@@ -214,6 +241,11 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
                     int32_t *list, int64_t cap);
 void cells_free(CellList *cl);
+int cells_scan(nbx_ctx *c, const int *in, int *out, int n, int *sums, int round_to, const int *cond);
+// nbx_fused.cu
+bool fused_eligible(nbx_ctx *c, int64_t nsteps);
+int fused_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done); // *steps_done < nsteps: continue unfused, positions already advanced
+void fused_free(nbx_ctx *c);
 // nbx_slab.cu
 int slab_init(nbx_ctx *c, int rank, int nranks);
 int slab_pack(nbx_ctx *c);
@@ -329,6 +361,39 @@ __device__ __forceinline__ double r2_unfused(double x, double y, double z)
 {
     return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
 }
+// binning copy of a coordinate, wrapped into [0, L) (cf. src/nbody_simulation_result.jl:571)
+__device__ __forceinline__ double wrapped_coord(double x, double L)
+{
+    double w = x - L * floor(x / L);
+    if (w < 0.0) w += L;
+    if (w >= L) w -= L;
+    return w;
+}
+__device__ __forceinline__ int cell_coord(double x, double L, int nc)
+{
+    int cx = (int)(wrapped_coord(x, L) * ((double)nc / L));
+    return cx < 0 ? 0 : (cx >= nc ? nc - 1 : cx);
+}
+
+// 1/x to < 1 ulp-ish (error e^3, e = seed error ~2^-22) without the IEEE division's slow path
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y0, p, y0);
+}
+
+// one 32-byte cell-order record with a single 256-bit load (LDG.E.ENL2.256): half the L1 sector traffic of
+// a 128 + 64 bit pair when every lane gathers a different record
+__device__ __forceinline__ double4 load_rec(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 #endif
 
 } // namespace nbx

@@ -141,6 +141,33 @@ def test_gravity_shard_matches_full(oracle):
     assert not part[:, :1000].any() and not part[:, 2300:].any()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_gravity_pair_sharding_partials_sum_to_the_full_result(oracle, world):
+    """Multi-GPU pair sharding on ONE device: rank r of `world` evaluates the ring offsets k = r (mod world) of
+    the Newton's-third-law kernel and ends with partial accelerations of ALL bodies; their sum over the ranks
+    (the reduce-scatter of parallel.ShardedStepper) is the full result."""
+    import torch
+
+    from nbody_b200.parallel import CudaEngine
+
+    n = 20481  # 21 tiles of 1,024 after padding: odd tile count, offsets 0..10
+    rng, u, v = _rand(n, 77)
+    spec = dict(ms=rng.random(n) + 0.1, gravity=dict(G=0.9))
+    ref = make_oracle(oracle, spec).rhs(u, v, NT)
+    total = np.zeros((3, n))
+    for r in range(world):
+        ctx = make_context(spec)
+        eng = CudaEngine(ctx, 0)
+        ctx.upload(u, v)
+        ctx.shard_pairs(r, world)
+        ctx.vv_begin(0.0)  # dt = 0: the positions stay where they are
+        ctx.vv_forces()
+        torch.cuda.synchronize()
+        total += eng.acc_rows()[:, :n].cpu().numpy()
+        ctx.close()
+    _check(total, ref)
+
+
 # ------------------------------------------------------------------------------------------
 # Coulomb / dipole, InfiniteBox (src/basic_potentials.jl:274-304, :333-365)
 # ------------------------------------------------------------------------------------------
