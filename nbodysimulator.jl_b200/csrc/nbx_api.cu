@@ -883,7 +883,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         if (value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "fused_cluster: 1, 2, 4 or 8");
         c->opt_fused_cluster = (int)value;
     }
-    else if (!strcmp(key, "fused_min_steps")) c->fused_min_steps = (value < 2 && value != -12345) ? 2 : value;
+    else if (!strcmp(key, "fused_debug")) c->opt_fused_debug = (int)value;
+    else if (!strcmp(key, "fused_min_steps")) c->fused_min_steps = value < 2 ? 2 : value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
     else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;

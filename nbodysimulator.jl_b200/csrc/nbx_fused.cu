@@ -44,7 +44,8 @@ struct FzArgs {
     double *sa, *ref;
     float4 *sl;
     int *pid, *scell, *cell_of, *arrival, *tmp_idx, *count, *start, *list, *nlist, *flags;
-    double *partial, *scal;
+    double *partial, *scal; // partial: [cap_slots / 128] block sums, then the group sums
+    int *gcount;            // arrivals per group of blocks
     double *pos, *vel, *acc;          // particle order, row stride ld
     const double *mass, *charge;
     int64_t ld, cap_slots;
@@ -59,6 +60,7 @@ struct FzArgs {
 };
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int FZ_GROUP = 64; // blocks per group of the temperature sum
 
 // rebuild chain guard: nothing to do without a request, and nothing more to do once a list has overflowed
 __device__ __forceinline__ bool fz_skip(const FzArgs &a) { return !a.flags[a.req] || a.flags[FZ_OVER]; }
@@ -234,8 +236,10 @@ template <int POT, int C, bool BEREND, bool ADVANCE>
 __global__ void __launch_bounds__(128) fz_step_kernel(const FzArgs a)
 {
     __shared__ double wsum[4];
-    __shared__ int s_last;
+    __shared__ int s_cnt;
     if (a.flags[FZ_OVER]) return; // a list overflowed: the state stays frozen at the last complete step
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads(); // the only block barrier: before any work
     const int nslots = a.flags[FZ_NSLOTS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double sc = 0.0;
@@ -248,7 +252,8 @@ __global__ void __launch_bounds__(128) fz_step_kernel(const FzArgs a)
         const int k = blockIdx.x * 128 + tid;
         const bool active = k < nslots;
         const int kk = active ? k : nslots - 1;
-        const double4 xi = a.xr[kk];
+        const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
+        const double4 xi = load_rec_nc_hint(a.xr + kk, keep);
         const int gl = lane & ~(C - 1), c0 = lane & (C - 1), gbase = kk & ~(C - 1);
         double tx[C], ty[C], tz[C], f[C][3];
 #pragma unroll
@@ -258,52 +263,85 @@ __global__ void __launch_bounds__(128) fz_step_kernel(const FzArgs a)
             tz[c] = __shfl_sync(FULL, xi.z, gl + c);
             f[c][0] = f[c][1] = f[c][2] = 0.0;
         }
-        const int cnt = active ? a.nlist[kk] : 0;
-        auto pairs = [&](const double4 pj, int m) {
+        const int cnt = active ? __ldcs(a.nlist + kk) : 0;
+        // One batch = FLY gathered records x C targets, evaluated WITHOUT a branch per pair: the displacement of
+        // every pair first, one (rare) branch for the whole batch if any component needs the wrap loops, then the
+        // exact predicate as a select (out-of-cutoff, self and past-the-end pairs contribute g = 0).  The
+        // independent chains interleave, so the FP64 latency is covered with few warps per SM.
+        constexpr int FLY = C >= 8 ? 1 : (C == 4 ? 2 : (C == 2 ? 3 : 4));
+        auto batch = [&](const double4 (&p)[FLY], const int (&m)[FLY], int e) {
+            double rx[FLY][C], ry[FLY][C], rz[FLY][C];
+            int hmax = 0;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                double rx = __dsub_rn(tx[c], pj.x), ry = __dsub_rn(ty[c], pj.y), rz = __dsub_rn(tz[c], pj.z);
-                const int hx = __double2hiint(rx) & 0x7fffffff, hy = __double2hiint(ry) & 0x7fffffff,
-                          hz = __double2hiint(rz) & 0x7fffffff;
-                if (max(hx, max(hy, hz)) >= a.hi_radius) { // rare: the pair straddles a periodic face
-                    rx = wrap_cubic(rx, a.radius, a.L);
-                    ry = wrap_cubic(ry, a.radius, a.L);
-                    rz = wrap_cubic(rz, a.radius, a.L);
+            for (int u = 0; u < FLY; ++u) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    rx[u][c] = __dsub_rn(tx[c], p[u].x);
+                    ry[u][c] = __dsub_rn(ty[c], p[u].y);
+                    rz[u][c] = __dsub_rn(tz[c], p[u].z);
+                    const int hx = __double2hiint(rx[u][c]) & 0x7fffffff, hy = __double2hiint(ry[u][c]) & 0x7fffffff,
+                              hz = __double2hiint(rz[u][c]) & 0x7fffffff;
+                    hmax = max(hmax, max(hx, max(hy, hz)));
                 }
-                const double r2 = r2_unfused(rx, ry, rz);
-                // r2 >= 0 and R2 > 0: IEEE order == order of the bit patterns (keeps the test off the FP64 pipe)
-                if (__double_as_longlong(r2) < __double_as_longlong(a.R2) && m != gbase + c) {
+            }
+            if (hmax >= a.hi_radius) { // rare: some pair of the batch straddles a periodic face
+#pragma unroll
+                for (int u = 0; u < FLY; ++u) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        rx[u][c] = wrap_cubic(rx[u][c], a.radius, a.L);
+                        ry[u][c] = wrap_cubic(ry[u][c], a.radius, a.L);
+                        rz[u][c] = wrap_cubic(rz[u][c], a.radius, a.L);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FLY; ++u) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double r2 = r2_unfused(rx[u][c], ry[u][c], rz[u][c]);
+                    // r2 >= 0 and R2 > 0: IEEE order == order of the bit patterns (keeps the test off the FP64 pipe)
+                    const bool in = __double_as_longlong(r2) < __double_as_longlong(a.R2) && m[u] != gbase + c && e + u < cnt;
+                    const double r2s = in ? r2 : 1.0;
                     double g;
                     if (POT == 0) {
-                        const double inv = rcp_fast(r2);
+                        const double inv = rcp_fast(r2s);
                         const double qq = a.sigma2 * inv;
                         const double s6 = qq * qq * qq;
                         g = (s6 * inv) * fma(2.0, s6, -1.0); // (2 s12 - s6) / r2
                     } else {
-                        g = w_rinv3(r2, pj.w);
+                        g = w_rinv3(r2s, p[u].w);
                     }
-                    f[c][0] = fma(g, rx, f[c][0]);
-                    f[c][1] = fma(g, ry, f[c][1]);
-                    f[c][2] = fma(g, rz, f[c][2]);
+                    g = in ? g : 0.0;
+                    f[c][0] = fma(g, rx[u][c], f[c][0]);
+                    f[c][1] = fma(g, ry[u][c], f[c][1]);
+                    f[c][2] = fma(g, rz[u][c], f[c][2]);
                 }
             }
         };
+        // Software pipeline over the lane's entries, FLY at a time: the indices run two batches ahead of the
+        // arithmetic and the 256-bit gathers one batch ahead, so neither latency sits on the critical path.
+        // Entries past the end read the lane's own slot (a valid address) and are not evaluated.
         const int *lp = a.list + kk;
-        constexpr int FLY = C >= 4 ? 2 : 4; // gathers in flight per lane
-        int e = 0;
-        for (; e + FLY <= cnt; e += FLY) {
-            int m[FLY];
-            double4 p[FLY];
+        int m0[FLY], m1[FLY];
+        double4 p0[FLY];
 #pragma unroll
-            for (int u = 0; u < FLY; ++u) m[u] = __ldg(lp + (size_t)(e + u) * a.cap_slots);
+        for (int u = 0; u < FLY; ++u) m0[u] = u < cnt ? __ldcs(lp + (size_t)u * a.cap_slots) : kk;
 #pragma unroll
-            for (int u = 0; u < FLY; ++u) p[u] = load_rec(a.xr + m[u]);
+        for (int u = 0; u < FLY; ++u) m1[u] = FLY + u < cnt ? __ldcs(lp + (size_t)(FLY + u) * a.cap_slots) : kk;
 #pragma unroll
-            for (int u = 0; u < FLY; ++u) pairs(p[u], m[u]);
-        }
-        for (; e < cnt; ++e) {
-            const int m = __ldg(lp + (size_t)e * a.cap_slots);
-            pairs(load_rec(a.xr + m), m);
+        for (int u = 0; u < FLY; ++u) p0[u] = load_rec_nc_hint(a.xr + m0[u], keep);
+        for (int e = 0; e < cnt; e += FLY) {
+            double4 p1[FLY];
+            int m2[FLY];
+#pragma unroll
+            for (int u = 0; u < FLY; ++u) p1[u] = load_rec_nc_hint(a.xr + m1[u], keep);
+#pragma unroll
+            for (int u = 0; u < FLY; ++u)
+                m2[u] = e + 2 * FLY + u < cnt ? __ldcs(lp + (size_t)(e + 2 * FLY + u) * a.cap_slots) : kk;
+            batch(p0, m0, e);
+#pragma unroll
+            for (int u = 0; u < FLY; ++u) { p0[u] = p1[u]; m0[u] = m1[u]; m1[u] = m2[u]; }
         }
         // the C lanes' partial sums of every target (butterfly: the same value in every lane of the cluster)
         double F0 = 0.0, F1 = 0.0, F2 = 0.0;
@@ -320,52 +358,83 @@ __global__ void __launch_bounds__(128) fz_step_kernel(const FzArgs a)
         }
         const int i = active ? a.pid[kk] : -1;
         if (i >= 0) {
-            const double4 v0 = a.vm[kk];
+            const double4 v0 = load_rec_hint(a.vm + kk, stream);
             double coeff = a.scale / v0.w;
             if (POT == 1) coeff *= xi.w;
             double an0 = coeff * F0, an1 = coeff * F1, an2 = coeff * F2;
             if (BEREND) { an0 += sc * v0.x; an1 += sc * v0.y; an2 += sc * v0.z; }
-            const double vx = fma(a.hdt, a.sa[kk] + an0, v0.x);
-            const double vy = fma(a.hdt, a.sa[a.cap_slots + kk] + an1, v0.y);
-            const double vz = fma(a.hdt, a.sa[2 * a.cap_slots + kk] + an2, v0.z);
-            a.sa[kk] = an0; a.sa[a.cap_slots + kk] = an1; a.sa[2 * a.cap_slots + kk] = an2;
-            a.vm[kk] = make_double4(vx, vy, vz, v0.w);
+            const double vx = fma(a.hdt, __ldcs(a.sa + kk) + an0, v0.x);
+            const double vy = fma(a.hdt, __ldcs(a.sa + a.cap_slots + kk) + an1, v0.y);
+            const double vz = fma(a.hdt, __ldcs(a.sa + 2 * a.cap_slots + kk) + an2, v0.z);
+            __stcs(a.sa + kk, an0); __stcs(a.sa + a.cap_slots + kk, an1); __stcs(a.sa + 2 * a.cap_slots + kk, an2);
+            store_rec_hint(a.vm + kk, make_double4(vx, vy, vz, v0.w), stream);
             mv2 = v0.w * fma(vz, vz, fma(vy, vy, vx * vx));
             if (ADVANCE) {
                 const double nx = fma(a.hdt2, an0, fma(a.dt, vx, xi.x));
                 const double ny = fma(a.hdt2, an1, fma(a.dt, vy, xi.y));
                 const double nz = fma(a.hdt2, an2, fma(a.dt, vz, xi.z));
-                a.xw[kk] = make_double4(nx, ny, nz, xi.w);
-                const double dx = nx - a.ref[kk], dy = ny - a.ref[a.cap_slots + kk], dz = nz - a.ref[2 * a.cap_slots + kk];
+                store_rec_hint(a.xw + kk, make_double4(nx, ny, nz, xi.w), keep); // the next step's gather target
+                const double dx = nx - __ldcs(a.ref + kk), dy = ny - __ldcs(a.ref + a.cap_slots + kk),
+                             dz = nz - __ldcs(a.ref + 2 * a.cap_slots + kk);
                 const double d2 = dx * dx + dy * dy + dz * dz;
                 if (!(d2 <= a.lim2)) a.flags[a.req ^ 1] = 1; // also catches NaN
             }
         } else if (active && ADVANCE) {
-            a.xw[kk] = xi; // padding slot
+            store_rec_hint(a.xw + kk, xi, keep); // padding slot
         }
     }
-    // block partial of sum m v^2 (fixed order), then the grand total by the last block to finish
+    // sum m v^2 without a block barrier (a warp that is done must not hold its slot for the slowest one): warp sums
+    // -> the block's last warp adds the four in warp order -> the last block of a group of 64 adds the group's
+    // block sums in block order -> the last group adds the group sums in group order.  Who comes last varies;
+    // what is added, and in which order, does not.
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mv2 += __shfl_down_sync(FULL, mv2, o);
-    if (lane == 0) wsum[warp] = mv2;
-    __syncthreads();
-    if (tid == 0) {
-        a.partial[blockIdx.x] = ((wsum[0] + wsum[1]) + wsum[2]) + wsum[3];
-        __threadfence();
-        s_last = atomicAdd(&a.flags[FZ_DONE], 1) == (int)gridDim.x - 1;
+    int last = 0;
+    if (lane == 0) {
+        wsum[warp] = mv2;
+        __threadfence_block();
+        last = atomicAdd(&s_cnt, 1) == 3;
     }
-    __syncthreads();
-    if (!s_last) return;
+    last = __shfl_sync(FULL, last, 0);
+    if (!last) return;
+    const int nb = (int)gridDim.x, ng = (nb + FZ_GROUP - 1) / FZ_GROUP, grp = (int)blockIdx.x / FZ_GROUP;
+    if (lane == 0) {
+        __threadfence_block();
+        const volatile double *ws = wsum;
+        a.partial[blockIdx.x] = ((ws[0] + ws[1]) + ws[2]) + ws[3];
+        __threadfence();
+        const int members = min(FZ_GROUP, nb - grp * FZ_GROUP);
+        last = atomicAdd(&a.gcount[grp], 1) == members - 1;
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (!last) return;
+    __threadfence();
+    {
+        const int b0 = grp * FZ_GROUP;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < FZ_GROUP / 32; ++q) {
+            const int b = b0 + q * 32 + lane;
+            v += b < nb ? __ldcg(a.partial + b) : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        if (lane == 0) {
+            a.partial[a.cap_slots / 128 + grp] = v;
+            a.gcount[grp] = 0;
+            __threadfence();
+            last = atomicAdd(&a.flags[FZ_DONE], 1) == ng - 1;
+        }
+        last = __shfl_sync(FULL, last, 0);
+    }
+    if (!last) return;
     __threadfence();
     double v = 0.0;
-    for (int b = tid; b < (int)gridDim.x; b += 128) v += __ldcg(a.partial + b);
+    for (int g = lane; g < ng; g += 32) v += __ldcg(a.partial + a.cap_slots / 128 + g);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-    __syncthreads();
-    if (lane == 0) wsum[warp] = v;
-    __syncthreads();
-    if (tid == 0) {
-        a.scal[0] = ((wsum[0] + wsum[1]) + wsum[2]) + wsum[3];
+    if (lane == 0) {
+        a.scal[0] = v;
         a.flags[FZ_DONE] = 0;
         a.flags[FZ_STEPS] += 1;
         a.flags[a.req] = 0; // the request this step's chain consumed
@@ -408,7 +477,7 @@ void fused_free(nbx_ctx *c)
     cudaFree(z.x[0]); cudaFree(z.x[1]); cudaFree(z.vm); cudaFree(z.sa); cudaFree(z.ref); cudaFree(z.sl);
     cudaFree(z.pid); cudaFree(z.scell); cudaFree(z.cell_of); cudaFree(z.arrival); cudaFree(z.tmp_idx);
     cudaFree(z.count); cudaFree(z.start); cudaFree(z.sums); cudaFree(z.list); cudaFree(z.nlist); cudaFree(z.flags);
-    cudaFree(z.partial);
+    cudaFree(z.partial); cudaFree(z.gcount);
     const bool disabled = z.disabled;
     const int64_t st = z.steps_total, rb = z.rebuilds_total;
     z = FusedState();
@@ -439,7 +508,9 @@ static int fz_ensure(nbx_ctx *c, int C, int64_t ncell, int cap_e)
     NBX_TRY(dev_alloc(c, &z.list, (size_t)cap_e * (size_t)cap));
     NBX_TRY(dev_alloc(c, &z.nlist, (size_t)cap));
     NBX_TRY(dev_alloc(c, &z.flags, (size_t)FZ_NFLAGS));
-    NBX_TRY(dev_alloc(c, &z.partial, (size_t)(cap / 128)));
+    NBX_TRY(dev_alloc(c, &z.partial, (size_t)(cap / 128) + (size_t)(cap / 128 / FZ_GROUP + 2)));
+    NBX_TRY(dev_alloc(c, &z.gcount, (size_t)(cap / 128 / FZ_GROUP + 2)));
+    NBX_CUDA(c, cudaMemsetAsync(z.gcount, 0, sizeof(int) * (size_t)(cap / 128 / FZ_GROUP + 2), c->stream));
     z.C = C; z.n = c->n; z.ncell = ncell; z.cap_slots = cap; z.cap_e = cap_e;
     return NBX_OK;
 }
@@ -507,7 +578,7 @@ static int fz_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done)
     a.vm = z.vm; a.sa = z.sa; a.ref = z.ref; a.sl = z.sl;
     a.pid = z.pid; a.scell = z.scell; a.cell_of = z.cell_of; a.arrival = z.arrival; a.tmp_idx = z.tmp_idx;
     a.count = z.count; a.start = z.start; a.list = z.list; a.nlist = z.nlist; a.flags = z.flags;
-    a.partial = z.partial; a.scal = c->d_scal;
+    a.partial = z.partial; a.scal = c->d_scal; a.gcount = z.gcount;
     a.pos = c->pos; a.vel = c->vel; a.acc = c->acc; a.mass = c->mass; a.charge = c->has_q ? c->charge : nullptr;
     a.ld = c->npad; a.cap_slots = z.cap_slots;
     a.n = (int)c->n; a.nc = g.nc[0]; a.ncell = (int)g.ncell; a.cap_e = z.cap_e;
@@ -546,7 +617,7 @@ static int fz_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done)
     NBX_CUDA(c, cudaMemsetAsync(z.flags, 0, sizeof(int) * FZ_NFLAGS, c->stream));
     NBX_CUDA(c, cudaMemsetAsync(z.flags + FZ_REQ1, 1, sizeof(int), c->stream)); // != 0: build before step 1
     int64_t j = 1;
-    if (c->fused_min_steps == -12345) { // test hook: build only, leave the run to the unfused path
+    if (c->opt_fused_debug & 4) { // test hook ("fused_debug" bit 2): lists only, the unfused path runs the steps
         NBX_TRY(fz_chain<C>(c, args_of(1), true));
         NBX_CUDA(c, cudaStreamSynchronize(c->stream));
         *steps_done = 0;

@@ -77,7 +77,8 @@ struct FusedState {
     int *list = nullptr;       // [cap_e][cap_slots]
     int *nlist = nullptr;      // [cap_slots]
     int *flags = nullptr;      // [16] device flags (nbx_fused.cu)
-    double *partial = nullptr; // [cap_slots / 128] block partials of sum m v^2
+    double *partial = nullptr; // [cap_slots / 128] block partials of sum m v^2, then the sums of groups of blocks
+    int *gcount = nullptr;     // arrivals per group
     int64_t steps_total = 0, rebuilds_total = 0; // diagnostics (nbx_get_info "fused_steps", "verlet_rebuilds")
 };
 
@@ -168,7 +169,12 @@ struct nbx_ctx {
     int opt_prefilter = 1;
     int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
-    int opt_fused = 1;             // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu)
+    // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu).  OFF by default: measured on
+    // B200 at 1,048,576 argon atoms the fused step costs the SUM of its parts (0.36 ms vs 0.285 ms unfused, r01c):
+    // force loop and per-slot update wait on the same L1/LSU path, so fusing them hides nothing, and cluster lists
+    // (C > 1) pay more in issue slots than they save in gathers.  Kept as a tested option ("fused_step").
+    int opt_fused = 0;
+    int opt_fused_debug = 0;
     int opt_fused_cluster = 4;     // slots per cluster (1, 2, 4 or 8)
     int64_t fused_min_steps = 16;  // shorter runs stay on the unfused path (every fused run starts with a list build)
     nbx::FusedState fz;
@@ -394,6 +400,39 @@ __device__ __forceinline__ double4 load_rec(const double4 *p)
     return r;
 }
 
+// L2 eviction policies (createpolicy): the gathered position records should stay resident, the streamed per-slot
+// state and the lists should not displace them (at 1M atoms a step streams ~400 MB past a 35 MB gather target).
+__device__ __forceinline__ uint64_t l2_policy_keep()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double4 load_rec_nc_hint(const double4 *p, uint64_t pol)
+{
+    double4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double4 load_rec_hint(const double4 *p, uint64_t pol)
+{
+    double4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void store_rec_hint(double4 *p, const double4 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+}
 #endif
 
 } // namespace nbx

@@ -132,3 +132,49 @@ def test_fused_list_overflow_hands_over_to_the_unfused_path(oracle):
     assert info["fused_disabled"] == 1 and info["fused_steps"] < steps
     for a, b in zip(got, ref):
         assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_fused_cluster_lists_cover_every_in_cutoff_pair(cluster):
+    """Structure of the cluster lists after a build (nbx_debug_fetch): padded cell starts are multiples of the
+    cluster size, a cluster never spans two cells, the slots hold a permutation of the particles, no padding slot is
+    ever listed, and every pair the reference's predicate accepts (src/boundary_conditions.jl:138-165 +
+    src/basic_potentials.jl:258) is in the union list of the target's cluster."""
+    w, u, v = _argon(6, 41, hot=0.0)  # 864 atoms, 4 cells per dimension: every cell touches the periodic faces
+    n = u.shape[1]
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ctx = make_context(spec)
+    ctx.set_option("fused_step", 1)
+    ctx.set_option("fused_cluster", cluster)
+    ctx.set_option("fused_min_steps", 2)
+    ctx.set_option("fused_debug", 4)  # build the lists, leave the steps to the unfused kernels
+    ctx.upload(u, v)
+    ctx.step_vv(0.0, 2)
+    start, pid, scell, nlist = (ctx.debug_fetch(k) for k in ("start", "pid", "scell", "nlist"))
+    cap = len(pid)
+    lst = ctx.debug_fetch("list").reshape(-1, cap)
+    x1 = ctx.debug_fetch("x", 1).reshape(-1, 4)
+    ctx.close()
+    ns = int(start[-1])
+    assert (start % cluster == 0).all() and ns % cluster == 0
+    real = pid[:ns] >= 0
+    assert np.array_equal(np.sort(pid[:ns][real]), np.arange(n))
+    cells = scell[:ns].reshape(-1, cluster)
+    assert (cells == cells[:, :1]).all()
+    assert np.array_equal(x1[:ns][real, :3], u.T[pid[:ns][real]])
+    L, R = w["L"], w["lj"]["R"]
+    pos = u.T[np.maximum(pid[:ns], 0)]
+    for g in range(ns // cluster):
+        ks = range(g * cluster, (g + 1) * cluster)
+        union = set()
+        for k in ks:
+            union |= set(lst[:nlist[k], k].tolist())
+        assert all(pid[m] >= 0 for m in union)
+        for k in ks:
+            if pid[k] < 0:
+                continue
+            d = pos[k] - pos
+            d -= L * np.round(d / L)
+            r2 = (d ** 2).sum(axis=1)
+            inside = set(np.where((r2 < R * R) & real)[0].tolist()) - {k}
+            assert inside <= union, (g, k, sorted(inside - union))
