@@ -1,0 +1,88 @@
+"""1000-step energy drift (BASELINE.json north_star: "1000-step energy drift must stay within the reference's
+drift").  The reference's drift is the drift of ITS arithmetic under velocity Verlet: the CPU oracle's RHS stepped by
+the textbook scheme (oracle.velocity_verlet; the integrator itself lives upstream).  The device
+loop (nbx_step_vv) must not drift more than that, measured with the reference's own energy definitions
+(src/nbody_simulation_result.jl:209-212, :293-397) evaluated by the oracle on both final states.
+"""
+import numpy as np
+import pytest
+
+import nbody_b200.workloads as wl
+from tests._common import F, make_context, make_oracle
+
+pytestmark = pytest.mark.gpu
+NT = 16
+
+
+def _drifts(oracle, spec, u, v, dt, steps):
+    s = make_oracle(oracle, spec)
+    e0 = s.kinetic_energy(v) + s.potential_energy(u)
+    ur, vr = oracle.velocity_verlet(s, u, v, dt, steps, NT)
+    ctx = make_context(spec)
+    ctx.upload(u, v)
+    ctx.step_vv(dt, steps)
+    ug, vg, _ = ctx.download()
+    ek_dev, ep_dev, _ = ctx.energy()
+    ctx.close()
+    e_ref = s.kinetic_energy(vr) + s.potential_energy(ur)
+    e_gpu = s.kinetic_energy(vg) + s.potential_energy(ug)
+    assert ek_dev + ep_dev == pytest.approx(e_gpu, rel=1e-10)  # the device reductions agree with the oracle's
+    return (e_ref - e0) / abs(e0), (e_gpu - e0) / abs(e0), np.abs(ug - ur).max() / np.abs(ur).max()
+
+
+def test_lj_argon_1000_steps(oracle):
+    """Liquid argon, reduced units, cubic PBC, R = 2.25 sigma, NVE, the example's time step
+    (examples/liquid_argon_reduced.jl:11-32): 500 atoms, lattice + jitter."""
+    w = wl.fcc_argon_reduced(5)
+    rng = np.random.Generator(np.random.Philox(61))
+    u = F(w["u"] + 0.03 * rng.standard_normal(w["u"].shape))
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    d_ref, d_gpu, du = _drifts(oracle, spec, u, w["v"], 10 * w["dt"], 1000)
+    assert abs(d_gpu) <= 1.02 * abs(d_ref) + 1e-12, (d_ref, d_gpu)
+    assert abs(d_ref) < 1e-3 and du < 1e-6  # same trajectory up to the order of summation
+
+
+def test_charged_particles_1000_steps(oracle):
+    """test/electrostatics_test.jl:84-119 at 216 charges: cubic PBC, cutoff 0.45 L, 1000 VV steps, drift < 1e-3."""
+    rng = np.random.Generator(np.random.Philox(62))
+    m, L, k = 6, 1.0, 9e9
+    g = (np.arange(m) + 0.5) * (L / m)
+    u = F(np.stack(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1) + 0.01 * rng.standard_normal((3, m ** 3)))
+    n = u.shape[1]
+    ijk = np.indices((m, m, m)).reshape(3, -1).sum(axis=0)
+    spec = dict(ms=np.ones(n), qs=1e-6 * np.where(ijk % 2 == 0, 1.0, -1.0), bc=("cubic", L), coulomb=dict(k=k, R=0.45 * L))
+    d_ref, d_gpu, du = _drifts(oracle, spec, u, F(np.zeros((3, n))), 1e-4, 1000)
+    assert abs(d_gpu) <= 1.02 * abs(d_ref) + 1e-12, (d_ref, d_gpu)
+    assert abs(d_ref) < 1e-3 and du < 1e-6
+
+
+def test_water_spcfw_1000_steps(oracle):
+    """SPC/Fw water, OMM units (examples/water_spc_fw_omm_units.jl:3-33; test/water_test.jl:76-77 asks < 1 % over 10
+    steps): 64 molecules, both cutoffs 0.45 L, 1000 steps of the example's dt."""
+    w = wl.water_omm(4)
+    R = 0.45 * w["L"]
+    lj = dict(w["lj"]); lj["R"] = R
+    spec = dict(ms=w["ms"], qs=w["qs"], water=True, bc=("cubic", w["L"]), lj=lj, coulomb=dict(k=w["coulomb"]["k"], R=R),
+                spcfw=w["spcfw"])
+    d_ref, d_gpu, du = _drifts(oracle, spec, w["u"], w["v"], w["dt"], 1000)
+    assert abs(d_gpu) <= 1.02 * abs(d_ref) + 1e-9, (d_ref, d_gpu)
+    assert abs(d_ref) < 1e-2 and du < 1e-5
+
+
+def test_lj_argon_32k_atoms_1000_steps_property():
+    """Size-independent property at a size the CPU oracle cannot step: 32,000 atoms, 1000 steps, |dE/E| small and the
+    total momentum stays at rounding level (Newton's third law on every pair)."""
+    w = wl.fcc_argon_reduced(20)
+    rng = np.random.Generator(np.random.Philox(63))
+    u = F(w["u"] + 0.03 * rng.standard_normal(w["u"].shape))
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ctx = make_context(spec)
+    ctx.upload(u, w["v"])
+    ek0, ep0, _ = ctx.energy()
+    ctx.step_vv(10 * w["dt"], 1000)
+    ek1, ep1, _ = ctx.energy()
+    _, vg, _ = ctx.download()
+    ctx.close()
+    assert abs((ek1 + ep1) - (ek0 + ep0)) / abs(ek0 + ep0) < 2e-4
+    p = (vg * w["ms"]).sum(axis=1)
+    assert np.abs(p).max() < 1e-9 * np.abs(vg * w["ms"]).sum()
