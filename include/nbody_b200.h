@@ -216,6 +216,14 @@ NBX_API int nbx_synchronize(nbx_ctx *ctx);
 /* Device pointers of the resident SoA state: which = 0 pos, 1 vel, 2 acc; each is
  * double[3][*ld] (x-row, y-row, z-row) with row stride *ld >= n. */
 NBX_API int nbx_device_ptr(nbx_ctx *ctx, int which, void **ptr, int64_t *ld);
+/* Split-phase RHS drop-in for a pair-sharded context (nbx_shard + nbx_shard_pairs; unbounded gravity / Coulomb).
+ * nbx_accel_begin copies u (HOST, 3 x ncols as nbx_accel) to the device and enqueues this rank's share of the
+ * unordered pair set: the resident acceleration rows (nbx_device_ptr which = 2) then hold PARTIAL sums for ALL
+ * bodies.  The caller adds the rows across the ranks on ctx's stream (reduce-scatter; parallel.ShardedStepper does
+ * it over NCCL) and nbx_accel_end returns the columns [lo, hi) of nbx_shard into dv (HOST; other columns zero) and
+ * synchronises.  Replaces the same call as nbx_accel (soode_system!, src/nbody_to_ode.jl:474-488). */
+NBX_API int nbx_accel_begin(nbx_ctx *ctx, const double *u);
+NBX_API int nbx_accel_end(nbx_ctx *ctx, double *dv);
 /* Device-pointer form of nbx_accel (u, v, dv are DEVICE pointers, AoS 3 x ncols). */
 NBX_API int nbx_accel_device(nbx_ctx *ctx, const double *u_dev, double *v_dev, double t,
                              double *dv_dev);

@@ -72,6 +72,8 @@ SIGNATURES = {
     "nbx_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64)]),
     "nbx_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "nbx_measure_hbm_peak": (C.c_int, [_vp, _dp]),
+    "nbx_accel_begin": (C.c_int, [_vp, _dp]),
+    "nbx_accel_end": (C.c_int, [_vp, _dp]),
     "nbx_debug_fetch": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, _i64, C.POINTER(_i64)]),
 }
 
@@ -199,6 +201,15 @@ class Context:
                 raise ValueError("v must be a float64 Fortran-ordered (3, ncols) array (it may be written)")
         dv = np.empty((3, self.ncols), order="F") if out is None else out
         self._ck(self.lib.nbx_accel(self.h, _p(u), _p(v), float(t), _p(dv)))
+        return dv
+
+    def accel_begin(self, u):
+        """Split-phase RHS drop-in of a pair-sharded context: partial accelerations of all bodies stay on the device."""
+        self._ck(self.lib.nbx_accel_begin(self.h, _p(_f(u, self.ncols))))
+
+    def accel_end(self, out=None):
+        dv = np.empty((3, self.ncols), order="F") if out is None else out
+        self._ck(self.lib.nbx_accel_end(self.h, _p(dv)))
         return dv
 
     # -- resident stepping ---------------------------------------------------------------------

@@ -599,6 +599,34 @@ int nbx_accel(nbx_ctx *c, const double *u, double *v, double t, double *dv)
     return finish_and_check(c);
 }
 
+int nbx_accel_begin(nbx_ctx *c, const double *u)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_accel_begin"));
+    NBX_TRY(no_slab(c, "nbx_accel_begin"));
+    if (!u) return fail(c, NBX_ERR_INVALID, "nbx_accel_begin: u is required");
+    if (c->pair_nranks <= 1) return fail(c, NBX_ERR_INVALID, "nbx_accel_begin: the context is not pair-sharded (use nbx_accel)");
+    if (needs_velocity(c)) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_accel_begin: thermostats with an RHS term need nbx_accel");
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u, bytes, cudaMemcpyHostToDevice, c->stream));
+    NBX_TRY(launch_aos_to_soa(c, c->aos_u, c->pos, c->n));
+    NBX_TRY(check_finite(c, c->pos, c->n));
+    NBX_TRY(compute_pairs(c)); // partial sums of all bodies (pair sharding)
+    c->resident = false;
+    return NBX_OK;
+}
+
+int nbx_accel_end(nbx_ctx *c, double *dv)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_accel_end"));
+    if (!dv) return fail(c, NBX_ERR_INVALID, "nbx_accel_end: dv is required");
+    NBX_TRY(launch_soa_to_aos(c, c->acc, c->aos_dv, c->n, c->ncols, c->tgt_lo, c->tgt_hi));
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    NBX_CUDA(c, cudaMemcpyAsync(dv, c->aos_dv, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return finish_and_check(c);
+}
+
 int nbx_accel_device(nbx_ctx *c, const double *u_dev, double *v_dev, double t, double *dv_dev)
 {
     (void)t;

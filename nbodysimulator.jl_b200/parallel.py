@@ -27,6 +27,7 @@ The plumbing works on an *engine* (duck-typed):
     engine.acc_rows()  -> tensor   (3, ld) view of the SoA acceleration rows after vv_forces
     engine.scalars()   -> tensor   (16,) view of the scalar block ([0] = shard's sum m v^2)
     engine.vv_begin(dt) / engine.vv_forces() / engine.vv_finish(dt) / engine.needs_temperature
+    engine.accel(u, out) / engine.accel_begin(u) / engine.accel_end(out)   RHS drop-in, whole and split-phase
 ``CudaEngine`` wraps a libnbody_b200 context; the CPU tests drive the same plumbing over gloo with a
 NumPy engine (tests/test_parallel_gloo.py).
 """
@@ -95,6 +96,15 @@ class CudaEngine:
 
     def vv_forces(self):
         self.ctx.vv_forces()
+
+    def accel(self, u, out=None):
+        return self.ctx.accel(u, out=out)
+
+    def accel_begin(self, u):
+        self.ctx.accel_begin(u)
+
+    def accel_end(self, out=None):
+        return self.ctx.accel_end(out)
 
     def vv_finish(self, dt):
         self.ctx.vv_finish(dt)
@@ -224,6 +234,18 @@ class ShardedStepper:
         else:
             for d in range(3):
                 dist.all_reduce(rows[d, :n], op=dist.ReduceOp.SUM, group=self.group)
+
+    def accel(self, u, out=None):
+        """The RHS drop-in (soode_system!, src/nbody_to_ode.jl:474-488) over the group: every rank passes the same
+        host positions u (3, n) and gets the accelerations of its own columns [lo, hi) in ``out`` (other columns
+        zero).  pairs mode: each rank evaluates its share of the unordered pairs, one reduce-scatter of the
+        acceleration rows completes the own block; targets mode: the own block against all sources, no exchange."""
+        e = self.engine
+        if self.mode != "pairs" or self.world == 1:
+            return e.accel(u, out)
+        e.accel_begin(u)
+        self._sum_partial_accelerations()
+        return e.accel_end(out)
 
     def step(self, dt: float, nsteps: int = 1):
         for _ in range(nsteps):

@@ -101,6 +101,7 @@ def main():
         return ctx
 
     ok = True
+    a_ref = None
     for thermo in (False, True):
         ref = make(thermo)
         ref.upload(u, v)
@@ -119,6 +120,15 @@ def main():
             lo, hi = st.lo, st.hi
             eu = np.abs(ug - ur).max() / np.abs(ur).max()          # all positions are gathered on every rank
             ev = np.abs(vg[:, lo:hi] - vr[:, lo:hi]).max() / np.abs(vr).max()
+            if not thermo:  # the RHS drop-in over the group (pairs mode: accel_begin / reduce-scatter / accel_end)
+                a_own = st.accel(u)
+                if a_ref is None:
+                    one = make(False)
+                    a_ref = one.accel(u).copy()
+                    one.close()
+                ea = np.abs(a_own[:, lo:hi] - a_ref[:, lo:hi]).max() / np.abs(a_ref).max()
+                outside = np.abs(a_own[:, :lo]).max(initial=0.0) + np.abs(a_own[:, hi:]).max(initial=0.0)
+                ev = max(ev, ea, 1.0 if outside else 0.0)
             t = torch.tensor([eu, ev], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:

@@ -97,6 +97,23 @@ class NumpyEngine:
         self.vel[:, s] += 0.5 * dt * (self.acc_old + self.accbuf[:, s])
         self.scal[0] = float(np.dot(self.ms[s], (self.vel[:, s] ** 2).sum(axis=0)))
 
+    # RHS drop-in: whole (targets mode) and split-phase (pairs mode)
+    def accel(self, u, out=None):
+        out = np.zeros((3, self.n), order="F") if out is None else out
+        out[:] = 0.0
+        out[:, self.lo:self.hi] = self.sys.accel_targets(np.asfortranarray(u), np.arange(self.lo, self.hi))
+        return out
+
+    def accel_begin(self, u):
+        self.pos[:, :self.n] = u
+        self.vv_forces()
+
+    def accel_end(self, out=None):
+        out = np.zeros((3, self.n), order="F") if out is None else out
+        out[:] = 0.0
+        out[:, self.lo:self.hi] = self.accbuf[:, self.lo:self.hi]
+        return out
+
 
 def _worker(rank, world, port, n, out_dir, mode):
     import torch.distributed as dist
@@ -114,6 +131,44 @@ def _worker(rank, world, port, n, out_dir, mode):
     np.save(os.path.join(out_dir, f"scal{rank}.npy"), eng.scal[:1])
     np.save(os.path.join(out_dir, f"vel{rank}.npy"), eng.vel[:, st.lo:st.hi])
     dist.destroy_process_group()
+
+
+def _accel_worker(rank, world, port, n, out_dir, mode):
+    import torch.distributed as dist
+
+    import nbody_b200.workloads as wl
+    from nbody_b200.parallel import ShardedStepper
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    u, v, ms = wl.plummer(n, seed=3)
+    st = ShardedStepper(NumpyEngine(dict(ms=ms, gravity=dict(G=1.0)), u, v), mode=mode)
+    rng = np.random.Generator(np.random.Philox(9))
+    x = np.asfortranarray(u + 0.01 * rng.standard_normal(u.shape))  # the integrator asks for other positions
+    dv = st.accel(x)
+    np.save(os.path.join(out_dir, f"dv{rank}.npy"), dv)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["targets", "pairs"])
+def test_two_rank_rhs_dropin_matches_serial(tmp_path, mode):
+    """ShardedStepper.accel: every rank returns its own block of soode_system!'s dv (src/nbody_to_ode.jl:474-488);
+    pairs mode goes through accel_begin / reduce / accel_end."""
+    import torch.multiprocessing as mp
+
+    import nbody_b200.workloads as wl
+    from oracle import nbody_oracle as orc
+    from tests._common import make_oracle
+
+    n, world = 64, 2
+    mp.spawn(_accel_worker, args=(world, _free_port(), n, str(tmp_path), mode), nprocs=world, join=True)
+    u, v, ms = wl.plummer(n, seed=3)
+    rng = np.random.Generator(np.random.Philox(9))
+    x = np.asfortranarray(u + 0.01 * rng.standard_normal(u.shape))
+    ref = make_oracle(orc, dict(ms=ms, gravity=dict(G=1.0))).rhs(x, v)
+    total = sum(np.load(os.path.join(str(tmp_path), f"dv{r}.npy")) for r in range(world))
+    assert np.abs(total - ref).max() <= 1e-12 * np.abs(ref).max()
+    blocks = [np.load(os.path.join(str(tmp_path), f"dv{r}.npy")) for r in range(world)]
+    assert not (blocks[0][:, n // 2:]).any() and not (blocks[1][:, :n // 2]).any()
 
 
 def _free_port():
