@@ -251,6 +251,74 @@ def lj_secondary(local, world, steps, warmup, cells=LJ_CELLS):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# the remaining BASELINE.json configs (4: SPC/Fw water x 32,768 molecules; 5: 65,536 charged / magnetic bodies,
+# Langevin SDE variant), one GPU, state resident, CUDA events on the library's stream -- reported beside the headline
+# ------------------------------------------------------------------------------------------------
+def other_configs(local, steps=5):
+    import torch
+
+    import nbody_b200.workloads as wl
+    from nbody_b200 import _lib
+
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    out = {}
+
+    def timed(ctx, run, k):
+        run(2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    try:
+        for tag, rel, what in (("config4_water_cutoff_0.9162nm", 0.9162, "cell lists for O-O Lennard-Jones and Coulomb"),
+                               ("config4_water_cutoff_0.49L", None, "Coulomb cutoff 4.886 nm = half the box: all-pairs kernel "
+                                                                    "with the exact periodic predicate")):
+            w = wl.water_omm(32, Rel=rel)
+            ctx = _lib.Context(local)
+            ctx.set_stream(side.cuda_stream)
+            ctx.system(w["ms"], qs=w["qs"], water=True)
+            ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+            ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+            ctx.add_coulomb(w["coulomb"]["k"], w["coulomb"]["R"])
+            ctx.add_spcfw(w["spcfw"]["rOH"], w["spcfw"]["aHOH"], w["spcfw"]["kb"], w["spcfw"]["ka"])
+            ctx.upload(w["u"], w["v"])
+            ms = timed(ctx, lambda k: ctx.step_vv(w["dt"], k), steps if rel is None else 10 * steps)
+            out[tag] = {"metric": "SPC/Fw water molecule-steps/s (32,768 molecules, LJ + Coulomb cutoff + bonds/angles, velocity Verlet)",
+                        "value": w["nmol"] / (ms * 1e-3), "unit": "molecule-steps/s", "ms_per_step": ms, "n_atoms": 3 * w["nmol"],
+                        "coulomb_cutoff_nm": w["coulomb"]["R"], "path": what}
+            ctx.close()
+        n = 65536
+        for tag, gen in (("config5a_coulomb", wl.charged_lattice), ("config5b_dipole", wl.dipole_lattice)):
+            w = gen(n)
+            ctx = _lib.Context(local)
+            ctx.set_stream(side.cuda_stream)
+            ctx.system(w["ms"], qs=w.get("qs"), mm=w.get("mm"))
+            if "coulomb" in w:
+                ctx.add_coulomb(w["coulomb"]["k"], float("inf"))
+            else:
+                ctx.add_dipole(w["dipole"]["mu_4pi"])
+            # Langevin SDE variant (src/nbody_to_ode.jl:567-598, Euler-Maruyama as test/thermostat_test.jl:85-89)
+            ctx.thermostat(_lib.THERMO_LANGEVIN, 90.0, 10.0, 1.38e-23, n, 0)
+            ctx.upload(w["u"], w["v"])
+            dt = 1e-9
+            ms = timed(ctx, lambda k: ctx.step_em(dt, k), steps)
+            out[tag] = {"metric": "pair-interactions/s (65,536 bodies, all-pairs, Langevin thermostat, Euler-Maruyama steps)",
+                        "value": float(n) * float(n - 1) / (ms * 1e-3), "unit": "pair-interactions/s", "ms_per_step": ms,
+                        "n_bodies": n}
+            ctx.close()
+    except Exception as e:  # never lose the headline line
+        out["error"] = repr(e)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    return out
+
+
 def lj_rooflines(out, hbm_peak, fp64_peak, src):
     value = out["value"]
     out["roofline_fp64"] = {"achieved": LJ_FLOP_PER_ATOM_STEP * value / 1e12, "peak": fp64_peak * out["n_gpus"],
@@ -374,6 +442,7 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    others = other_configs(local) if (world == 1 and not args.no_lj) else None
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peak_tf, eff_mhz = ctx.measure_fp64_peak()
@@ -427,6 +496,8 @@ def run_b200(args):
             hbm, src = measured_hbm_peak()
             lj_rooflines(lj, hbm, peak_tf, src)
         out["lj"] = lj
+    if others is not None:
+        out["other_configs"] = others
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

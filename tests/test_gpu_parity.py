@@ -106,6 +106,28 @@ def test_gravity_plummer_262k_subsample(oracle):
     assert (np.abs(p) <= 1e-11 * scale).all()
 
 
+def test_gravity_plummer_1m_subsample(oracle):
+    """BASELINE config 2 at its largest size (1,048,576 bodies; the 8-GPU target of the north star, here on one
+    device: 1.1e12 ordered pairs): 512 targets against all sources, and the momentum property."""
+    n = 1048576
+    u, v, ms = wl.plummer(n)
+    spec = dict(ms=ms, gravity=dict(G=1.0))
+    ctx = make_context(spec)
+    a = ctx.accel(u)
+    ctx.close()
+    assert np.isfinite(a).all()
+    targets = np.random.Generator(np.random.Philox(8)).choice(n, 512, replace=False)
+    ref = make_oracle(oracle, spec).accel_targets(u, targets, NT)
+    exact = oracle.gravity_targets_ld(u, ms, 1.0, targets, NT)
+    e_gpu = rel_err_per_body(a[:, targets], exact)
+    e_ref = rel_err_per_body(ref, exact)
+    e_pair = rel_err_per_body(a[:, targets], ref)
+    ok = (e_pair <= TOL) | (e_gpu <= np.maximum(TOL, 2.0 * e_ref))
+    assert ok.all(), (e_pair.max(), e_gpu.max(), e_ref.max())
+    p = (a * ms).sum(axis=1)
+    assert (np.abs(p) <= 1e-11 * np.abs(a * ms).sum(axis=1)).all()
+
+
 @pytest.mark.parametrize("uniform", [False, True])
 @pytest.mark.parametrize("n", [8192, 9000, 20481])
 def test_gravity_symmetric_pairs_kernel(oracle, n, uniform):
