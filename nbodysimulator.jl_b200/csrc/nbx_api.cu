@@ -906,6 +906,10 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "verlet_lanes")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "verlet_lanes: 0, 1, 2, 4 or 8");
+        c->opt_verlet_lanes = (int)value;
+    }
     else if (!strcmp(key, "fused_step")) { c->opt_fused = (int)value; if (value) c->fz.disabled = false; }
     else if (!strcmp(key, "fused_cluster")) {
         if (value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "fused_cluster: 1, 2, 4 or 8");

@@ -654,19 +654,25 @@ __global__ void verlet_refresh_kernel(const double *__restrict__ px, int64_t ld,
     sp4[k] = make_double4(px[i], px[ld + i], px[2 * ld + i], w ? w[i] : 0.0);
 }
 
-template <int POT>
+// P lanes share one target (P = 1, 2, 4, 8): lane s of the group takes the entries s, s + P, ... and the partial sums
+// meet in a butterfly (fixed order).  Small systems with long lists (32,768 water oxygens x 136 entries, 98,304
+// charges x 424) otherwise leave most of the machine idle and walk every list serially.
+template <int POT, int P>
 __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a, const VerletArgs v, double scale,
                                                            const double *__restrict__ mass, int mstride,
                                                            const double *__restrict__ charge, int lo, int hi,
                                                            double *__restrict__ acc, int64_t ld, int accumulate)
 {
     if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= a.n) return;
-    const int i = a.sorted_idx[k];
-    if (i < lo || i >= hi) return;
-    const double4 pi = a.sp4[k];
-    const int cnt = v.nlist[k];
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const int k = t / P, sub = t % P;
+    const bool valid = k < a.n;
+    const int kk = valid ? k : a.n - 1;
+    const int i = a.sorted_idx[kk];
+    const bool live = valid && i >= lo && i < hi;
+    if (P == 1 && !live) return;
+    const double4 pi = a.sp4[kk];
+    const int cnt = live ? v.nlist[kk] : 0;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
     auto pair = [&](const double4 pj) {
         double rx = __dsub_rn(pi.x, pj.x), ry = __dsub_rn(pi.y, pj.y), rz = __dsub_rn(pi.z, pj.z);
@@ -693,16 +699,25 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
             f2 = fma(f, rz, f2);
         }
     };
-    const int *lp = v.list + k;
-    int e = 0;
-    for (; e + 4 <= cnt; e += 4) { // four gathers in flight per lane
-        const int m0 = lp[(size_t)e * v.stride], m1 = lp[(size_t)(e + 1) * v.stride], m2 = lp[(size_t)(e + 2) * v.stride],
-                  m3 = lp[(size_t)(e + 3) * v.stride];
+    const int *lp = v.list + kk;
+    int e = sub;
+    for (; e + 3 * P < cnt; e += 4 * P) { // four gathers in flight per lane
+        const int m0 = lp[(size_t)e * v.stride], m1 = lp[(size_t)(e + P) * v.stride], m2 = lp[(size_t)(e + 2 * P) * v.stride],
+                  m3 = lp[(size_t)(e + 3 * P) * v.stride];
         const double4 p0 = load_rec(a.sp4 + m0), p1 = load_rec(a.sp4 + m1), p2 = load_rec(a.sp4 + m2),
                       p3 = load_rec(a.sp4 + m3);
         pair(p0); pair(p1); pair(p2); pair(p3);
     }
-    for (; e < cnt; ++e) pair(load_rec(a.sp4 + lp[(size_t)e * v.stride]));
+    for (; e < cnt; e += P) pair(load_rec(a.sp4 + lp[(size_t)e * v.stride]));
+    if (P > 1) {
+#pragma unroll
+        for (int o = 1; o < P; o <<= 1) {
+            f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+            f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+            f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+        }
+        if (!live || sub != 0) return;
+    }
     double coeff = scale / mass[(size_t)i * mstride];
     if (POT == 1) coeff *= charge[i];
     if (accumulate) {
@@ -710,6 +725,25 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
     } else {
         acc[i] = coeff * f0; acc[ld + i] = coeff * f1; acc[2 * ld + i] = coeff * f2;
     }
+}
+
+template <int POT>
+static void launch_verlet_force(nbx_ctx *c, const CellPairArgs &a, const VerletArgs &v, double scale, int mstride, int lo,
+                                int hi, double *acc_out, int64_t ld_out, int acc_flag)
+{
+    // lanes per target: enough threads to fill the machine (148 SMs x 2048) when the system is small
+    const int64_t want = (int64_t)c->sm_count * 2048;
+    int P = 1;
+    while (P < 8 && (int64_t)a.n * P < want) P <<= 1;
+    if (c->opt_verlet_lanes > 0) P = c->opt_verlet_lanes;
+    const unsigned blocks = (unsigned)(((int64_t)a.n * P + 127) / 128);
+#define NBX_VF(PP) verlet_force_kernel<POT, PP><<<blocks, 128, 0, c->stream>>>(a, v, scale, c->mass, mstride, c->charge, lo, hi, \
+                                                                              acc_out, ld_out, acc_flag)
+    if (P == 1) NBX_VF(1);
+    else if (P == 2) NBX_VF(2);
+    else if (P == 4) NBX_VF(4);
+    else NBX_VF(8);
+#undef NBX_VF
 }
 
 static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
@@ -822,7 +856,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         cl->v_valid = true; cl->v_n = n; cl->v_px = px; cl->v_R = R; cl->v_skin = skin; cl->v_L = L;
         cl->v_key_div = key_div; cl->v_nc = cl->grid.nc[0]; cl->v_cap = cap;
     }
-    const int blocks256 = (ni + 255) / 256, blocks128 = (ni + 127) / 128;
+    const int blocks256 = (ni + 255) / 256;
     const double lim = 0.5 * skin * (1.0 - 1e-9);
     timer_begin(c, NBX_T_CELL_BUILD);
     verlet_check_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, lim * lim, cl->v_flags);
@@ -839,12 +873,8 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     a = make_args(c, cl, R2);
     const int acc_flag = accumulate ? 1 : 0;
     timer_begin(c, NBX_T_PAIR_CELLS);
-    if (pot == 0)
-        verlet_force_kernel<0><<<blocks128, 128, 0, c->stream>>>(a, v, 24.0 * c->lj_eps, c->mass, mstride, c->charge, (int)lo,
-                                                                (int)hi, acc_out, ld_out, acc_flag);
-    else
-        verlet_force_kernel<1><<<blocks128, 128, 0, c->stream>>>(a, v, c->el_k, c->mass, 1, c->charge, (int)lo, (int)hi, acc_out,
-                                                                ld_out, acc_flag);
+    if (pot == 0) launch_verlet_force<0>(c, a, v, 24.0 * c->lj_eps, mstride, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
+    else launch_verlet_force<1>(c, a, v, c->el_k, 1, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
     timer_end(c, NBX_T_PAIR_CELLS);
     NBX_CUDA(c, cudaGetLastError());
     // fallback when a list overflowed (dense clusters): the cells were rebuilt above (flags[1] forces it)

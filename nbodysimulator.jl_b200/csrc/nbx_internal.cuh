@@ -169,6 +169,7 @@ struct nbx_ctx {
     int opt_prefilter = 1;
     int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
+    int opt_verlet_lanes = 0;      // lanes per target of the Verlet force kernel (0: chosen from the system size; 1, 2, 4, 8)
     // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu).  OFF by default: measured on
     // B200 at 1,048,576 argon atoms the fused step costs the SUM of its parts (0.36 ms vs 0.285 ms unfused, r01c):
     // force loop and per-slot update wait on the same L1/LSU path, so fusing them hides nothing, and cluster lists

@@ -296,20 +296,30 @@ int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int 
                     double *acc_out, bool accumulate)
 {
     // variants (option "sym_variant"): T stationary and U travelling bodies per lane, CTAs per SM, ring unroll.
-    // Measured on the 262,144-body sphere (r01): <8,2,2,2> 44.6 ms, <4,4,3,2> 46.6 ms, <4,4,3,1> 49.2 ms.
+    // Measured on the 262,144-body sphere, equal masses (r01c, ms per launch): <8,2,2,4> 42.7 (default), <8,1,2,2> 43.5,
+    // <8,2,2,2> 44.2, <8,2,2,1> 44.2, <8,4,2,1> 44.9, <8,1,3,4> 46.8, <4,4,3,2> 47.2; ordered kernel 70.8.
     switch (c->opt_sym_variant) {
     case 1:
         if (uniform) return run_sym<4, 4, true, 3, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
         return run_sym<4, 4, false, 3, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     case 2:
-        if (uniform) return run_sym<8, 2, true, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
-        return run_sym<8, 2, false, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        if (uniform) return run_sym<8, 2, true, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 2, false, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     case 3:
         if (uniform) return run_sym<8, 1, true, 3, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
         return run_sym<8, 1, false, 3, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 4:
+        if (uniform) return run_sym<8, 2, true, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 2, false, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 5:
+        if (uniform) return run_sym<8, 1, true, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 1, false, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 6:
+        if (uniform) return run_sym<8, 4, true, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 4, false, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     default:
-        if (uniform) return run_sym<8, 2, true, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
-        return run_sym<8, 2, false, 2, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        if (uniform) return run_sym<8, 2, true, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 2, false, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     }
 }
 

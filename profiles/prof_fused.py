@@ -15,7 +15,7 @@ ctx = _lib.Context(0)
 ctx.system(w["ms"]); ctx.boundary(_lib.BC_CUBIC, [w["L"]])
 ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
 ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 10 * w["dt"], w["kB"], n, 0)
-ctx.set_option("graph", 0); ctx.set_option("fused_cluster", C)
+ctx.set_option("graph", 0); ctx.set_option("fused_step", 1); ctx.set_option("fused_cluster", C)
 ctx.upload(u, w["v"])
 ctx.step_vv(w["dt"], steps)
 print("fused steps", ctx.info("fused_steps"))

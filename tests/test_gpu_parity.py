@@ -380,6 +380,28 @@ def test_lj_verlet_list_follows_the_particles(oracle):
             assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()  # only the summation order differs
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+def test_verlet_force_lanes_per_target(oracle, lanes):
+    """The list kernel with 1, 2, 4 or 8 lanes per target (small systems with long lists): same pair set, sums in a
+    fixed butterfly order; LJ argon and the two pair terms of SPC/Fw water."""
+    w, u = _fcc(8, 0.05, 35, drift=True)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ctx = make_context(spec)
+    ctx.set_option("verlet_lanes", lanes)
+    a = ctx.accel(u).copy()
+    assert ctx.info("verlet_lj") > 0 and ctx.info("verlet_overflow") == 0
+    _check(a, make_oracle(oracle, spec).rhs(u, w["v"], NT))
+    assert np.array_equal(a, ctx.accel(u))  # deterministic
+    ctx.close()
+    ww, uw, wspec = _water(12, 4, Rel=0.9162)
+    ctx = make_context(wspec)
+    ctx.set_option("verlet_lanes", lanes)
+    aw = ctx.accel(uw)
+    assert ctx.info("verlet_lj") > 0 and ctx.info("verlet_el") > 0
+    _check(aw, make_oracle(oracle, wspec).rhs(uw, ww["v"], NT))
+    ctx.close()
+
+
 def test_lj_verlet_rhs_dropin_with_arbitrary_positions(oracle):
     """nbx_accel gets whatever positions the integrator asks for: small moves reuse the list, large ones rebuild."""
     w, u = _fcc(8, 0.05, 33)
