@@ -191,6 +191,25 @@ NBX_API int nbx_slab_init(nbx_ctx *ctx, int rank, int nranks);
 NBX_API int nbx_slab_pack(nbx_ctx *ctx);
 NBX_API int nbx_slab_unpack(nbx_ctx *ctx, int64_t *counts);
 NBX_API int nbx_slab_check(nbx_ctx *ctx, int64_t *counts);
+/* Verlet lists inside a slab (one cutoff potential, option verlet_skin_permille > 0; nbx_get_info "slab_verlet" = 1):
+ * the local numbering stays put between COLLECTIVE rebuilds, so the lists survive.  Every step the driver calls
+ * nbx_slab_verlet_check after nbx_vv_begin (out2 = two device ints: [0] some own particle moved more than
+ * soft_fraction x skin/2 since the last rebuild, [1] more than skin/2 or a list overflowed = the lists are no longer
+ * a superset), combines the ints over all ranks (max) and, when it decides to rebuild -- on the same step on every
+ * rank -- runs
+ *     nbx_slab_pack; exchange; nbx_slab_unpack;                 (migration, as without lists)
+ *     nbx_set_option("slab_record_halo", 1); nbx_slab_pack; exchange; nbx_slab_unpack;   (halo incl. the arrivals)
+ *     nbx_set_option("slab_rebuild", 1); nbx_vv_forces; nbx_vv_finish
+ * and otherwise only moves the positions of the recorded boundary-layer particles:
+ *     nbx_slab_refresh_send; exchange; nbx_slab_refresh_recv; nbx_vv_forces; nbx_vv_finish.
+ * parallel.SlabStepper reads the combined ints two steps late (no host stall) and rebuilds at a soft limit of 0.75.
+ * nbx_slab_prime builds the lists from the positions as they are (after a migration + halo round) without touching
+ * the resident accelerations: the driver calls it once after the initial distribution, so that the first step already
+ * runs from lists and the rebuild schedule is that of a single context. */
+NBX_API int nbx_slab_prime(nbx_ctx *ctx);
+NBX_API int nbx_slab_refresh_send(nbx_ctx *ctx);
+NBX_API int nbx_slab_refresh_recv(nbx_ctx *ctx);
+NBX_API int nbx_slab_verlet_check(nbx_ctx *ctx, double soft_fraction, void *out2_dev);
 /* Direct exchange over NVLink peer memory (optional, between nbx_slab_init and the first nbx_slab_pack):
  * nbx_slab_rx returns this rank's receive area (device pointer, size, and -- if ipc_handle64 != NULL -- its
  * 64-byte CUDA IPC handle for another process).  nbx_slab_connect maps the neighbours' receive areas, given

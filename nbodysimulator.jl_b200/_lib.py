@@ -56,6 +56,10 @@ SIGNATURES = {
     "nbx_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
     "nbx_slab_pack": (C.c_int, [_vp]),
     "nbx_slab_unpack": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "nbx_slab_prime": (C.c_int, [_vp]),
+    "nbx_slab_refresh_send": (C.c_int, [_vp]),
+    "nbx_slab_refresh_recv": (C.c_int, [_vp]),
+    "nbx_slab_verlet_check": (C.c_int, [_vp, C.c_double, _vp]),
     "nbx_slab_rx": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _vp]),
     "nbx_slab_connect": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "nbx_slab_check": (C.c_int, [_vp, C.POINTER(_i64)]),
@@ -281,6 +285,19 @@ class Context:
         counts = (_i64 * 6)()
         self._ck(self.lib.nbx_slab_check(self.h, counts))
         return [int(x) for x in counts]
+
+    def slab_prime(self):
+        self._ck(self.lib.nbx_slab_prime(self.h))
+
+    def slab_refresh_send(self):
+        self._ck(self.lib.nbx_slab_refresh_send(self.h))
+
+    def slab_refresh_recv(self):
+        self._ck(self.lib.nbx_slab_refresh_recv(self.h))
+
+    def slab_verlet_check(self, out_ptr, soft_fraction=0.75):
+        """Enqueues the displacement check of the own particles; out_ptr: device pointer to two int32."""
+        self._ck(self.lib.nbx_slab_verlet_check(self.h, float(soft_fraction), _vp(out_ptr)))
 
     def slab_rx(self, want_handle=False):
         """(device pointer, doubles, 64-byte CUDA IPC handle or None) of this slab's receive area."""

@@ -9,6 +9,8 @@
 
 #include "nbx_internal.cuh"
 
+#include <utility>
+
 namespace nbx {
 
 static thread_local std::string g_create_error;
@@ -497,6 +499,40 @@ int nbx_slab_unpack(nbx_ctx *c, int64_t *counts)
     return slab_unpack(c, counts);
 }
 
+int nbx_slab_prime(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_prime"));
+    if (!c->slab.on || !c->slab.verlet || c->slab.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_prime: no complete Verlet-list slab state");
+    // evaluate the pair terms into the spare acceleration rows: cells and lists get built, a(t) stays what it is
+    c->slab.rebuild_now = true;
+    std::swap(c->acc, c->acc_old);
+    const int rc = compute_pairs(c);
+    std::swap(c->acc, c->acc_old);
+    return rc;
+}
+
+int nbx_slab_refresh_send(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_refresh_send"));
+    return slab_refresh_send(c);
+}
+
+int nbx_slab_refresh_recv(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_refresh_recv"));
+    return slab_refresh_recv(c);
+}
+
+int nbx_slab_verlet_check(nbx_ctx *c, double soft_fraction, void *out2_dev)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_verlet_check"));
+    return slab_verlet_check(c, soft_fraction, static_cast<int *>(out2_dev));
+}
+
 int nbx_slab_rx(nbx_ctx *c, void **ptr, int64_t *ndoubles, void *ipc_handle64)
 {
     NBX_TRY(guard(c));
@@ -906,6 +942,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "slab_rebuild")) c->slab.rebuild_now = value != 0;
+    else if (!strcmp(key, "slab_record_halo")) c->slab.record_halo = value != 0;
     else if (!strcmp(key, "verlet_lanes")) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "verlet_lanes: 0, 1, 2, 4 or 8");
         c->opt_verlet_lanes = (int)value;
@@ -939,6 +977,7 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "slab_layer_lo")) *value = c->slab.c0;
     else if (!strcmp(key, "slab_layer_hi")) *value = c->slab.c1;
     else if (!strcmp(key, "slab_layers")) *value = c->slab.nc;
+    else if (!strcmp(key, "slab_verlet")) *value = (c->slab.on && c->slab.verlet) ? 1 : 0;
     else if (!strcmp(key, "verlet_overflow") || !strcmp(key, "verlet_rebuilds")) {
         // device flags of the LJ list (synchronises): [1] sticky overflow, [2] rebuilds so far
         int h[4] = {0, 0, 0, 0};

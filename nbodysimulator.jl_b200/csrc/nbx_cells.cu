@@ -579,6 +579,7 @@ struct VerletArgs {
     int *flags;
     int cap;
     int64_t stride;
+    const int *dyn; // slab mode: [0] own, [1] ghosts on the device (launch sizes are bounds); else null
 };
 
 // one lane per slot: the fp32 scan of cell_pairs2_kernel, survivors appended to the slot's list
@@ -587,7 +588,8 @@ __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const V
 __global__ void __launch_bounds__(128) verlet_build_kernel(const CellPairArgs a, const VerletArgs v)
 {
     if (!v.flags[0] || v.flags[1]) return;
-    for (int k = blockIdx.x * 128 + threadIdx.x; k < a.n; k += gridDim.x * 128)
+    const int n_loc = dyn_loc(v.dyn, a.n);
+    for (int k = blockIdx.x * 128 + threadIdx.x; k < n_loc; k += gridDim.x * 128)
         verlet_build_slot(a, v, k);
 }
 
@@ -632,9 +634,10 @@ __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const V
 
 // after a rebuild: remember the positions the list was built from
 __global__ void verlet_ref_kernel(const double *__restrict__ px, int64_t ld, double *__restrict__ ref, int64_t rld, int n,
-                                  int *__restrict__ flags)
+                                  int *__restrict__ flags, const int *__restrict__ dyn)
 {
     if (!flags[0]) return;
+    n = dyn_loc(dyn, n);
     if (blockIdx.x == 0 && threadIdx.x == 0) flags[2] += 1; // rebuild counter (diagnostics)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         ref[i] = px[i]; ref[rld + i] = px[ld + i]; ref[2 * rld + i] = px[2 * ld + i];
@@ -645,11 +648,11 @@ __global__ void verlet_ref_kernel(const double *__restrict__ px, int64_t ld, dou
 // (nothing after this kernel reads flags[0])
 __global__ void verlet_refresh_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ w,
                                       const int *__restrict__ sorted_idx, int n, double4 *__restrict__ sp4,
-                                      int *__restrict__ flags)
+                                      int *__restrict__ flags, const int *__restrict__ dyn)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) flags[0] = 0;
-    if (k >= n) return;
+    if (k >= dyn_loc(dyn, n)) return;
     const int i = sorted_idx[k];
     sp4[k] = make_double4(px[i], px[ld + i], px[2 * ld + i], w ? w[i] : 0.0);
 }
@@ -666,8 +669,10 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
     if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
     const int t = blockIdx.x * 128 + threadIdx.x;
     const int k = t / P, sub = t % P;
-    const bool valid = k < a.n;
-    const int kk = valid ? k : a.n - 1;
+    const int n_loc = dyn_loc(v.dyn, a.n);
+    if (v.dyn) hi = min(hi, v.dyn[0]); // slab mode: the own particles are the targets, the ghosts only sources
+    const bool valid = k < n_loc;
+    const int kk = valid ? k : max(n_loc - 1, 0);
     const int i = a.sorted_idx[kk];
     const bool live = valid && i >= lo && i < hi;
     if (P == 1 && !live) return;
@@ -814,8 +819,10 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
 {
     *used = false;
     const double R2 = R * R;
-    // Verlet lists need the whole system in one context with stable slots (not the slab decomposition)
-    bool verlet = c->opt_verlet_permille > 0 && c->opt_prefilter && !c->slab.on && c->dyn == nullptr;
+    // Verlet lists need stable slots: the whole system in one context, or a slab that renumbers only at collective
+    // rebuilds (SlabState::verlet: the host layer decides when, nbx_slab.cu)
+    const bool slabv = c->slab.on && c->slab.verlet;
+    bool verlet = c->opt_verlet_permille > 0 && c->opt_prefilter && ((!c->slab.on && c->dyn == nullptr) || slabv);
     const double skin = verlet ? R * 1e-3 * (double)c->opt_verlet_permille : 0.0;
     if (verlet) {
         NBX_TRY(cells_plan(c, R + skin, nplan, &cl->grid));
@@ -834,10 +841,10 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     NBX_TRY(ensure_cells(c, cl, n, cl->grid.ncell));
     // list capacity from the mean density: 1.5 x the expected partners within R + skin (+ slack)
     const double L = c->bc[0];
-    const double expect = (double)n / (L * L * L) * 4.18879020478639 * (R + skin) * (R + skin) * (R + skin);
+    const double expect = (double)nplan / (L * L * L) * 4.18879020478639 * (R + skin) * (R + skin) * (R + skin);
     int cap = (int)(1.5 * expect) + 24;
     if (cap > ni - 1) cap = ni > 1 ? ni - 1 : 1;
-    const bool same = cl->v_valid && cl->v_n == n && cl->v_px == px && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
+    const bool same = cl->v_valid && cl->v_n == n && (slabv || cl->v_px == px) && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
                       cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap;
     if (!same) {
         if (cl->v_cap_alloc < (int64_t)cap * cl->cap_n) {
@@ -855,8 +862,36 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         NBX_CUDA(c, cudaMemsetAsync(cl->v_ref, 0, sizeof(double) * 3 * (size_t)cl->cap_n, c->stream));
         cl->v_valid = true; cl->v_n = n; cl->v_px = px; cl->v_R = R; cl->v_skin = skin; cl->v_L = L;
         cl->v_key_div = key_div; cl->v_nc = cl->grid.nc[0]; cl->v_cap = cap;
+        if (slabv) c->slab.rebuild_now = true;
     }
     const int blocks256 = (ni + 255) / 256;
+    if (slabv) {
+        // the host layer decided (collectively, SlabStepper) whether this evaluation follows a migration round: then the
+        // local numbering is new and cells + lists are rebuilt here, unconditionally; otherwise nothing is even launched
+        CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin));
+        VerletArgs v{};
+        v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = c->dyn;
+        if (c->slab.rebuild_now) {
+            NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream));
+            NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags));
+            timer_begin(c, NBX_T_CELL_BUILD);
+            verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
+            verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags, c->dyn);
+            timer_end(c, NBX_T_CELL_BUILD);
+            c->slab.rebuild_now = false;
+        }
+        timer_begin(c, NBX_T_CELL_BUILD);
+        verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, c->dyn);
+        timer_end(c, NBX_T_CELL_BUILD);
+        a = make_args(c, cl, R2);
+        const int acc_flag = accumulate ? 1 : 0;
+        timer_begin(c, NBX_T_PAIR_CELLS);
+        if (pot == 0) launch_verlet_force<0>(c, a, v, 24.0 * c->lj_eps, mstride, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
+        else launch_verlet_force<1>(c, a, v, c->el_k, 1, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
+        timer_end(c, NBX_T_PAIR_CELLS);
+        NBX_CUDA(c, cudaGetLastError());
+        return NBX_OK; // a list overflow is reported by nbx_slab_verlet_check (no scan fallback on stale cells)
+    }
     const double lim = 0.5 * skin * (1.0 - 1e-9);
     timer_begin(c, NBX_T_CELL_BUILD);
     verlet_check_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, lim * lim, cl->v_flags);
@@ -864,11 +899,11 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags));
     CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin)); // scan threshold of the list build
     VerletArgs v{};
-    v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n;
+    v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = nullptr;
     timer_begin(c, NBX_T_CELL_BUILD);
     verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
-    verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags);
-    verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags);
+    verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags, nullptr);
+    verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, nullptr);
     timer_end(c, NBX_T_CELL_BUILD);
     a = make_args(c, cl, R2);
     const int acc_flag = accumulate ? 1 : 0;

@@ -101,6 +101,12 @@ struct SlabState {
     double *pos2 = nullptr, *vel2 = nullptr, *acc2 = nullptr, *mass2 = nullptr, *charge2 = nullptr; // compaction targets
     int *gid_a = nullptr, *gid_b = nullptr;
     int *blockcnt = nullptr, *blockoff = nullptr, *d_counts = nullptr, *h_counts = nullptr;
+    // Verlet lists inside the slab (one cutoff potential, skin > 0): local slots stay put between COLLECTIVE
+    // rebuilds; in between only the positions of a fixed halo index list travel (slab_refresh_send / _recv)
+    bool verlet = false;
+    bool rebuild_now = true;   // the host's decision for the next force evaluation (set after a migration round)
+    bool record_halo = false;  // the next pack records the halo index lists (second round of a rebuild)
+    int *halo_idx[2] = {nullptr, nullptr}; // [capH] local indices of the own boundary-layer particles, message order
 };
 
 } // namespace nbx
@@ -259,6 +265,9 @@ int slab_pack(nbx_ctx *c);
 int slab_unpack(nbx_ctx *c, int64_t *counts);
 int slab_check(nbx_ctx *c, int64_t *counts);
 int slab_connect(nbx_ctx *c, const void *left_handle, const void *right_handle, void *left_ptr, void *right_ptr);
+int slab_refresh_send(nbx_ctx *c);
+int slab_refresh_recv(nbx_ctx *c);
+int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev);
 void slab_free(nbx_ctx *c);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);

@@ -46,7 +46,8 @@ enum { CAT_STAY = 0, CAT_MIGL = 1, CAT_MIGR = 2, CAT_HALOL = 3, CAT_HALOR = 4, C
 // device counters
 enum { CNT_ARRL = 5, CNT_ARRR = 6, CNT_N = 8 };
 // persistent counters d_n
-enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_MSG = 4, DN_TICKET = 5, DN_TIMEOUT = 6, DN_N = 8 };
+enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_MSG = 4, DN_TICKET = 5, DN_TIMEOUT = 6, DN_HALOL = 8, DN_HALOR = 9,
+       DN_N = 12 };
 constexpr int kRxHdr = 16; // doubles in front of the receive area: [0] 'message m from the left is complete', [1] same from the right
 
 
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
                                                                int *__restrict__ counts, double *__restrict__ sendL,
                                                                double *__restrict__ sendR, int capM, int capH,
                                                                int *__restrict__ dn, const int *__restrict__ dyn,
-                                                               double *peerL, double *peerR, int64_t msg_doubles)
+                                                               double *peerL, double *peerR, int64_t msg_doubles,
+                                                               int *__restrict__ halo_idxL, int *__restrict__ halo_idxR)
 {
     __shared__ int wcnt[kSlabBlock / 32][CAT_N];
     __shared__ int last_block;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
         if (remR) { remR[0] = hr0; remR[1] = hr1; }
         if (counts[CAT_MIGL] > capM || counts[CAT_MIGR] > capM || counts[CAT_HALOL] > capH || counts[CAT_HALOR] > capH)
             dn[DN_CAP] = 1;
+        if (halo_idxL) { dn[DN_HALOL] = (int)hl1; dn[DN_HALOR] = (int)hr1; }
     }
     if (i < n && f != 0u) {
         const double x = src.pos[i], y = src.pos[ld + i], z = src.pos[2 * ld + i];
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
                 double *out = side == 0 ? (remL ? remL : sendL) : (remR ? remR : sendR);
                 double *rec = out + kHdr + (size_t)capM * kMigW + (size_t)rank[cat] * kHaloW;
                 rec[0] = (double)id; rec[1] = x; rec[2] = y; rec[3] = z; rec[4] = q;
+                if (halo_idxL) (side == 0 ? halo_idxL : halo_idxR)[rank[cat]] = d; // slot of this record from now on
             }
         } else {
             const int cat = (f & (1u << CAT_MIGL)) ? CAT_MIGL : CAT_MIGR;
@@ -229,6 +233,107 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
     }
 }
 
+// direct mode: wait until both neighbours have published message `msg` in this rank's receive area (thread 0 of every
+// block spins, bounded by 10 s of %globaltimer: a dead neighbour must not hang the GPU).  Returns false on a timeout.
+__device__ __forceinline__ bool slab_wait_messages(double *rx, int msg)
+{
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) {
+        timed_out = 0;
+        const volatile long long *flag = reinterpret_cast<const volatile long long *>(rx);
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (flag[0] < msg || flag[1] < msg) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) { timed_out = 1; break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    return !timed_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// between rebuilds (Verlet lists inside the slab): nothing migrates and nothing is renumbered; the positions of the
+// boundary-layer particles recorded at the rebuild travel in the same message layout, by the same flag protocol
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSlabBlock) slab_halo_send_kernel(SlabArrays src, int64_t ld, const int *__restrict__ idxL,
+                                                                    const int *__restrict__ idxR, int *__restrict__ dn,
+                                                                    double *__restrict__ sendL, double *__restrict__ sendR,
+                                                                    int capM, int capH, double *peerL, double *peerR,
+                                                                    int64_t msg_doubles)
+{
+    __shared__ int last_block;
+    const int msg = dn[DN_MSG] + 1;
+    double *outL = peerL ? rx_msg(peerL, 1, msg & 1, msg_doubles) : sendL;
+    double *outR = peerR ? rx_msg(peerR, 0, msg & 1, msg_doubles) : sendR;
+    const int nL = dn[DN_HALOL], nR = dn[DN_HALOR];
+    const int t = blockIdx.x * kSlabBlock + threadIdx.x;
+    if (t == 0) {
+        outL[0] = 0.0; outL[1] = (double)nL; outR[0] = 0.0; outR[1] = (double)nR;
+        sendL[0] = 0.0; sendL[1] = (double)nL; sendR[0] = 0.0; sendR[1] = (double)nR; // no migrants kept as ghosts
+    }
+    const int side = t / capH, k = t - side * capH;
+    if (side < 2 && k < (side == 0 ? nL : nR)) {
+        const int i = (side == 0 ? idxL : idxR)[k];
+        double *rec = (side == 0 ? outL : outR) + kHdr + (size_t)capM * kMigW + (size_t)k * kHaloW;
+        rec[0] = (double)(src.gid ? src.gid[i] : i);
+        rec[1] = src.pos[i]; rec[2] = src.pos[ld + i]; rec[3] = src.pos[2 * ld + i];
+        rec[4] = src.charge ? src.charge[i] : 0.0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_block = atomicAdd(&dn[DN_TICKET], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last_block && threadIdx.x == 0) {
+        __threadfence_system();
+        if (peerL) *reinterpret_cast<volatile long long *>(peerL + 1) = (long long)msg;
+        if (peerR) *reinterpret_cast<volatile long long *>(peerR + 0) = (long long)msg;
+        dn[DN_TICKET] = 0;
+        dn[DN_MSG] = msg;
+    }
+}
+
+// the ghost slots were laid down by the rebuild's unpack: halos from the left, then from the right, after the own
+__global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restrict__ dn, double *rx, int64_t msg_doubles,
+                                      int direct, int capM, int capH)
+{
+    const int msg = dn[DN_MSG];
+    if (direct && !slab_wait_messages(rx, msg)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) dn[DN_TIMEOUT] = 1;
+        return;
+    }
+    const double *recvL = rx_msg(rx, 0, direct ? (msg & 1) : 0, msg_doubles);
+    const double *recvR = rx_msg(rx, 1, direct ? (msg & 1) : 0, msg_doubles);
+    const int haloL = min((int)recvL[1], capH), haloR = min((int)recvR[1], capH);
+    const int n_own = dn[DN_OWN];
+    if (haloL + haloR != dn[DN_GHOST]) { // a neighbour changed its halo without a collective rebuild
+        if (blockIdx.x == 0 && threadIdx.x == 0) dn[DN_CAP] = 1;
+        return;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = t / capH, k = t - side * capH;
+    if (side >= 2 || k >= (side == 0 ? haloL : haloR)) return;
+    const double *rec = (side == 0 ? recvL : recvR) + kHdr + (size_t)capM * kMigW + (size_t)k * kHaloW;
+    const int d = n_own + (side == 0 ? 0 : haloL) + k;
+    dst.pos[d] = rec[1]; dst.pos[ld + d] = rec[2]; dst.pos[2 * ld + d] = rec[3];
+}
+
+// displacement of the own particles from the positions the lists were built from: out[0] |= beyond the soft limit
+// (ask for a collective rebuild), out[1] |= beyond skin/2 or a list overflowed (the lists are no longer a superset)
+__global__ void slab_verlet_check_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ ref, int64_t rld,
+                                         const int *__restrict__ dn, double soft2, double hard2,
+                                         const int *__restrict__ vflags, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && vflags[1]) out[1] = 1;
+    if (i >= dn[DN_OWN]) return;
+    const double dx = px[i] - ref[i], dy = px[ld + i] - ref[rld + i], dz = px[2 * ld + i] - ref[2 * rld + i];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 <= soft2)) out[0] = 1;
+    if (!(d2 <= hard2)) out[1] = 1;
+}
+
 // segments, in the order they are laid down: arrivals (left, right) extend the own particles; the ghosts are
 // the migrants just sent (left, right) and the received halos (left, right)
 __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
@@ -238,24 +343,9 @@ __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols,
 {
     // direct mode: the neighbours store into this rank's receive area and raise its flags (message number)
     const int msg = dn[DN_MSG];
-    if (direct) {
-        __shared__ int timed_out;
-        if (threadIdx.x == 0) {
-            timed_out = 0;
-            const volatile long long *flag = reinterpret_cast<const volatile long long *>(rx);
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (flag[0] < msg || flag[1] < msg) {
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 10000000000ull) { timed_out = 1; break; } // 10 s: a neighbour died; do not hang the GPU
-            }
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (timed_out) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) { dn[DN_TIMEOUT] = 1; dn[DN_OWN] = 0; dn[DN_GHOST] = 0; }
-            return;
-        }
+    if (direct && !slab_wait_messages(rx, msg)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { dn[DN_TIMEOUT] = 1; dn[DN_OWN] = 0; dn[DN_GHOST] = 0; }
+        return;
     }
     const double *recvL = rx_msg(rx, 0, direct ? (msg & 1) : 0, msg_doubles);
     const double *recvR = rx_msg(rx, 1, direct ? (msg & 1) : 0, msg_doubles);
@@ -317,7 +407,7 @@ void slab_free(nbx_ctx *c)
     cudaFree(s.msg[0]); cudaFree(s.msg[1]); cudaFree(s.rx);
     cudaFree(s.pos2); cudaFree(s.vel2); cudaFree(s.acc2); cudaFree(s.mass2); cudaFree(s.charge2);
     cudaFree(s.gid_a); cudaFree(s.gid_b); cudaFree(s.blockcnt); cudaFree(s.blockoff); cudaFree(s.d_counts);
-    cudaFree(s.d_n);
+    cudaFree(s.d_n); cudaFree(s.halo_idx[0]); cudaFree(s.halo_idx[1]);
     if (s.h_counts) cudaFreeHost(s.h_counts);
     if (s.ev_counts) cudaEventDestroy(s.ev_counts);
     s = SlabState{};
@@ -355,8 +445,10 @@ static int run_pack(nbx_ctx *c, int init)
     slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
     slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0], s.msg[1],
                                                       (int)s.capM, (int)s.capH, s.d_n, dyn, s.direct ? s.peer[0] : nullptr,
-                                                      s.direct ? s.peer[1] : nullptr, s.msg_doubles);
+                                                      s.direct ? s.peer[1] : nullptr, s.msg_doubles,
+                                                      s.record_halo ? s.halo_idx[0] : nullptr, s.record_halo ? s.halo_idx[1] : nullptr);
     NBX_CUDA(c, cudaGetLastError());
+    s.record_halo = false;
     // the compacted state is the state from here on (stream-ordered: later kernels see the new pointers)
     std::swap(c->pos, s.pos2); std::swap(c->vel, s.vel2); std::swap(c->acc, s.acc2); std::swap(c->mass, s.mass2);
     if (c->charge) std::swap(c->charge, s.charge2);
@@ -378,12 +470,22 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     if (c->tgt_lo != 0 || c->tgt_hi != c->n || c->pair_nranks > 1) return fail(c, NBX_ERR_INVALID, "nbx_slab_init: context is already sharded");
     const double R = fmax(c->has_lj ? c->lj_R : 0.0, coul_cut ? c->el_R : 0.0);
     CellGrid grid;
-    NBX_TRY(cells_plan(c, R, c->n, &grid));
+    // Verlet lists inside the slab: one cutoff potential and a grid of edge >= R + skin that still gives every rank two
+    // layers (the ghost layer must hold everything within R + skin of the face)
+    bool verlet = c->opt_verlet_permille > 0 && c->opt_prefilter && (c->has_lj != coul_cut);
+    if (verlet) {
+        const double skin = R * 1e-3 * (double)c->opt_verlet_permille; // as cells_pairs computes it
+        NBX_TRY(cells_plan(c, R + skin, c->n, &grid));
+        if (!grid.valid || (nranks > 1 && grid.nc[0] < 2 * nranks)) verlet = false;
+    }
+    if (!verlet) NBX_TRY(cells_plan(c, R, c->n, &grid));
     if (!grid.valid) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: the cutoff does not allow a cell grid (R >= L/3)");
     const int nc = grid.nc[0];
     if (nranks > 1 && nc < 2 * nranks)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_slab_init: %d cell layers cannot give %d slabs of >= 2 layers", nc, nranks);
     SlabState &s = c->slab;
+    s.verlet = verlet;
+    s.rebuild_now = true;
     s.rank = rank; s.nranks = nranks; s.nc = nc;
     auto lo_of = [&](int r) { return (int)((int64_t)r * nc / nranks); };
     s.c0 = lo_of(rank); s.c1 = lo_of(rank + 1);
@@ -416,6 +518,8 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
     NBX_TRY(dev_alloc(c, &s.blockcnt, nbmax * CAT_N)); NBX_TRY(dev_alloc(c, &s.blockoff, nbmax * CAT_N));
     NBX_TRY(dev_alloc(c, &s.d_counts, (size_t)CNT_N));
     NBX_TRY(dev_alloc(c, &s.d_n, (size_t)DN_N));
+    NBX_TRY(dev_alloc(c, &s.halo_idx[0], (size_t)s.capH));
+    NBX_TRY(dev_alloc(c, &s.halo_idx[1], (size_t)s.capH));
     NBX_CUDA(c, cudaMemsetAsync(s.d_n, 0, sizeof(int) * DN_N, c->stream));
     NBX_CUDA(c, cudaMallocHost((void **)&s.h_counts, sizeof(int) * (CNT_N + DN_N)));
     NBX_CUDA(c, cudaEventCreateWithFlags(&s.ev_counts, cudaEventDisableTiming));
@@ -476,6 +580,55 @@ int slab_pack(nbx_ctx *c)
         return NBX_OK;
     }
     return run_pack(c, 0);
+}
+
+// halo refresh between rebuilds (see slab_halo_send_kernel)
+int slab_refresh_send(nbx_ctx *c)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.verlet || s.first) return fail(c, NBX_ERR_INVALID, "nbx_slab_refresh_send: no Verlet-list slab state");
+    if (s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_refresh_send: the previous message was not received");
+    const int64_t threads = 2 * s.capH;
+    const SlabArrays src = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
+    slab_halo_send_kernel<<<(unsigned)((threads + kSlabBlock - 1) / kSlabBlock), kSlabBlock, 0, c->stream>>>(
+        src, c->npad, s.halo_idx[0], s.halo_idx[1], s.d_n, s.msg[0], s.msg[1], (int)s.capM, (int)s.capH,
+        s.direct ? s.peer[0] : nullptr, s.direct ? s.peer[1] : nullptr, s.msg_doubles);
+    NBX_CUDA(c, cudaGetLastError());
+    s.packed = true;
+    return NBX_OK;
+}
+
+int slab_refresh_recv(nbx_ctx *c)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.packed) return fail(c, NBX_ERR_INVALID, "nbx_slab_refresh_recv: nothing was sent");
+    const int64_t threads = 2 * s.capH;
+    const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
+    slab_halo_recv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.d_n, s.rx, s.msg_doubles,
+                                                                                  s.direct ? 1 : 0, (int)s.capM, (int)s.capH);
+    NBX_CUDA(c, cudaGetLastError());
+    s.packed = false;
+    return NBX_OK;
+}
+
+// out2_dev[0] |= some own particle moved more than soft_fraction x skin/2 since the lists were built (or there are no
+// lists yet); out2_dev[1] |= more than skin/2, or a list overflowed.  Enqueued on the context's stream.
+int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.verlet) return fail(c, NBX_ERR_INVALID, "nbx_slab_verlet_check: the slab does not keep Verlet lists");
+    if (!out2_dev) return fail(c, NBX_ERR_INVALID, "nbx_slab_verlet_check: out is NULL");
+    CellList *cl = c->has_lj ? &c->cl_lj : &c->cl_el;
+    if (!cl->v_valid || !cl->v_ref || s.rebuild_now) { // nothing to compare with: ask for a rebuild
+        NBX_CUDA(c, cudaMemsetAsync(out2_dev, 1, sizeof(int), c->stream));
+        return NBX_OK;
+    }
+    const double lim = 0.5 * cl->v_skin * (1.0 - 1e-9), soft = lim * soft_fraction;
+    const int n = (int)s.cap_loc;
+    slab_verlet_check_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pos, c->npad, cl->v_ref, cl->cap_n, s.d_n, soft * soft,
+                                                                    lim * lim, cl->v_flags, out2_dev);
+    NBX_CUDA(c, cudaGetLastError());
+    return NBX_OK;
 }
 
 // waits for the last asynchronous read-back and reports accumulated errors

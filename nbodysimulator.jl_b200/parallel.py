@@ -168,6 +168,26 @@ class CudaEngine:
     def slab_check(self):
         return self.ctx.slab_check()
 
+    # Verlet lists inside the slab (csrc/nbx_slab.cu): collective rebuilds, halo refresh in between
+    def slab_verlet(self):
+        return bool(self.ctx.info("slab_verlet"))
+
+    def slab_verlet_check(self, flags, soft_fraction=0.75):
+        """flags: int32 device tensor of two elements (ORed into)."""
+        self.ctx.slab_verlet_check(flags.data_ptr(), soft_fraction)
+
+    def slab_refresh_send(self):
+        self.ctx.slab_refresh_send()
+
+    def slab_refresh_recv(self):
+        self.ctx.slab_refresh_recv()
+
+    def slab_prime(self):
+        self.ctx.slab_prime()
+
+    def slab_mark(self, key):
+        self.ctx.set_option(key, 1)  # "slab_record_halo" before the second pack of a rebuild, "slab_rebuild" before its forces
+
     def slab_download(self):
         return self.ctx.slab_download()
 
@@ -286,9 +306,60 @@ class SlabStepper:
         engine.slab_pack()  # the first pack selects the own particles out of the full upload
         self._exchange()
         self.counts = engine.slab_unpack()
+        # Verlet lists inside the slabs: every rank rebuilds on the same step.  The decision is the max over the ranks of
+        # a displacement flag computed on the device after each position update; it is read LAG steps late, so the
+        # host never waits for the step it is enqueuing, and taken at a soft limit (0.75 of skin/2) that leaves room
+        # for those steps.  A hard flag (beyond skin/2, or a list overflow) that was not covered by a rebuild raises.
+        self.verlet = bool(hasattr(engine, "slab_verlet") and engine.slab_verlet())
+        self.k = 0
+        self.last_rebuild = -1
+        self.rebuilds = 0
+        self.force_rebuild = False
+        if self.verlet:
+            import torch
+
+            # a second round records the halo index lists; the lists are built from the distributed positions right away
+            engine.slab_mark("slab_record_halo")
+            engine.slab_pack()
+            self._exchange()
+            self.counts = engine.slab_unpack()
+            engine.slab_prime()
+
+            dev = engine.device
+            self._flags_dev = torch.zeros((self.SLOTS, 2), dtype=torch.int32, device=dev)
+            self._flags_host = torch.zeros((self.SLOTS, 2), dtype=torch.int32).pin_memory()
+            self._events = [torch.cuda.Event() for _ in range(self.SLOTS)]
+
+    LAG, SLOTS, SOFT = 2, 8, 0.75
 
     def _peer(self, r):
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def _rebuild_wanted(self):
+        """Enqueue this step's displacement check (+ max over the ranks) and return the decision for THIS step from the
+        check of LAG steps ago.  Identical on every rank: all read the same reduced flags of the same step."""
+        import torch
+
+        e, k = self.engine, self.k
+        slot = k % self.SLOTS
+        buf = self._flags_dev[slot]
+        buf.zero_()
+        e.slab_verlet_check(buf, self.SOFT)
+        if self.world > 1:
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
+        self._flags_host[slot].copy_(buf, non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(e.device))
+        want = self.force_rebuild
+        j = k - self.LAG
+        if j >= 0 and j > self.last_rebuild:  # a check against the lists that are in use
+            self._events[j % self.SLOTS].synchronize()
+            soft, hard = (int(x) for x in self._flags_host[j % self.SLOTS])
+            if hard:
+                raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last "
+                                   "rebuild (or a list overflowed) before the collective rebuild could happen; use a larger "
+                                   "verlet_skin_permille, a smaller time step, or verlet_skin_permille = 0")
+            want = want or bool(soft)
+        return want
 
     def _exchange(self):
         """send-to-left -> the left neighbour's recv-from-right, send-to-right -> the right neighbour's
@@ -308,9 +379,24 @@ class SlabStepper:
     def _one_step(self, dt):
         e = self.engine
         e.vv_begin(dt)
-        e.slab_pack()
-        self._exchange()
-        e.slab_unpack(sync=False)  # counts stay on the device: no host round trip inside a step
+        if self.verlet and not self._rebuild_wanted():
+            e.slab_refresh_send()       # nothing migrates, nothing is renumbered: only the halo positions travel
+            self._exchange()
+            e.slab_refresh_recv()
+        else:
+            e.slab_pack()
+            self._exchange()
+            e.slab_unpack(sync=False)  # counts stay on the device: no host round trip inside a step
+            if self.verlet:
+                e.slab_mark("slab_record_halo")  # second round: the halo now includes the arrivals, and is remembered
+                e.slab_pack()
+                self._exchange()
+                e.slab_unpack(sync=False)
+                e.slab_mark("slab_rebuild")
+                self.last_rebuild = self.k
+                self.force_rebuild = False
+                self.rebuilds += 1
+        self.k += 1
         e.vv_forces()
         e.vv_finish(dt)
         if e.needs_temperature and self.world > 1:

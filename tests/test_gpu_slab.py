@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 class LocalRing:
     """K slab contexts on one device; neighbour exchange by tensor copies."""
 
-    def __init__(self, make_ctx, u, v, world, thermostat, direct=False):
+    def __init__(self, make_ctx, u, v, world, thermostat, direct=False, soft=1.0):
         import torch
 
         from nbody_b200.parallel import CudaEngine
@@ -27,6 +27,8 @@ class LocalRing:
         self.torch = torch
         self.world = world
         self.thermostat = thermostat
+        self.soft = soft
+        self.rebuilds = 0
         self.engines = []
         for r in range(world):
             ctx = make_ctx()
@@ -45,6 +47,29 @@ class LocalRing:
             e.slab_pack()
         self._exchange()
         self.counts = [e.slab_unpack() for e in self.engines]
+        self.verlet = all(e.slab_verlet() for e in self.engines)
+        self.flags = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in self.engines]
+        self.force_rebuild = False
+        if self.verlet:  # as parallel.SlabStepper: record the halo lists, build the Verlet lists from x(0)
+            for e in self.engines:
+                e.slab_mark("slab_record_halo")
+                e.slab_pack()
+            self._exchange()
+            self.counts = [e.slab_unpack() for e in self.engines]
+            for e in self.engines:
+                e.slab_prime()
+
+    def _rebuild_wanted(self):
+        """The collective decision of parallel.SlabStepper, taken synchronously here (no lag): max over the ranks."""
+        for e, f in zip(self.engines, self.flags):
+            f.zero_()
+            e.slab_verlet_check(f, self.soft)
+        self.torch.cuda.synchronize()
+        soft = max(int(f[0]) for f in self.flags)
+        hard = max(int(f[1]) for f in self.flags)
+        want = self.force_rebuild or bool(soft)
+        assert want or not hard, "a list went stale without a rebuild"
+        return want
 
     def _exchange(self):
         if self.world == 1 or self.direct:
@@ -59,10 +84,28 @@ class LocalRing:
         for _ in range(nsteps):
             for e in self.engines:
                 e.vv_begin(dt)
-                e.slab_pack()
-            self._exchange()
-            self.counts = [e.slab_unpack() for e in self.engines]
-            migrated += sum(c[2] + c[3] for c in self.counts)
+            if self.verlet and not self._rebuild_wanted():
+                for e in self.engines:
+                    e.slab_refresh_send()
+                self._exchange()
+                for e in self.engines:
+                    e.slab_refresh_recv()
+            else:
+                for e in self.engines:
+                    e.slab_pack()
+                self._exchange()
+                self.counts = [e.slab_unpack() for e in self.engines]
+                migrated += sum(c[2] + c[3] for c in self.counts)
+                if self.verlet:  # second round of a rebuild: halo including the arrivals, recorded for the refreshes
+                    for e in self.engines:
+                        e.slab_mark("slab_record_halo")
+                        e.slab_pack()
+                    self._exchange()
+                    self.counts = [e.slab_unpack() for e in self.engines]
+                    for e in self.engines:
+                        e.slab_mark("slab_rebuild")
+                    self.force_rebuild = False
+                    self.rebuilds += 1
             for e in self.engines:
                 e.vv_forces()
                 e.vv_finish(dt)
@@ -134,6 +177,83 @@ def test_slabs_reproduce_the_single_context_trajectory(world, thermostat, direct
     else:
         for a, b in ((ug, ur), (vg, vr), (ag, ar)):
             assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("thermostat", [False, True])
+def test_slabs_with_verlet_lists_reproduce_the_single_context_trajectory(world, thermostat, direct):
+    """Verlet lists inside the slabs: local slots stay put between collective rebuilds, only the halo positions travel.
+    With the single context's own criterion (rebuild as soon as a particle has moved skin/2, decided without lag) the
+    rebuilds fall on the same steps, the lists hold the same partners in the same order, and the trajectory is
+    bit-identical to the single-context Verlet run (one lane per target on both sides)."""
+    w, u, v = _argon(12, 5)  # 6,912 atoms; 8 cell layers of edge >= R + skin
+    n = u.shape[1]
+    dt, steps = 2e-3, 60
+
+    def make_ctx():
+        ctx = _lib.Context(0)
+        ctx.system(w["ms"])
+        ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+        ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+        ctx.set_option("verlet_lanes", 1)
+        if thermostat:
+            ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 20 * dt, w["kB"], n, 0)
+        return ctx
+
+    ref = make_ctx()
+    ref.upload(u, v)
+    ref.step_vv(dt, steps)
+    ur, vr, ar = ref.download(want_dv=True)
+    ref_rebuilds = ref.info("verlet_rebuilds")
+    ref.close()
+
+    ring = LocalRing(make_ctx, u, v, world, thermostat, direct)
+    assert ring.verlet
+    migrated = ring.step(dt, steps)
+    ug, vg, ag = ring.gather(n)
+    ring.close()
+    assert 3 <= ring.rebuilds < steps // 2   # several collective rebuilds, halo refreshes in between
+    assert ring.rebuilds == ref_rebuilds - 1  # (both also built once from x(0): at upload / after the distribution)
+    if world > 1:
+        assert migrated > 0
+    if not thermostat:
+        assert np.array_equal(ug, ur) and np.array_equal(vg, vr) and np.array_equal(ag, ar)
+    else:
+        for a, b in ((ug, ur), (vg, vr), (ag, ar)):
+            assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
+
+
+def test_slab_stepper_lagged_rebuilds_single_rank():
+    """parallel.SlabStepper itself (one rank, no process group): the rebuild decision is read two steps late at a soft
+    limit of 0.75 x skin/2, so rebuilds fall on other steps than in the single context -- the pair set is the same, the
+    order of summation is not: 1e-9 after 80 hot steps."""
+    from nbody_b200.parallel import CudaEngine, SlabStepper
+
+    w, u, v = _argon(10, 7)
+    dt, steps = 2e-3, 80
+
+    def make_ctx():
+        ctx = _lib.Context(0)
+        ctx.system(w["ms"])
+        ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+        ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+        return ctx
+
+    ref = make_ctx()
+    ref.upload(u, v)
+    ref.step_vv(dt, steps)
+    ur, vr, _ = ref.download()
+    ref.close()
+    ctx = make_ctx()
+    ctx.upload(u, v)
+    st = SlabStepper(CudaEngine(ctx, 0))
+    assert st.verlet
+    st.step(dt, steps)
+    ug, vg, _ = st.gather(u.shape[1])
+    ctx.close()
+    assert 3 <= st.rebuilds < steps // 2
+    assert np.abs(ug - ur).max() <= 1e-9 * np.abs(ur).max() and np.abs(vg - vr).max() <= 1e-9 * np.abs(vr).max()
 
 
 def test_slab_errors_are_reported():
