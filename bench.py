@@ -197,7 +197,7 @@ def lj_secondary(local, world, steps, warmup, cells=LJ_CELLS):
             torch.cuda.synchronize()
 
     # One GPU: the library's own loop (nbx_step_vv: Verlet lists with on-device rebuild decisions, two-step CUDA
-    # graph).  N GPUs: the slab stepper (cells rescanned every step, messages through peer memory).
+    # graph).  N GPUs: the slab stepper (Verlet lists between collective rebuilds, messages through peer memory).
     steps = max(steps, 200 if world == 1 else 50)   # long enough to amortise list rebuilds / graph capture
     run = (lambda k: ctx.step_vv(w["dt"], k)) if world == 1 else (lambda k: stepper.step(w["dt"], k, check=False))
     run(max(warmup, 3) + 40)
@@ -232,14 +232,17 @@ def lj_secondary(local, world, steps, warmup, cells=LJ_CELLS):
         "metric": "LJ argon atom-steps/s (1,048,576 atoms, cell list, Berendsen, velocity Verlet)",
         "value": value, "unit": "atom-steps/s", "ms_per_step": ms / steps, "steps": steps, "n_atoms": n,
         "n_gpus": world, "scaling": "strong",
-        "parallelism": "1 GPU" if world == 1 else f"x-slabs x{world}: 1 message per neighbour per step (migrants + halo), "
-                                                    "8-byte all-reduce of sum m v^2",
+        "parallelism": "1 GPU" if world == 1 else f"x-slabs x{world}: 1 message per neighbour per step (halo positions; migrants + halo at "
+                                                    "a rebuild), 8-byte all-reduces of sum m v^2 and of the rebuild flags",
         "cells": ctx.info("cells_lj"), "temperature_after": mv2 / (w["kB"] * 3 * n),
         "inputs": "25 MB positions: smaller than L2, cell rebuild every step; not flushed",
         "ms_per_step_pair_kernel": pair_ms / k_t, "ms_per_step_cell_build": build_ms / k_t,
         "ms_per_step_integrate": int_ms / k_t,
         "neighbour_structure": ("Verlet lists (skin 0.1 R) over the cell list, rebuilt on the device when a particle moved skin/2; "
-                                f"{rebuilds} rebuilds so far" if world == 1 else "cell list rebuilt and rescanned every step"),
+                                f"{rebuilds} rebuilds so far" if world == 1 else
+                                (f"Verlet lists inside the slabs: {stepper.rebuilds} collective rebuilds so far (max over ranks of a device "
+                                 "displacement flag, read two steps late), halo positions refreshed in between"
+                                 if stepper.verlet else "cell list rebuilt and rescanned every step")),
     }
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.default_stream())

@@ -28,13 +28,15 @@ def slab_main(cells):
     v = np.asfortranarray(3.0 * w["v"])
     dt, steps = 2e-3, 40
     ok = True
-    for thermo, direct in ((False, True), (True, True), (False, False)):
+    # skin 0: cells rescanned every step (bit-identical to one GPU); skin 100: Verlet lists inside the slabs, collective
+    # rebuilds decided two steps late (other rebuild steps than on one GPU: same pair set, other summation order)
+    for thermo, direct, skin in ((False, True, 0), (True, True, 0), (False, False, 0), (False, True, 100), (True, False, 100)):
         def make():
             ctx = _lib.Context(local)
             ctx.system(w["ms"])
             ctx.boundary(_lib.BC_CUBIC, [w["L"]])
             ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
-            ctx.set_option("verlet_skin_permille", 0)  # one summation order everywhere (slabs rescan every step)
+            ctx.set_option("verlet_skin_permille", skin)
             if thermo:
                 ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 20 * dt, w["kB"], n, 0)
             return ctx
@@ -57,14 +59,18 @@ def slab_main(cells):
         t = torch.tensor([float(moved)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         if rank == 0:
-            if thermo:
+            if skin:
+                err = max(np.abs(a - b).max() / np.abs(b).max() for a, b in ((ug, ur), (vg, vr), (ag, ar)))
+                good = err < 1e-9 and st.verlet and 2 <= st.rebuilds < steps // 2
+                t += 1.0  # (migrations are only counted on rebuild steps here)
+            elif thermo:
                 err = max(np.abs(a - b).max() / np.abs(b).max() for a, b in ((ug, ur), (vg, vr), (ag, ar)))
                 good = err < 1e-11
             else:  # cell order is ranked by global id: bit-identical to the single-GPU sums
                 err = 0.0 if (np.array_equal(ug, ur) and np.array_equal(vg, vr) and np.array_equal(ag, ar)) else 1.0
                 good = err == 0.0
-            print(f"slab thermo={thermo} direct={st.direct} world={world} n={n} own={st.counts[0]} ghosts={st.counts[1]} "
-                  f"migrations={int(t.item())} err={err:.2e}")
+            print(f"slab thermo={thermo} direct={st.direct} skin={skin} rebuilds={st.rebuilds} world={world} n={n} own={st.counts[0]} "
+                  f"ghosts={st.counts[1]} migrations={int(t.item())} err={err:.2e}")
             ok = ok and good and t.item() > 0 and (st.direct or not direct)
         ctx.close()
     if rank == 0:
