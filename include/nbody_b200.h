@@ -207,6 +207,16 @@ NBX_API int nbx_slab_check(nbx_ctx *ctx, int64_t *counts);
  * the resident accelerations: the driver calls it once after the initial distribution, so that the first step already
  * runs from lists and the rebuild schedule is that of a single context. */
 NBX_API int nbx_slab_prime(nbx_ctx *ctx);
+/* The two halves of a slab step as single calls (fewer host round trips per step; the exchange must be direct or the
+ * slab alone).  The driver keeps three doubles of the scalar block (nbx_device_ptr which = 3) in flight: [12] this
+ * rank's sum m v^2 of the previous step, [13] / [14] the soft / hard rebuild flags of nbx_slab_verlet_check as 0.0 / 1.0.
+ *   nbx_slab_step_begin(dt, soft_fraction): nbx_vv_begin, zero [13..14], displacement check into them.
+ *   (driver: ONE sum over the ranks of [12..14] -- [13..14] only on the first step --, asynchronous copy of [13..14] home)
+ *   nbx_slab_step_end(dt, refresh): refresh != 0: nbx_slab_refresh_send + nbx_slab_refresh_recv; then nbx_vv_forces,
+ *   nbx_vv_finish (the Berendsen term reads the summed [12]; the new local sum is written to [0] and [12]).
+ * nbx_slab_step_begin switches the context to slot 12 for good (option "temperature_slot"). */
+NBX_API int nbx_slab_step_begin(nbx_ctx *ctx, double dt, double soft_fraction);
+NBX_API int nbx_slab_step_end(nbx_ctx *ctx, double dt, int refresh);
 NBX_API int nbx_slab_refresh_send(nbx_ctx *ctx);
 NBX_API int nbx_slab_refresh_recv(nbx_ctx *ctx);
 NBX_API int nbx_slab_verlet_check(nbx_ctx *ctx, double soft_fraction, void *out2_dev);

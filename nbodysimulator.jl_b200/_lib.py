@@ -57,6 +57,8 @@ SIGNATURES = {
     "nbx_slab_pack": (C.c_int, [_vp]),
     "nbx_slab_unpack": (C.c_int, [_vp, C.POINTER(_i64)]),
     "nbx_slab_prime": (C.c_int, [_vp]),
+    "nbx_slab_step_begin": (C.c_int, [_vp, C.c_double, C.c_double]),
+    "nbx_slab_step_end": (C.c_int, [_vp, C.c_double, C.c_int]),
     "nbx_slab_refresh_send": (C.c_int, [_vp]),
     "nbx_slab_refresh_recv": (C.c_int, [_vp]),
     "nbx_slab_verlet_check": (C.c_int, [_vp, C.c_double, _vp]),
@@ -288,6 +290,12 @@ class Context:
 
     def slab_prime(self):
         self._ck(self.lib.nbx_slab_prime(self.h))
+
+    def slab_step_begin(self, dt, soft_fraction=0.75):
+        self._ck(self.lib.nbx_slab_step_begin(self.h, float(dt), float(soft_fraction)))
+
+    def slab_step_end(self, dt, refresh):
+        self._ck(self.lib.nbx_slab_step_end(self.h, float(dt), int(bool(refresh))))
 
     def slab_refresh_send(self):
         self._ck(self.lib.nbx_slab_refresh_send(self.h))

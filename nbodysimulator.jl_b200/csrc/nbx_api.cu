@@ -186,6 +186,7 @@ static void free_system(nbx_ctx *c)
     cells_free(&c->cl_el);
     fused_free(c);
     c->fz = FusedState();
+    c->T_slot = 0;
     slab_free(c);
     c->resident = false;
 }
@@ -530,7 +531,36 @@ int nbx_slab_verlet_check(nbx_ctx *c, double soft_fraction, void *out2_dev)
 {
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_slab_verlet_check"));
-    return slab_verlet_check(c, soft_fraction, static_cast<int *>(out2_dev));
+    return slab_verlet_check(c, soft_fraction, static_cast<int *>(out2_dev), nullptr);
+}
+
+int nbx_slab_step_begin(nbx_ctx *c, double dt, double soft_fraction)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_step_begin"));
+    if (!c->slab.on || !c->slab.verlet || c->slab.first) return fail(c, NBX_ERR_INVALID, "nbx_slab_step_begin: no Verlet-list slab state");
+    if (c->T_slot != 12) { // the sum of the upload is the global one: it becomes the summed slot as it is
+        NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 12, c->d_scal, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        c->T_slot = 12;
+    }
+    NBX_TRY(launch_vv_pos(c, dt));
+    NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
+    return slab_verlet_check(c, soft_fraction, nullptr, c->d_scal + 13);
+}
+
+int nbx_slab_step_end(nbx_ctx *c, double dt, int refresh)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_resident(c, "nbx_slab_step_end"));
+    if (!c->slab.on) return fail(c, NBX_ERR_INVALID, "nbx_slab_step_end: call nbx_slab_init first");
+    if (refresh) {
+        if (!c->slab.direct && c->slab.nranks > 1)
+            return fail(c, NBX_ERR_INVALID, "nbx_slab_step_end: without nbx_slab_connect the host has to move the messages");
+        NBX_TRY(slab_refresh_send(c));
+        NBX_TRY(slab_refresh_recv(c));
+    }
+    NBX_TRY(nbx_vv_forces(c));
+    return nbx_vv_finish(c, dt);
 }
 
 int nbx_slab_rx(nbx_ctx *c, void **ptr, int64_t *ndoubles, void *ipc_handle64)
@@ -942,6 +972,10 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "temperature_slot")) {
+        if (value != 0 && value != 12) return fail(c, NBX_ERR_INVALID, "temperature_slot: 0 or 12");
+        c->T_slot = (int)value;
+    }
     else if (!strcmp(key, "slab_rebuild")) c->slab.rebuild_now = value != 0;
     else if (!strcmp(key, "slab_record_halo")) c->slab.record_halo = value != 0;
     else if (!strcmp(key, "verlet_lanes")) {

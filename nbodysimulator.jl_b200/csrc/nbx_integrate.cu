@@ -122,12 +122,16 @@ __device__ __forceinline__ double block_sum(double v)
 }
 
 // out[0] = sum of partial[0..nb) in ascending order (single block)
-__global__ void final_sum_kernel(const double *__restrict__ partial, int nb, double *__restrict__ out)
+__global__ void final_sum_kernel(const double *__restrict__ partial, int nb, double *__restrict__ out,
+                                 double *__restrict__ out2 = nullptr)
 {
     double v = 0.0;
     for (int i = threadIdx.x; i < nb; i += kRedThreads) v += partial[i];
     const double s = block_sum(v);
-    if (threadIdx.x == 0) out[0] = s;
+    if (threadIdx.x == 0) {
+        out[0] = s;
+        if (out2) out2[0] = s;
+    }
 }
 
 // sum_i m_i |v_i|^2 over columns [lo,hi)   (md_temperature numerator, src/thermostats.jl:88)
@@ -297,12 +301,13 @@ int launch_vv_vel(nbx_ctx *c, double dt, bool with_thermostat)
     timer_begin(c, NBX_T_INTEGRATE);
     if (fused)
         vv_vel_kernel<true><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
-                                                              0.5 * dt, c->d_red, c->d_scal, c->kB, ndf, c->T0,
+                                                              0.5 * dt, c->d_red, c->d_scal + c->T_slot, c->kB, ndf, c->T0,
                                                               0.5 / c->tparam, c->dyn);
     else
         vv_vel_kernel<false><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
                                                                0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0, c->dyn);
-    final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal);
+    // (T_slot != 0: the slab driver keeps the all-reduced sum in its own slot, see nbx_slab_step_begin)
+    final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal, c->T_slot ? c->d_scal + c->T_slot : nullptr);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;

@@ -146,6 +146,7 @@ struct nbx_ctx {
     double T0 = 0, tparam = 0, kB = 0;
     int64_t thN = 0, thNc = 0;
     double *d_scal = nullptr;  // device scalars: [0] sum m v^2, [1] zeta, [2] zeta_dot, [3..15] scratch
+    int T_slot = 0;            // d_scal slot the velocity update reads sum m v^2 from (12 while nbx_slab_step_* drive the slab)
     double *d_red = nullptr;   // block partials for reductions
     int64_t red_cap = 0;
     uint64_t seed = 0x9E3779B97F4A7C15ull;
@@ -267,7 +268,7 @@ int slab_check(nbx_ctx *c, int64_t *counts);
 int slab_connect(nbx_ctx *c, const void *left_handle, const void *right_handle, void *left_ptr, void *right_ptr);
 int slab_refresh_send(nbx_ctx *c);
 int slab_refresh_recv(nbx_ctx *c);
-int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev);
+int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev, double *out2_dbl);
 void slab_free(nbx_ctx *c);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);

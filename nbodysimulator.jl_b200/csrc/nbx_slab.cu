@@ -323,15 +323,18 @@ __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restric
 // (ask for a collective rebuild), out[1] |= beyond skin/2 or a list overflowed (the lists are no longer a superset)
 __global__ void slab_verlet_check_kernel(const double *__restrict__ px, int64_t ld, const double *__restrict__ ref, int64_t rld,
                                          const int *__restrict__ dn, double soft2, double hard2,
-                                         const int *__restrict__ vflags, int *__restrict__ out)
+                                         const int *__restrict__ vflags, int *__restrict__ out, double *__restrict__ outd)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && vflags[1]) out[1] = 1;
-    if (i >= dn[DN_OWN]) return;
-    const double dx = px[i] - ref[i], dy = px[ld + i] - ref[rld + i], dz = px[2 * ld + i] - ref[2 * rld + i];
-    const double d2 = dx * dx + dy * dy + dz * dz;
-    if (!(d2 <= soft2)) out[0] = 1;
-    if (!(d2 <= hard2)) out[1] = 1;
+    bool soft = false, hard = i == 0 && vflags[1];
+    if (i < dn[DN_OWN]) {
+        const double dx = px[i] - ref[i], dy = px[ld + i] - ref[rld + i], dz = px[2 * ld + i] - ref[2 * rld + i];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        soft = !(d2 <= soft2);
+        hard = hard || !(d2 <= hard2);
+    }
+    if (soft) { if (out) out[0] = 1; else outd[0] = 1.0; }
+    if (hard) { if (out) out[1] = 1; else outd[1] = 1.0; }
 }
 
 // segments, in the order they are laid down: arrivals (left, right) extend the own particles; the ghosts are
@@ -613,20 +616,22 @@ int slab_refresh_recv(nbx_ctx *c)
 
 // out2_dev[0] |= some own particle moved more than soft_fraction x skin/2 since the lists were built (or there are no
 // lists yet); out2_dev[1] |= more than skin/2, or a list overflowed.  Enqueued on the context's stream.
-int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev)
+// (out2_dbl instead of out2_dev: the same two flags as doubles, 0.0 / 1.0, for a driver that sums them with sum m v^2)
+int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev, double *out2_dbl)
 {
     SlabState &s = c->slab;
     if (!s.on || !s.verlet) return fail(c, NBX_ERR_INVALID, "nbx_slab_verlet_check: the slab does not keep Verlet lists");
-    if (!out2_dev) return fail(c, NBX_ERR_INVALID, "nbx_slab_verlet_check: out is NULL");
+    if (!out2_dev && !out2_dbl) return fail(c, NBX_ERR_INVALID, "nbx_slab_verlet_check: out is NULL");
     CellList *cl = c->has_lj ? &c->cl_lj : &c->cl_el;
     if (!cl->v_valid || !cl->v_ref || s.rebuild_now) { // nothing to compare with: ask for a rebuild
-        NBX_CUDA(c, cudaMemsetAsync(out2_dev, 1, sizeof(int), c->stream));
+        if (out2_dev) NBX_CUDA(c, cudaMemsetAsync(out2_dev, 1, sizeof(int), c->stream));
+        else NBX_TRY(launch_fill(c, out2_dbl, 1.0, 1));
         return NBX_OK;
     }
     const double lim = 0.5 * cl->v_skin * (1.0 - 1e-9), soft = lim * soft_fraction;
     const int n = (int)s.cap_loc;
     slab_verlet_check_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pos, c->npad, cl->v_ref, cl->cap_n, s.d_n, soft * soft,
-                                                                    lim * lim, cl->v_flags, out2_dev);
+                                                                    lim * lim, cl->v_flags, out2_dev, out2_dbl);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
 }

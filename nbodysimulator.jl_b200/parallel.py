@@ -185,6 +185,12 @@ class CudaEngine:
     def slab_prime(self):
         self.ctx.slab_prime()
 
+    def slab_step_begin(self, dt, soft_fraction=0.75):
+        self.ctx.slab_step_begin(dt, soft_fraction)
+
+    def slab_step_end(self, dt, refresh):
+        self.ctx.slab_step_end(dt, refresh)
+
     def slab_mark(self, key):
         self.ctx.set_option(key, 1)  # "slab_record_halo" before the second pack of a rebuild, "slab_rebuild" before its forces
 
@@ -311,6 +317,7 @@ class SlabStepper:
         # host never waits for the step it is enqueuing, and taken at a soft limit (0.75 of skin/2) that leaves room
         # for those steps.  A hard flag (beyond skin/2, or a list overflow) that was not covered by a rebuild raises.
         self.verlet = bool(hasattr(engine, "slab_verlet") and engine.slab_verlet())
+        self.merged = False
         self.k = 0
         self.last_rebuild = -1
         self.rebuilds = 0
@@ -329,6 +336,11 @@ class SlabStepper:
             self._flags_dev = torch.zeros((self.SLOTS, 2), dtype=torch.int32, device=dev)
             self._flags_host = torch.zeros((self.SLOTS, 2), dtype=torch.int32).pin_memory()
             self._events = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            # merged mode (engines with slab_step_begin / slab_step_end, direct exchange or a single slab): two library
+            # calls and ONE collective per step -- the sum over the ranks of [sum m v^2, soft flag, hard flag]
+            self.merged = bool(hasattr(engine, "slab_step_begin") and (self.direct or self.world == 1))
+            self._flags_host_d = torch.zeros((self.SLOTS, 2), dtype=torch.float64).pin_memory()
+            self._T_pending = False  # slot 12 holds a local sum that has not been added over the ranks yet
 
     LAG, SLOTS, SOFT = 2, 8, 0.75
 
@@ -342,18 +354,28 @@ class SlabStepper:
 
         e, k = self.engine, self.k
         slot = k % self.SLOTS
-        buf = self._flags_dev[slot]
-        buf.zero_()
-        e.slab_verlet_check(buf, self.SOFT)
-        if self.world > 1:
-            self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
-        self._flags_host[slot].copy_(buf, non_blocking=True)
+        if self.merged:  # the position update and the check were enqueued by slab_step_begin
+            s = e.scalars()
+            if self.world > 1:
+                lo = 12 if self._T_pending else 13
+                self.dist.all_reduce(s[lo:15], op=self.dist.ReduceOp.SUM, group=self.group)
+            self._T_pending = True
+            host = self._flags_host_d
+            host[slot].copy_(s[13:15], non_blocking=True)
+        else:
+            buf = self._flags_dev[slot]
+            buf.zero_()
+            e.slab_verlet_check(buf, self.SOFT)
+            if self.world > 1:
+                self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
+            host = self._flags_host
+            host[slot].copy_(buf, non_blocking=True)
         self._events[slot].record(torch.cuda.current_stream(e.device))
         want = self.force_rebuild
         j = k - self.LAG
         if j >= 0 and j > self.last_rebuild:  # a check against the lists that are in use
             self._events[j % self.SLOTS].synchronize()
-            soft, hard = (int(x) for x in self._flags_host[j % self.SLOTS])
+            soft, hard = (int(x) for x in host[j % self.SLOTS])
             if hard:
                 raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last "
                                    "rebuild (or a list overflowed) before the collective rebuild could happen; use a larger "
@@ -378,6 +400,25 @@ class SlabStepper:
 
     def _one_step(self, dt):
         e = self.engine
+        if self.merged:
+            e.slab_step_begin(dt, self.SOFT)
+            if self._rebuild_wanted():
+                e.slab_pack()           # migration round, then the halo round that is remembered (see below)
+                self._exchange()
+                e.slab_unpack(sync=False)
+                e.slab_mark("slab_record_halo")
+                e.slab_pack()
+                self._exchange()
+                e.slab_unpack(sync=False)
+                e.slab_mark("slab_rebuild")
+                self.last_rebuild = self.k
+                self.force_rebuild = False
+                self.rebuilds += 1
+                e.slab_step_end(dt, False)
+            else:
+                e.slab_step_end(dt, True)
+            self.k += 1
+            return
         e.vv_begin(dt)
         if self.verlet and not self._rebuild_wanted():
             e.slab_refresh_send()       # nothing migrates, nothing is renumbered: only the halo positions travel
@@ -407,6 +448,12 @@ class SlabStepper:
         if any step lost a particle or overflowed a buffer (``self.counts`` = counts of the last step)."""
         for _ in range(nsteps):
             self._one_step(dt)
+        if self.merged and self._T_pending and self.world > 1 and self.engine.needs_temperature:
+            # leave the scalar block as the unmerged path does: [0] = the sum over all ranks
+            s = self.engine.scalars()
+            self.dist.all_reduce(s[12:13], op=self.dist.ReduceOp.SUM, group=self.group)
+            s[0:1].copy_(s[12:13])
+            self._T_pending = False
         if check:
             self.counts = self.engine.slab_check()
 
