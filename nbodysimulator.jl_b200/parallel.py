@@ -341,6 +341,15 @@ class SlabStepper:
             self.merged = bool(hasattr(engine, "slab_step_begin") and (self.direct or self.world == 1))
             self._flags_host_d = torch.zeros((self.SLOTS, 2), dtype=torch.float64).pin_memory()
             self._T_pending = False  # slot 12 holds a local sum that has not been added over the ranks yet
+            # views made once: slicing tensors every step costs more host time than the kernels they feed
+            self._host_i = [self._flags_host[k] for k in range(self.SLOTS)]
+            self._host_d = [self._flags_host_d[k] for k in range(self.SLOTS)]
+            self._np_i = self._flags_host.numpy()
+            self._np_d = self._flags_host_d.numpy()
+            self._stream = torch.cuda.current_stream(dev)
+            if self.merged:
+                s = engine.scalars()
+                self._s_flags, self._s_all = s[13:15], s[12:15]
 
     LAG, SLOTS, SOFT = 2, 8, 0.75
 
@@ -350,32 +359,31 @@ class SlabStepper:
     def _rebuild_wanted(self):
         """Enqueue this step's displacement check (+ max over the ranks) and return the decision for THIS step from the
         check of LAG steps ago.  Identical on every rank: all read the same reduced flags of the same step."""
-        import torch
-
         e, k = self.engine, self.k
         slot = k % self.SLOTS
         if self.merged:  # the position update and the check were enqueued by slab_step_begin
-            s = e.scalars()
             if self.world > 1:
-                lo = 12 if self._T_pending else 13
-                self.dist.all_reduce(s[lo:15], op=self.dist.ReduceOp.SUM, group=self.group)
+                self.dist.all_reduce(self._s_all if self._T_pending else self._s_flags, op=self.dist.ReduceOp.SUM,
+                                     group=self.group)
             self._T_pending = True
-            host = self._flags_host_d
-            host[slot].copy_(s[13:15], non_blocking=True)
+            host = self._np_d
+            self._host_d[slot].copy_(self._s_flags, non_blocking=True)
         else:
             buf = self._flags_dev[slot]
             buf.zero_()
             e.slab_verlet_check(buf, self.SOFT)
             if self.world > 1:
                 self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
-            host = self._flags_host
-            host[slot].copy_(buf, non_blocking=True)
-        self._events[slot].record(torch.cuda.current_stream(e.device))
+            host = self._np_i
+            self._host_i[slot].copy_(buf, non_blocking=True)
+        self._events[slot].record(self._stream)
         want = self.force_rebuild
         j = k - self.LAG
         if j >= 0 and j > self.last_rebuild:  # a check against the lists that are in use
-            self._events[j % self.SLOTS].synchronize()
-            soft, hard = (int(x) for x in host[j % self.SLOTS])
+            jj = j % self.SLOTS
+            if not self._events[jj].query():
+                self._events[jj].synchronize()
+            soft, hard = int(host[jj, 0]), int(host[jj, 1])
             if hard:
                 raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last "
                                    "rebuild (or a list overflowed) before the collective rebuild could happen; use a larger "
