@@ -454,12 +454,12 @@ def run_b200(args):
     pairs_per_launch = float(hi - lo) * float(n - 1)
     achieved_tf = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp64", "kernel": "sym_kernel<8,2,uniform> (Newton 3rd law, 18 FP64 instr per unordered pair = 9 per ordered pair)" if (world == 1 or args.mode == "pairs") else "allpairs_kernel<GravPolicy> (16 FP64 instr per ordered pair)", "achieved": achieved_tf, "peak": peak_tf,
+        "bound": "fp64", "kernel": "sym_kernel<8,2,uniform,2,4> (Newton 3rd law, 18 FP64 instr per unordered pair = 9 per ordered pair)" if (world == 1 or args.mode == "pairs") else "allpairs_kernel<GravPolicy> (16 FP64 instr per ordered pair)", "achieved": achieved_tf, "peak": peak_tf,
         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one sym_kernel launch at N = 262,144 on one GPU, from the
-        # ncu --set full capture profiles/prof_gravity_r01b.summary.csv (30.4 MB read + 910.5 MB written: the
-        # per-slot partial sums that make the result bit-reproducible; 21 GB/s, 0.3 % of HBM -- the kernel is FP64-bound)
-        "traffic": 940.9e6 if world == 1 else None,
+        # ncu --set full capture profiles/prof_gravity_r01c.summary.csv (29.1 MB read + 911.4 MB written: the
+        # per-slot partial sums that make the result bit-reproducible; 22 GB/s, 0.3 % of HBM -- the kernel is FP64-bound)
+        "traffic": 940.4e6 if world == 1 else None,
         "peak_source": "DFMA saturation microbenchmark measured live on this device (MEASURED_PEAKS.json has no "
                        "FP64 figure); nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
         "peak_effective_sm_mhz": eff_mhz, "flop_per_pair": FLOP_PER_PAIR,
