@@ -296,6 +296,20 @@ def other_configs(local, steps=5):
                         "value": w["nmol"] / (ms * 1e-3), "unit": "molecule-steps/s", "ms_per_step": ms, "n_atoms": 3 * w["nmol"],
                         "coulomb_cutoff_nm": w["coulomb"]["R"], "path": what}
             ctx.close()
+        # config 2 at its largest size (the 8-GPU target of the north star), here on one device: 1.1e12 pairs per evaluation
+        n1 = 1048576
+        u1, v1, m1 = wl.plummer(n1)
+        ctx = _lib.Context(local)
+        ctx.set_stream(side.cuda_stream)
+        ctx.system(m1)
+        ctx.add_gravity(1.0)
+        ctx.upload(u1, v1)
+        ms = timed(ctx, lambda k: ctx.step_vv(1e-4, k), 2)
+        out["config2_gravity_1048576"] = {"metric": "gravity pair-interactions/s (all-pairs Plummer sphere, 1,048,576 bodies, fp64)",
+                                          "value": float(n1) * float(n1 - 1) / (ms * 1e-3), "unit": "pair-interactions/s",
+                                          "ms_per_step": ms, "n_bodies": n1,
+                                          "tflops_at_20_flop_per_pair": 20.0 * float(n1) * float(n1 - 1) / (ms * 1e-3) / 1e12}
+        ctx.close()
         n = 65536
         for tag, gen in (("config5a_coulomb", wl.charged_lattice), ("config5b_dipole", wl.dipole_lattice)):
             w = gen(n)

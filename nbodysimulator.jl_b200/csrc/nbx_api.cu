@@ -972,6 +972,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
+    else if (!strcmp(key, "tiles")) c->opt_tiles = (int)value;
+    else if (!strcmp(key, "tiles_min_n")) c->tiles_min_n = value;
     else if (!strcmp(key, "temperature_slot")) {
         if (value != 0 && value != 12) return fail(c, NBX_ERR_INVALID, "temperature_slot: 0 or 12");
         c->T_slot = (int)value;
@@ -1024,6 +1026,8 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "fused_steps")) *value = c->fz.steps_total;
     else if (!strcmp(key, "fused_disabled")) *value = c->fz.disabled ? 1 : 0;
     else if (!strcmp(key, "fused_list_cap")) *value = c->fz.cap_e;
+    else if (!strcmp(key, "tiles_lj")) *value = (c->cl_lj.v_valid && c->cl_lj.v_tiles) ? 1 : 0;
+    else if (!strcmp(key, "tiles_el")) *value = (c->cl_el.v_valid && c->cl_el.v_tiles) ? 1 : 0;
     else if (!strcmp(key, "verlet_lj")) *value = c->cl_lj.v_valid ? c->cl_lj.v_cap : 0;
     else if (!strcmp(key, "verlet_el")) *value = c->cl_el.v_valid ? c->cl_el.v_cap : 0;
     else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;

@@ -56,6 +56,10 @@ struct CellList {
     const double *v_px = nullptr;
     double v_R = 0, v_skin = 0, v_L = 0;
     int v_key_div = 0, v_nc = 0, v_cap = 0;
+    // tile kernels (nbx_cells.cu): the same lists as 16-bit indices into a CTA's shared-memory staging area
+    unsigned short *t_list = nullptr;
+    int64_t t_cap_alloc = 0;
+    bool v_tiles = false;
 };
 
 // Fused cutoff step (nbx_fused.cu): the state in padded cell order ("slots"), cluster lists, device flags
@@ -176,6 +180,12 @@ struct nbx_ctx {
     int opt_prefilter = 1;
     int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
+    // list kernel over shared-memory staged candidate rows (tile_force_kernel, nbx_cells.cu).  OFF by default: bit-identical
+    // to verlet_force_kernel but measured 0.44 ms against 0.21 ms at 1,048,576 argon atoms (r01c) -- the staging area
+    // limits the SM to 16-24 warps and the 8-byte shared gathers conflict 3-fold; kept as a tested option ("tiles").
+    int opt_tiles = 0;
+    int64_t tiles_min_n = 200000;
+    bool tiles_attr_set = false;
     int opt_verlet_lanes = 0;      // lanes per target of the Verlet force kernel (0: chosen from the system size; 1, 2, 4, 8)
     // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu).  OFF by default: measured on
     // B200 at 1,048,576 argon atoms the fused step costs the SUM of its parts (0.36 ms vs 0.285 ms unfused, r01c):
