@@ -256,6 +256,24 @@ def test_slab_stepper_lagged_rebuilds_single_rank():
     assert np.abs(ug - ur).max() <= 1e-9 * np.abs(ur).max() and np.abs(vg - vr).max() <= 1e-9 * np.abs(vr).max()
 
 
+def test_slab_stepper_raises_when_a_list_goes_stale_before_the_collective_rebuild():
+    """The rebuild decision is read two steps late.  Particles fast enough to cross skin/2 inside that window must not
+    be integrated with a stale list silently: the hard flag of the displacement check raises."""
+    from nbody_b200.parallel import CudaEngine, SlabStepper
+
+    w, u, v = _argon(8, 11, hot=40.0)  # velocities ~ 40 sigma per time unit: 0.08 sigma per step, skin/2 = 0.11 sigma
+    ctx = _lib.Context(0)
+    ctx.system(w["ms"])
+    ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+    ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+    ctx.upload(u, v)
+    st = SlabStepper(CudaEngine(ctx, 0))
+    assert st.verlet
+    with pytest.raises(RuntimeError, match="skin/2"):
+        st.step(2e-3, 12)
+    ctx.close()
+
+
 def test_slab_errors_are_reported():
     w, u, v = _argon(8, 2)
     ctx = _lib.Context(0)
