@@ -9,6 +9,7 @@
 
 #include "nbx_internal.cuh"
 
+#include <cmath>
 #include <utility>
 
 namespace nbx {
@@ -311,6 +312,7 @@ int nbx_destroy(nbx_ctx *c)
     for (auto &t : c->timers)
         for (cudaEvent_t ev : t.ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     delete c;
     return NBX_OK;
 }
@@ -803,8 +805,17 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
         if (s >= nsteps) return NBX_OK;
         skip_pos = true;
     }
+    // one cutoff potential over Verlet lists: the position update also checks the displacements and refreshes the
+    // cell-order records (vv_pos_lists_kernel); decided per step, the first evaluation after a (re)configuration is plain
+    const bool one_cutoff = !c->water && !c->has_grav && !c->has_dip && !c->has_spcfw && c->tgt_lo == 0 && c->tgt_hi == c->n &&
+                            (c->has_lj != (c->has_coul && std::isfinite(c->el_R)));
+    CellList *ucl = c->has_lj ? &c->cl_lj : &c->cl_el;
+    const double *uw = c->has_lj ? nullptr : c->charge;
     auto one_step = [&]() -> int {
-        if (!skip_pos) NBX_TRY(launch_vv_pos(c, dt));
+        if (!skip_pos) {
+            if (one_cutoff && lists_can_fuse_update(c, ucl, c->pos)) NBX_TRY(launch_vv_pos_lists(c, ucl, uw, dt));
+            else NBX_TRY(launch_vv_pos(c, dt));
+        }
         skip_pos = false;
         double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
         NBX_TRY(compute_pairs(c));
@@ -822,13 +833,30 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
         for (int w = 0; w < 2; ++w, ++s) NBX_TRY(one_step()); // warm-up: allocations and attribute calls happen outside the capture
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-        if (e == cudaSuccess) {
+        cudaError_t e = cudaSuccess;
+        if (c->opt_cond_nodes && !c->cond_fail && !c->aux_stream &&
+            cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { c->aux_stream = nullptr; cudaGetLastError(); }
+        for (int attempt = 0; attempt < 2; ++attempt) { // second attempt: plain capture, should the IF nodes be refused
+            cudaStream_t main_stream = c->stream;
+            c->cond_capture = c->opt_cond_nodes && !c->cond_fail && c->aux_stream != nullptr;
+            const bool with_nodes = c->cond_capture;
+            double *acc0 = c->acc, *acc_old0 = c->acc_old;
+            e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) { c->cond_capture = false; break; }
             int rc = one_step();
             if (rc == NBX_OK) rc = one_step();
+            c->cond_capture = false;
+            c->stream = main_stream;
             e = cudaStreamEndCapture(c->stream, &graph);
-            if (rc != NBX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+            if (rc == NBX_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+            if (rc == NBX_OK && e == cudaSuccess) break;
+            if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+            exec = nullptr;
+            cudaGetLastError();
+            c->acc = acc0; c->acc_old = acc_old0; c->forces_done = false; // nothing of the failed capture ran
+            if (!with_nodes) { if (rc != NBX_OK) return rc; break; }
+            c->cond_fail = true; // try again without
+            e = cudaSuccess;
         }
         if (e == cudaSuccess && exec) {
             for (; s + 2 <= nsteps; s += 2) {
@@ -973,6 +1001,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "tiles")) c->opt_tiles = (int)value;
+    else if (!strcmp(key, "fuse_update")) c->opt_fuse_update = (int)value;
+    else if (!strcmp(key, "graph_if_nodes")) { c->opt_cond_nodes = (int)value; if (value) c->cond_fail = false; }
     else if (!strcmp(key, "tiles_min_n")) c->tiles_min_n = value;
     else if (!strcmp(key, "temperature_slot")) {
         if (value != 0 && value != 12) return fail(c, NBX_ERR_INVALID, "temperature_slot: 0 or 12");
@@ -1023,6 +1053,7 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
         }
         *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2] + c->fz.rebuilds_total;
     }
+    else if (!strcmp(key, "graph_if_nodes")) *value = (c->opt_cond_nodes && !c->cond_fail) ? 1 : 0;
     else if (!strcmp(key, "fused_steps")) *value = c->fz.steps_total;
     else if (!strcmp(key, "fused_disabled")) *value = c->fz.disabled ? 1 : 0;
     else if (!strcmp(key, "fused_list_cap")) *value = c->fz.cap_e;

@@ -191,7 +191,7 @@ __global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, co
                                    const int *__restrict__ cell_of, const int *__restrict__ start, int n, double L,
                                    int nc, int key_div, int *__restrict__ sorted_idx, double4 *__restrict__ sp4,
                                    float4 *__restrict__ sl4, int *__restrict__ scell, const int *__restrict__ dyn,
-                                   const int *__restrict__ cond)
+                                   const int *__restrict__ cond, int *__restrict__ slot_of)
 {
     if (cond && !cond[0]) return;
     n = dyn_loc(dyn, n);
@@ -207,6 +207,7 @@ __global__ void rank_gather_kernel(const double *__restrict__ px, int64_t ld, co
         const int dst = b + rank;
         const double x = px[i], y = px[ld + i], z = px[2 * ld + i];
         sorted_idx[dst] = i;
+        slot_of[i] = dst;
         sp4[dst] = make_double4(x, y, z, w ? w[i] : 0.0);
         sl4[dst] = make_float4((float)(wrapped_coord(x, L) * s), (float)(wrapped_coord(y, L) * s),
                                (float)(wrapped_coord(z, L) * s), __int_as_float(mine / key_div));
@@ -232,6 +233,7 @@ static int ensure_cells(nbx_ctx *c, CellList *cl, int64_t n, int64_t ncell)
         NBX_TRY(dev_alloc(c, &cl->tmp_idx, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->tmp_key, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sorted_idx, (size_t)np));
+        NBX_TRY(dev_alloc(c, &cl->slot_of, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->scell, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sp4, (size_t)np));
         NBX_TRY(dev_alloc(c, &cl->sl4, (size_t)np));
@@ -268,7 +270,7 @@ int cells_build(nbx_ctx *c, CellList *cl, const double *px, const double *w, con
                                                            cl->tmp_key, c->dyn, cond);
     rank_gather_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(px, ld, w, cl->tmp_idx, gid ? cl->tmp_key : nullptr,
                                                                cl->cell_of, cl->start, ni, g.len[0], g.nc[0], key_div,
-                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn, cond);
+                                                               cl->sorted_idx, cl->sp4, cl->sl4, cl->scell, c->dyn, cond, cl->slot_of);
     timer_end(c, NBX_T_CELL_BUILD);
     NBX_CUDA(c, cudaGetLastError());
     cl->n = n;
@@ -580,6 +582,7 @@ struct VerletArgs {
     int cap;
     int64_t stride;
     const int *dyn; // slab mode: [0] own, [1] ghosts on the device (launch sizes are bounds); else null
+    int consume;    // the force kernel clears flags[0] (no refresh kernel ran: the position update refreshed the records)
 };
 
 // one lane per slot: the fp32 scan of cell_pairs2_kernel, survivors appended to the slot's list
@@ -666,6 +669,7 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
                                                            const double *__restrict__ charge, int lo, int hi,
                                                            double *__restrict__ acc, int64_t ld, int accumulate)
 {
+    if (v.consume && blockIdx.x == 0 && threadIdx.x == 0) v.flags[0] = 0; // the rebuild request was consumed by the chain before
     if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
     const int t = blockIdx.x * 128 + threadIdx.x;
     const int k = t / P, sub = t % P;
@@ -934,6 +938,109 @@ __global__ void __launch_bounds__(128) tile_force_kernel(const CellPairArgs a, c
     }
 }
 
+// Position update of velocity Verlet fused with the two O(N) passes the lists need on every evaluation: the
+// displacement check against the build-time positions (-> rebuild request) and the refresh of the cell-order record
+// (through the inverse permutation slot_of).  Same arithmetic as vv_pos_kernel / verlet_check_kernel /
+// verlet_refresh_kernel; saves two launches and re-reading the positions twice.
+__global__ void vv_pos_lists_kernel(double *__restrict__ pos, const double *__restrict__ vel, const double *__restrict__ acc,
+                                    const double *__restrict__ w, int64_t ld, int n, double dt, double hdt2,
+                                    const double *__restrict__ ref, int64_t rld, double lim2, const int *__restrict__ slot_of,
+                                    double4 *__restrict__ sp4, int *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && flags[1]) flags[0] = 1;
+    if (i >= n) return;
+    const double x = fma(hdt2, acc[i], fma(dt, vel[i], pos[i]));
+    const double y = fma(hdt2, acc[ld + i], fma(dt, vel[ld + i], pos[ld + i]));
+    const double z = fma(hdt2, acc[2 * ld + i], fma(dt, vel[2 * ld + i], pos[2 * ld + i]));
+    pos[i] = x; pos[ld + i] = y; pos[2 * ld + i] = z;
+    const double dx = x - ref[i], dy = y - ref[rld + i], dz = z - ref[2 * rld + i];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 <= lim2)) flags[0] = 1; // also catches NaN
+    sp4[slot_of[i]] = make_double4(x, y, z, w ? w[i] : 0.0);
+}
+
+// true when the next position update of nbx_step_vv can run as vv_pos_lists_kernel for this list
+bool lists_can_fuse_update(const nbx_ctx *c, const CellList *cl, const double *px)
+{
+    return c->opt_fuse_update && cl->v_valid && cl->v_px == px && cl->v_n == c->n && cl->slot_of && cl->v_ref && !c->slab.on &&
+           c->dyn == nullptr && c->thermo != NBX_THERMO_NOSEHOOVER;
+}
+
+int launch_vv_pos_lists(nbx_ctx *c, CellList *cl, const double *w, double dt)
+{
+    const int n = (int)c->n;
+    const double lim = 0.5 * cl->v_skin * (1.0 - 1e-9);
+    timer_begin(c, NBX_T_INTEGRATE);
+    vv_pos_lists_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pos, c->vel, c->acc, w, c->npad, n, dt, 0.5 * dt * dt, cl->v_ref,
+                                                               cl->cap_n, lim * lim, cl->slot_of, cl->sp4, cl->v_flags);
+    timer_end(c, NBX_T_INTEGRATE);
+    NBX_CUDA(c, cudaGetLastError());
+    cl->prechecked = true;
+    return NBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the rebuild chain as the body of a graph IF node (while nbx_step_vv captures)
+// ------------------------------------------------------------------------------------------------
+__global__ void cond_set_kernel(cudaGraphConditionalHandle h, const int *__restrict__ flag)
+{
+    cudaGraphSetConditional(h, flag[0] != 0 ? 1u : 0u);
+}
+
+struct CondScope {
+    bool active = false;
+    cudaStream_t saved = nullptr;
+};
+
+// From here to cond_scope_end the launches on c->stream land in the IF node's body graph.  No-op outside a capture.
+static int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
+{
+    sc->active = false;
+    if (!c->cond_capture || c->cond_fail || !c->aux_stream) return NBX_OK;
+    cudaStreamCaptureStatus st;
+    unsigned long long id;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t nd = 0;
+    if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &g, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive || !g)
+        return NBX_OK;
+    cudaGraphConditionalHandle h;
+    if (cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return NBX_OK; }
+    cond_set_kernel<<<1, 1, 0, c->stream>>>(h, flag);
+    if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &g, &deps, &nd) != cudaSuccess) { c->cond_fail = true; return fail(c, NBX_ERR_CUDA, "graph IF node: capture info"); }
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = h;
+    p.conditional.type = cudaGraphCondTypeIf;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    if (cudaGraphAddNode(&node, g, deps, nd, &p) != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return fail(c, NBX_ERR_CUDA, "graph IF node: cudaGraphAddNode"); }
+    if (cudaStreamUpdateCaptureDependencies(c->stream, &node, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) {
+        c->cond_fail = true; cudaGetLastError();
+        return fail(c, NBX_ERR_CUDA, "graph IF node: cudaStreamUpdateCaptureDependencies");
+    }
+    if (cudaStreamBeginCaptureToGraph(c->aux_stream, p.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        c->cond_fail = true; cudaGetLastError();
+        return fail(c, NBX_ERR_CUDA, "graph IF node: cudaStreamBeginCaptureToGraph");
+    }
+    sc->saved = c->stream;
+    c->stream = c->aux_stream;
+    sc->active = true;
+    return NBX_OK;
+}
+
+static int cond_scope_end(nbx_ctx *c, CondScope *sc)
+{
+    if (!sc->active) return NBX_OK;
+    sc->active = false;
+    cudaGraph_t body = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &body);
+    c->stream = sc->saved;
+    if (e != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return fail(c, NBX_ERR_CUDA, "graph IF node: body capture"); }
+    return NBX_OK;
+}
+
 static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
 {
     CellPairArgs a{};
@@ -1093,13 +1200,24 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         return NBX_OK; // a list overflow is reported by nbx_slab_verlet_check (no scan fallback on stale cells)
     }
     const double lim = 0.5 * skin * (1.0 - 1e-9);
-    timer_begin(c, NBX_T_CELL_BUILD);
-    verlet_check_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, lim * lim, cl->v_flags);
-    timer_end(c, NBX_T_CELL_BUILD);
-    NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags));
+    // the position update already checked the displacements and refreshed the records (vv_pos_lists_kernel)
+    const bool pre = cl->prechecked && same;
+    cl->prechecked = false;
+    if (!pre) {
+        timer_begin(c, NBX_T_CELL_BUILD);
+        verlet_check_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, lim * lim, cl->v_flags);
+        timer_end(c, NBX_T_CELL_BUILD);
+    }
+    CondScope scope;
+    NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope)); // (graph capture: the chain below becomes the body of an IF node)
+    {
+        const int rc = cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags);
+        if (rc != NBX_OK) { cond_scope_end(c, &scope); return rc; }
+    }
     CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin)); // scan threshold of the list build
     VerletArgs v{};
     v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = nullptr;
+    v.consume = (pre && !tiles) ? 1 : 0;
     ta.tlist = cl->t_list;
     const unsigned tile_grid = (unsigned)(cl->grid.nc[0] * cl->grid.nc[0] * ta.chunks);
     const size_t tile_smem = sizeof(double) * kTileCap * (pot == 0 ? 3 : 4);
@@ -1112,7 +1230,8 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     if (tiles) tile_build_kernel<<<tile_grid, 128, 0, c->stream>>>(a, v, ta);
     else verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
     verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags, nullptr);
-    verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, nullptr);
+    NBX_TRY(cond_scope_end(c, &scope));
+    if (!v.consume) verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, nullptr);
     timer_end(c, NBX_T_CELL_BUILD);
     a = make_args(c, cl, R2);
     const int acc_flag = accumulate ? 1 : 0;
@@ -1236,7 +1355,7 @@ void cells_free(CellList *cl)
     cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->sums);
     cudaFree(cl->arrival); cudaFree(cl->tmp_idx); cudaFree(cl->tmp_key);
     cudaFree(cl->v_list); cudaFree(cl->v_nlist); cudaFree(cl->v_ref); cudaFree(cl->v_flags);
-    cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->sp4); cudaFree(cl->sl4);
+    cudaFree(cl->sorted_idx); cudaFree(cl->scell); cudaFree(cl->sp4); cudaFree(cl->sl4); cudaFree(cl->slot_of);
     *cl = CellList{};
 }
 

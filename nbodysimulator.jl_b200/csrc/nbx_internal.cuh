@@ -43,6 +43,8 @@ struct CellList {
     int *tmp_key = nullptr;     // [n] ordering key (global id) per slot, only when the context has ids
     int *sums = nullptr;        // scan block totals
     int *sorted_idx = nullptr;  // [n] particle index of the k-th slot in cell order
+    int *slot_of = nullptr;     // [n] inverse: slot of a particle
+    bool prechecked = false;    // the position update already did this evaluation's displacement check + record refresh
     int *scell = nullptr;       // [n] cell id of the k-th slot
     double4 *sp4 = nullptr;     // [n] cell order: x, y, z unwrapped (as the reference's predicate uses them), w = charge
     float4 *sl4 = nullptr;      // [n] cell order: wrapped coordinates in cell units (fp32 prefilter), w = exclusion key bits
@@ -184,6 +186,13 @@ struct nbx_ctx {
     // to verlet_force_kernel but measured 0.44 ms against 0.21 ms at 1,048,576 argon atoms (r01c) -- the staging area
     // limits the SM to 16-24 warps and the 8-byte shared gathers conflict 3-fold; kept as a tested option ("tiles").
     int opt_tiles = 0;
+    // CUDA graph of nbx_step_vv: the conditional rebuild chain (nine launches that return at once) becomes the body of
+    // an IF node decided by one single-thread kernel (cudaGraphSetConditional); falls back to plain capture if the
+    // runtime refuses
+    int opt_cond_nodes = 1;
+    bool cond_capture = false, cond_fail = false;
+    cudaStream_t aux_stream = nullptr;
+    int opt_fuse_update = 1;       // nbx_step_vv: position update + displacement check + record refresh in one kernel
     int64_t tiles_min_n = 200000;
     bool tiles_attr_set = false;
     int opt_verlet_lanes = 0;      // lanes per target of the Verlet force kernel (0: chosen from the system size; 1, 2, 4, 8)
@@ -265,6 +274,8 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
 int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64_t ld, double R2, int64_t *offsets,
                     int32_t *list, int64_t cap);
 void cells_free(CellList *cl);
+bool lists_can_fuse_update(const nbx_ctx *c, const CellList *cl, const double *px);
+int launch_vv_pos_lists(nbx_ctx *c, CellList *cl, const double *w, double dt);
 int cells_scan(nbx_ctx *c, const int *in, int *out, int n, int *sums, int round_to, const int *cond);
 // nbx_fused.cu
 bool fused_eligible(nbx_ctx *c, int64_t nsteps);

@@ -430,6 +430,34 @@ def test_tile_list_kernels_are_bit_identical_to_the_list_kernels(oracle, cells, 
     _check(out[1][0], make_oracle(oracle, spec).rhs(u, w["v"], NT))
 
 
+@pytest.mark.parametrize("thermo", [None, "berendsen"])
+def test_fused_position_update_is_bit_identical(oracle, thermo):
+    """nbx_step_vv with one cutoff potential: the position update also checks the displacements and refreshes the
+    cell-order records (vv_pos_lists_kernel) -- same arithmetic, same rebuild steps, bit-identical trajectory; eager and
+    graph replay."""
+    w, u = _fcc(10, 0.05, 39, drift=True)
+    v = F(3.0 * w["v"])
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    if thermo:
+        spec["thermostat"] = dict(kind="berendsen", T=90.0, tau=0.04, kB=w["kB"], N=u.shape[1], Nc=0)
+    out = {}
+    for fuse, graph in ((0, 1), (1, 1), (1, 0)):
+        ctx = make_context(spec)
+        ctx.set_option("fuse_update", fuse)
+        ctx.set_option("graph", graph)
+        ctx.upload(u, v)
+        ctx.step_vv(2e-3, 45)
+        ctx.step_vv(2e-3, 36)
+        out[(fuse, graph)] = ctx.download(want_dv=True)
+        assert ctx.info("verlet_rebuilds") >= 3 and ctx.info("verlet_overflow") == 0
+        if graph:
+            assert ctx.info("graph_if_nodes") == 1  # the rebuild chain was captured as the body of an IF node
+        ctx.close()
+    for key in ((1, 1), (1, 0)):
+        for a, b in zip(out[key], out[(0, 1)]):
+            assert np.array_equal(a, b)
+
+
 def test_tile_list_kernels_coulomb(oracle):
     rng = np.random.Generator(np.random.Philox(53))
     m, L = 16, 16.0
