@@ -261,8 +261,22 @@ NBX_API int nbx_accel_device(nbx_ctx *ctx, const double *u_dev, double *v_dev, d
 NBX_API int nbx_timing_enable(nbx_ctx *ctx, int enable);
 NBX_API int nbx_timing_get(nbx_ctx *ctx, int phase, double *total_ms, int64_t *count);
 NBX_API int nbx_timing_reset(nbx_ctx *ctx);
-/* Tuning knobs (integers): "cell_list" (0 = never, 1 = auto),
- * "rebuild_every", "pair_prefilter", "graph" ...  Unknown key -> NBX_ERR_INVALID. */
+/* Tuning knobs (integers; defaults in parentheses; DESIGN.md section 3 says what each buys).  Unknown key -> NBX_ERR_INVALID.
+ *   cutoff potentials : "cell_list" (1: cell lists where the box allows, 0: all-pairs kernel with the exact predicate),
+ *                       "prefilter" (1: fp32 candidate scan before the exact fp64 predicate),
+ *                       "verlet_skin_permille" (100: Verlet lists with skin = 0.1 R; 0: rescan the cells every evaluation),
+ *                       "verlet_lanes" (0: lanes per target chosen from the system size; 1, 2, 4, 8),
+ *                       "tiles" (0) / "tiles_min_n": list kernel over shared-memory staged candidate rows,
+ *                       "fused_step" (0) / "fused_cluster" (4) / "fused_min_steps" (16): one kernel per step (nbx_fused.cu),
+ *   nbx_step_vv       : "graph" (1: two-step CUDA graph), "graph_if_nodes" (1: rebuild chain as the body of an IF node),
+ *                       "fuse_update" (1: position update + displacement check + record refresh in one kernel),
+ *   all-pairs         : "symmetric_pairs" (1: Newton's-third-law kernel), "symmetric_min_n" (8192), "sym_variant" (0),
+ *                       "uniform_weights" (0 forgets that all masses / charges are equal),
+ *   slab driver       : "slab_record_halo", "slab_rebuild", "temperature_slot" (see the slab section above).
+ * nbx_get_info keys: "n", "npad", "ncols", "water", "sm_count", "cells_lj", "cells_el", "verlet_lj", "verlet_el",
+ * "verlet_overflow", "verlet_rebuilds", "tiles_lj", "tiles_el", "graph_if_nodes", "fused_steps", "fused_disabled",
+ * "fused_list_cap", "allpairs_grid", "allpairs_chunks", "slab_own", "slab_ghost", "slab_layer_lo", "slab_layer_hi",
+ * "slab_layers", "slab_verlet". */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, int64_t value);
 NBX_API int nbx_get_info(nbx_ctx *ctx, const char *key, int64_t *value);
 /* DFMA-saturation microbenchmark: the measured FP64 roofline denominator (TFLOP/s). */
