@@ -283,6 +283,19 @@ NBX_API int nbx_get_info(nbx_ctx *ctx, const char *key, int64_t *value);
 NBX_API int nbx_measure_fp64_peak(nbx_ctx *ctx, double *tflops, double *sm_mhz_effective);
 /* STREAM-style copy bandwidth (GB/s, read+write) of this device, for the HBM roofline. */
 NBX_API int nbx_measure_hbm_peak(nbx_ctx *ctx, double *gbs);
+/* ---- analysis of saved frames (the first caller-side hotspots once the step loop is fast) ---------
+ * rdf(sr), src/nbody_simulation_result.jl:664-709: O(frames x N^2) pair loop over the Lennard-Jones index set (all
+ * bodies, or the oxygens of water) with get_interparticle_distance of the cubic box.  Per frame: nbx_rdf_add(u) adds the
+ * frame's pairs to a device histogram (u: HOST 3 x ncols frame, or NULL for the resident positions) exactly as :676-693
+ * do -- `r2 < (0.5 L)^2`, bin = ceil(r / dr), `1 < bin <= maxbin` -> += 2; integer counts, bit-exact.  nbx_rdf_get
+ * returns the counts (hist[b - 1] = the reference's hist[b]) and the number of frames; the caller normalises as :695-707.
+ * nbx_rdf_reset(maxbin) clears it (the reference uses maxbin = 1000, the default).
+ * msd(sr), :730-783: nbx_msd(u0, u, out) = mean over the index set of |r(t) - r(0)|^2 for one frame (atoms), or of the
+ * mass-weighted molecular displacement (water); u NULL = the resident positions. */
+NBX_API int nbx_rdf_reset(nbx_ctx *ctx, int maxbin);
+NBX_API int nbx_rdf_add(nbx_ctx *ctx, const double *u);
+NBX_API int nbx_rdf_get(nbx_ctx *ctx, int64_t *hist, int64_t cap, int64_t *frames);
+NBX_API int nbx_msd(nbx_ctx *ctx, const double *u0, const double *u, double *out);
 /* Diagnostics for the tests: copies an internal device array of the fused cutoff step (csrc/nbx_fused.cu) to the
  * host.  name: "start" (ncell+1 int32 padded cell starts), "pid", "scell", "nlist" (int32 per slot), "list"
  * (cap_e x cap_slots int32), "x" (4 doubles per slot; which: position buffer 0/1).  *count receives the element

@@ -80,6 +80,10 @@ SIGNATURES = {
     "nbx_measure_hbm_peak": (C.c_int, [_vp, _dp]),
     "nbx_accel_begin": (C.c_int, [_vp, _dp]),
     "nbx_accel_end": (C.c_int, [_vp, _dp]),
+    "nbx_rdf_reset": (C.c_int, [_vp, C.c_int]),
+    "nbx_rdf_add": (C.c_int, [_vp, _dp]),
+    "nbx_rdf_get": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
+    "nbx_msd": (C.c_int, [_vp, _dp, _dp, _dp]),
     "nbx_debug_fetch": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, _i64, C.POINTER(_i64)]),
 }
 
@@ -372,6 +376,28 @@ class Context:
         tf, mhz = C.c_double(), C.c_double()
         self._ck(self.lib.nbx_measure_fp64_peak(self.h, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
+
+    # -- analysis of frames (rdf / msd of the reference's result accessors) ------------------------
+    def rdf_reset(self, maxbin=1000):
+        self._ck(self.lib.nbx_rdf_reset(self.h, int(maxbin)))
+        self._rdf_bins = int(maxbin)
+
+    def rdf_add(self, u=None):
+        """Adds one frame's pair distances to the device histogram (u None: the resident positions)."""
+        self._ck(self.lib.nbx_rdf_add(self.h, None if u is None else _p(_f(u, self.ncols))))
+
+    def rdf_get(self):
+        """(histogram as int64, hist[b - 1] = the reference's hist[b]; frames added)."""
+        bins = getattr(self, "_rdf_bins", 1000)
+        hist = np.zeros(bins, dtype=np.int64)
+        frames = _i64()
+        self._ck(self.lib.nbx_rdf_get(self.h, hist.ctypes.data_as(C.POINTER(_i64)), hist.size, C.byref(frames)))
+        return hist, int(frames.value)
+
+    def msd(self, u0, u=None):
+        out = C.c_double()
+        self._ck(self.lib.nbx_msd(self.h, _p(_f(u0, self.ncols)), None if u is None else _p(_f(u, self.ncols)), C.byref(out)))
+        return out.value
 
     def debug_fetch(self, name, which=0):
         """Internal array of the fused cutoff step (diagnostics for the tests)."""

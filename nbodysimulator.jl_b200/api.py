@@ -582,6 +582,46 @@ def initial_energy(simulation: NBodySimulation):
     return potential_energy(u0[:, :n], simulation) + kinetic_energy(v0[:, :n], get_masses(simulation.system))
 
 
+def rdf(sr: SimulationResult, device: int = 0):
+    """rdf(sr) -> (rs, gr): nbody_simulation_result.jl:664-709.  The O(frames x N^2) pair loop runs on the device, one
+    nbx_rdf_add per saved time (the histogram is integer: identical counts); the normalisation below is :695-707."""
+    sim = sr.simulation
+    if not isinstance(sim.boundary_conditions, CubicPeriodicBoundaryConditions):
+        raise TypeError("rdf reads pbc.L: it needs CubicPeriodicBoundaryConditions")
+    L = sim.boundary_conditions.L
+    n = _ncoord(sim.system)
+    indlen = len(sim.system.bodies)  # LJ index set: all bodies, or one oxygen per water molecule (:302-314)
+    ctx = _configure_context(NBodySimulation(sim.system, sim.tspan, sim.boundary_conditions, NullThermostat(), sim.kb), device)
+    maxbin = 1000
+    ctx.rdf_reset(maxbin)
+    for t in sr.t:
+        ctx.rdf_add(np.asfortranarray(get_position(sr, t)[:, :n]))
+    hist, tlen = ctx.rdf_get()
+    ctx.close()
+    dr = L / maxbin
+    c = 4 / 3 * np.pi * indlen / L ** 3
+    gr, rs = np.zeros(maxbin), np.zeros(maxbin)
+    for b in range(maxbin):
+        rlower = b * dr
+        rupper = rlower + dr
+        nideal = c * (rupper ** 3 - rlower ** 3)
+        gr[b] = (hist[b] / (tlen * indlen)) / nideal
+        rs[b] = rlower + dr / 2
+    return rs, gr
+
+
+def msd(sr: SimulationResult, device: int = 0):
+    """msd(sr) -> (ts, dr2): nbody_simulation_result.jl:730-783 (atoms: mean |r(t) - r(0)|^2; water: of the mass-weighted
+    molecular displacement), one device reduction per saved time."""
+    sim = sr.simulation
+    n = _ncoord(sim.system)
+    ctx = _configure_context(NBodySimulation(sim.system, sim.tspan, sim.boundary_conditions, NullThermostat(), sim.kb), device)
+    u0 = np.asfortranarray(get_position(sr, sr.t[0])[:, :n])
+    dr2 = np.array([ctx.msd(u0, np.asfortranarray(get_position(sr, t)[:, :n])) for t in sr.t])
+    ctx.close()
+    return sr.t.copy(), dr2
+
+
 def run_simulation(s: NBodySimulation, alg=None, *, dt: Optional[float] = None, saveat: Optional[int] = None,
                    save_everystep: Optional[bool] = None, device: int = 0, seed: int = 0, rtol=1e-6, atol=1e-9):
     """nbody_simulation_result.jl:468-492.  Langevin thermostats run the SDE path (EM), everything else

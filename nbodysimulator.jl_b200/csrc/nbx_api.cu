@@ -186,6 +186,7 @@ static void free_system(nbx_ctx *c)
     cells_free(&c->cl_lj);
     cells_free(&c->cl_el);
     fused_free(c);
+    analysis_free(c);
     c->fz = FusedState();
     c->T_slot = 0;
     slab_free(c);
@@ -1079,6 +1080,33 @@ int nbx_measure_hbm_peak(nbx_ctx *c, double *gbs)
 {
     NBX_TRY(guard(c));
     return measure_hbm_peak(c, gbs);
+}
+
+int nbx_rdf_reset(nbx_ctx *c, int maxbin)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_rdf_reset"));
+    return analysis_rdf_reset(c, maxbin);
+}
+
+int nbx_rdf_add(nbx_ctx *c, const double *u)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_rdf_add"));
+    return analysis_rdf_add(c, u);
+}
+
+int nbx_rdf_get(nbx_ctx *c, int64_t *hist, int64_t cap, int64_t *frames)
+{
+    NBX_TRY(guard(c));
+    return analysis_rdf_get(c, hist, cap, frames);
+}
+
+int nbx_msd(nbx_ctx *c, const double *u0, const double *u, double *out)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_msd"));
+    return analysis_msd(c, u0, u, out);
 }
 
 int nbx_debug_fetch(nbx_ctx *c, const char *name, int which, void *dst, int64_t cap, int64_t *count)

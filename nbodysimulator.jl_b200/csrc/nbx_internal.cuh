@@ -213,6 +213,12 @@ struct nbx_ctx {
     bool mass_uniform = false, charge_uniform = false; // all weights equal (value = first element)
     double h_q1 = 0.0;
 
+    // ---- analysis of frames (nbx_analysis.cu) ---------------------------------------------------
+    unsigned long long *an_hist = nullptr; // rdf pair-distance histogram
+    int an_bins = 0;
+    int64_t an_frames = 0;
+    double *an_pos = nullptr, *an_pos0 = nullptr, *an_red = nullptr;
+
     // ---- neighbour scratch ------------------------------------------------------------------
     // ---- host staging -----------------------------------------------------------------------
     double *h_pin = nullptr; size_t h_pin_bytes = 0;
@@ -277,6 +283,12 @@ void cells_free(CellList *cl);
 bool lists_can_fuse_update(const nbx_ctx *c, const CellList *cl, const double *px);
 int launch_vv_pos_lists(nbx_ctx *c, CellList *cl, const double *w, double dt);
 int cells_scan(nbx_ctx *c, const int *in, int *out, int n, int *sums, int round_to, const int *cond);
+// nbx_analysis.cu
+int analysis_rdf_reset(nbx_ctx *c, int maxbin);
+int analysis_rdf_add(nbx_ctx *c, const double *u_host);
+int analysis_rdf_get(nbx_ctx *c, int64_t *hist, int64_t cap, int64_t *frames);
+int analysis_msd(nbx_ctx *c, const double *u0_host, const double *u_host, double *out);
+void analysis_free(nbx_ctx *c);
 // nbx_fused.cu
 bool fused_eligible(nbx_ctx *c, int64_t nsteps);
 int fused_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done); // *steps_done < nsteps: continue unfused, positions already advanced

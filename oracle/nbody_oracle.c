@@ -442,6 +442,52 @@ ORC_API double orc_kinetic_energy(const double *vs, const double *ms, int64_t n)
     return e;
 }
 
+/* ---- analysis of saved frames (src/nbody_simulation_result.jl:664-783) -------------------------------
+ * rdf, one frame (:676-693): pairs i < j over the Lennard-Jones index set (every idx_stride-th column: all atoms, or
+ * the oxygens of water), distance through get_interparticle_distance of the cubic box, `if r2 < (0.5 L)^2:
+ * bin = ceil(r / dr); if 1 < bin <= maxbin: hist[bin] += 2` with dr = L / maxbin.  hist is 0-based here:
+ * hist[b - 1] is the reference's hist[b].  The normalisation (:695-707) stays with the caller. */
+ORC_API void orc_rdf_hist(const double *rs, int64_t n, int idx_stride, double L, int maxbin, int64_t *hist)
+{
+    const double bc[6] = {L, 0, 0, 0, 0, 0};
+    const double dr = L / maxbin;
+    const double lim = (0.5 * L) * (0.5 * L);
+    for (int64_t i = 0; i < n; i += idx_stride)
+        for (int64_t j = i + idx_stride; j < n; j += idx_stride) {
+            double rij[3], r, r2;
+            orc_distance_impl(rs + 3 * i, rs + 3 * j, 1, bc, rij, &r, &r2);
+            if (r2 < lim) {
+                const double b = ceil(r / dr);
+                if (b > 1 && b <= maxbin) hist[(int64_t)b - 1] += 2;
+            }
+        }
+}
+
+/* msd, one frame: atoms (:730-752) mean over the index set of |r(t) - r(0)|^2; water (:754-783) the same for the
+ * mass-weighted centre of each molecule ((dO mO + dH1 mH + dH2 mH) / (2 mH + mO)). */
+ORC_API double orc_msd(const double *rs, const double *rs0, int64_t n, int water, double mO, double mH)
+{
+    double s = 0.0;
+    if (!water) {
+        for (int64_t i = 0; i < n; ++i) {
+            const double d0 = rs[3 * i] - rs0[3 * i], d1 = rs[3 * i + 1] - rs0[3 * i + 1], d2 = rs[3 * i + 2] - rs0[3 * i + 2];
+            s += d0 * d0 + d1 * d1 + d2 * d2;
+        }
+        return s / (double)n;
+    }
+    const int64_t nm = n / 3;
+    for (int64_t m = 0; m < nm; ++m) {
+        double d[3];
+        for (int k = 0; k < 3; ++k) {
+            const double dO = rs[9 * m + k] - rs0[9 * m + k], dH1 = rs[9 * m + 3 + k] - rs0[9 * m + 3 + k],
+                         dH2 = rs[9 * m + 6 + k] - rs0[9 * m + 6 + k];
+            d[k] = (dO * mO + dH1 * mH + dH2 * mH) / (2 * mH + mO);
+        }
+        s += d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    }
+    return s / (double)nm;
+}
+
 ORC_API double orc_lj_potential(const double *rs, int64_t n, int idx_stride, double eps, double sigma2,
                                 double R2, int bc_kind, const double *bc)
 {

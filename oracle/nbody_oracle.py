@@ -79,6 +79,10 @@ def lib():
         L.orc_bond_potential.restype = C.c_double
         L.orc_angle_potential.argtypes = [dp, C.c_int64, C.c_double, C.c_double]
         L.orc_angle_potential.restype = C.c_double
+        L.orc_rdf_hist.argtypes = [dp, C.c_int64, C.c_int, C.c_double, C.c_int, ip64]
+        L.orc_rdf_hist.restype = None
+        L.orc_msd.argtypes = [dp, dp, C.c_int64, C.c_int, C.c_double, C.c_double]
+        L.orc_msd.restype = C.c_double
         L.orc_max_threads.argtypes = []
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -225,6 +229,32 @@ class System:
         v = _f(v)
         N = self.n if N is None else N
         return float(lib().orc_md_temperature(_dp(v), _dp(self.ms), float(kB), int(N), int(Nc), self.n))
+
+
+def rdf_hist(u, L, idx_stride=1, maxbin=1000):
+    """Pair-distance histogram of ONE frame exactly as rdf's inner loops build it
+    (src/nbody_simulation_result.jl:676-693); hist[b - 1] is the reference's hist[b]."""
+    u = _f(u)
+    hist = np.zeros(maxbin, dtype=np.int64)
+    lib().orc_rdf_hist(_dp(u), u.shape[1], int(idx_stride), float(L), int(maxbin), hist.ctypes.data_as(C.POINTER(C.c_int64)))
+    return hist
+
+
+def rdf_normalise(hist, nframes, nidx, L):
+    """(rs, gr) from the accumulated histogram: src/nbody_simulation_result.jl:695-707."""
+    maxbin = len(hist)
+    dr = L / maxbin
+    c = 4 / 3 * np.pi * nidx / L ** 3
+    rlower = np.arange(maxbin) * dr
+    rupper = rlower + dr
+    nideal = c * (rupper ** 3 - rlower ** 3)
+    return rlower + dr / 2, (hist / (nframes * nidx)) / nideal
+
+
+def msd(u, u0, water=False, mO=0.0, mH=0.0):
+    """Mean squared displacement of ONE frame against the first: src/nbody_simulation_result.jl:730-783."""
+    u, u0 = _f(u), _f(u0)
+    return float(lib().orc_msd(_dp(u), _dp(u0), u.shape[1], int(bool(water)), float(mO), float(mH)))
 
 
 def gravity_targets_ld(u, ms, G, targets, nthreads=1):

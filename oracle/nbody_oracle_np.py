@@ -249,3 +249,30 @@ def rhs(spec, u, v):
             for k in range(3):
                 dv[k, i] += s * float(v[k, i])
     return dv
+
+
+def rdf_hist(u, L, idx_stride=1, maxbin=1000):
+    """One frame of rdf's histogram (src/nbody_simulation_result.jl:676-693), plain Python loops; 0-based bins."""
+    n = u.shape[1]
+    dr = L / maxbin
+    hist = [0] * maxbin
+    bc = ("cubic", L)
+    for i in range(0, n, idx_stride):
+        ri = [float(u[k, i]) for k in range(3)]
+        for j in range(i + idx_stride, n, idx_stride):
+            _, r, r2 = distance(ri, [float(u[k, j]) for k in range(3)], bc)
+            if r2 < (0.5 * L) ** 2:
+                b = math.ceil(r / dr)
+                if 1 < b <= maxbin:
+                    hist[b - 1] += 2
+    return hist
+
+
+def msd(u, u0):
+    """src/nbody_simulation_result.jl:730-752 for one frame (atoms)."""
+    n = u.shape[1]
+    s = 0.0
+    for i in range(n):
+        d = [float(u[k, i]) - float(u0[k, i]) for k in range(3)]
+        s += d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+    return s / n

@@ -675,6 +675,48 @@ def test_energy_matches_oracle(oracle):
 # ------------------------------------------------------------------------------------------
 # error behaviour at the boundary
 # ------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------
+# analysis of frames: rdf / msd (src/nbody_simulation_result.jl:664-783)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("drift", [False, True])
+def test_rdf_histogram_is_bit_exact(oracle, drift):
+    """Integer pair-distance histogram of rdf's inner loops: every count equal to the oracle's, for atoms (several
+    tiles, drifted coordinates: the wrap loops) and for the oxygens of water (every third column); two frames add up."""
+    w, u = _fcc(9, 0.08, 61, drift)  # 2,916 atoms = 12 tiles of 256
+    ctx = make_context(dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"]))
+    ctx.rdf_reset(1000)
+    ctx.rdf_add(u)
+    h1, frames = ctx.rdf_get()
+    ref = oracle.rdf_hist(u, w["L"])
+    assert frames == 1 and h1.sum() > 0 and np.array_equal(h1, ref)
+    ctx.upload(u, w["v"])
+    ctx.rdf_add(None)  # the resident positions
+    h2, frames = ctx.rdf_get()
+    assert frames == 2 and np.array_equal(h2, 2 * ref)
+    ctx.close()
+    ww, uw, wspec = _water(8, 4)
+    ctx = make_context(wspec)
+    ctx.rdf_add(uw)
+    hw, _ = ctx.rdf_get()
+    assert np.array_equal(hw, oracle.rdf_hist(uw, ww["L"], idx_stride=3))
+    ctx.close()
+
+
+def test_msd_matches_oracle(oracle):
+    w, u = _fcc(8, 0.05, 63)
+    rng = np.random.Generator(np.random.Philox(64))
+    u1 = F(u + 0.3 * rng.standard_normal(u.shape))
+    ctx = make_context(dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"]))
+    assert ctx.msd(u, u1) == pytest.approx(oracle.msd(u1, u), rel=1e-13)
+    assert ctx.msd(u, u) == 0.0
+    ctx.close()
+    ww, uw, wspec = _water(6, 4)
+    uw1 = F(uw + 0.01 * rng.standard_normal(uw.shape))
+    ctx = make_context(wspec)
+    assert ctx.msd(uw, uw1) == pytest.approx(oracle.msd(uw1, uw, water=True, mO=ww["ms"][0], mH=ww["ms"][1]), rel=1e-13)
+    ctx.close()
+
+
 def test_errors_are_reported_not_thrown():
     from nbody_b200._lib import Context, NbxError, ERR_INVALID, ERR_NONFINITE
 

@@ -13,7 +13,7 @@ from nbody_b200.api import (AndersenThermostat, BerendsenThermostat, ChargedPart
                             PotentialNBodySystem, SPCFwParameters, SecondOrderODEProblem, Tsit5, VelocityVerlet,
                             WaterSPCFw, generate_bodies_in_cell_nodes, get_accelerating_function, get_position,
                             get_velocity, initial_energy, kinetic_energy, potential_energy, run_simulation,
-                            temperature, total_energy)
+                            msd, rdf, temperature, total_energy)
 
 pytestmark = pytest.mark.gpu
 
@@ -204,6 +204,32 @@ def test_water_spcfw_short_run():
     vs = get_velocity(sr, t1)
     ms = np.tile([water.mO, water.mH, water.mH], len(water.bodies))
     assert temperature(sr, t1) == pytest.approx(np.dot(ms, (vs ** 2).sum(axis=0)) / (kb * ndf), rel=1e-12)
+
+
+def test_lennard_jones_rdf_and_msd():
+    # test/lennard_jones_test.jl:120-150: 125 argon atoms, cubic PBC, R = 0.5 L, 400 VV steps; MSD grows, RDF peaks near sigma
+    T, kb = 120.0, 8.3144598e-3
+    eps, sigma, m = T * kb, 0.34, 39.95
+    L = 5 * sigma
+    N, tau = 125, 0.5e-3
+    bodies = generate_bodies_in_cell_nodes(N, m, math.sqrt(kb * T / m), L, rng=np.random.Generator(np.random.Philox(125)))
+    system = PotentialNBodySystem(bodies, {"lennard_jones": LennardJonesParameters(eps, sigma, 0.5 * L)})
+    sim = NBodySimulation(system, (0.0, 400 * tau), CubicPeriodicBoundaryConditions(L), kb)
+    result = run_simulation(sim, VelocityVerlet(), dt=tau, saveat=20)
+    ts, dr2 = msd(result)
+    assert dr2[0] < dr2[-1] and dr2[0] == 0.0
+    rs, grs = rdf(result)
+    assert rs[int(np.argmax(grs))] / sigma == pytest.approx(1.0, abs=1.0)
+    # the device histogram is the reference's, count for count; the device msd is the reference's sum to rounding
+    from oracle import nbody_oracle as orc
+
+    orc.build()
+    hist = sum(orc.rdf_hist(np.asfortranarray(get_position(result, t)), L) for t in result.t)
+    rs_o, gr_o = orc.rdf_normalise(hist, len(result.t), N, L)
+    assert np.allclose(rs, rs_o, rtol=1e-14, atol=0.0) and np.allclose(grs, gr_o, rtol=1e-12, atol=0.0)  # (same counts; the normalisation is host arithmetic)
+    x0 = np.asfortranarray(get_position(result, result.t[0]))
+    for t, d in zip(ts, dr2):
+        assert d == pytest.approx(orc.msd(np.asfortranarray(get_position(result, t)), x0), rel=1e-12, abs=0.0)
 
 
 def test_plugin_closure_contract():

@@ -322,3 +322,28 @@ def test_neighbor_predicate_matches_distance():
     nb = s.neighbors(u, 5, 2.25)
     ref = [j for j in range(u.shape[1]) if j != 5 and onp.distance(u[:, 5], u[:, j], ("cubic", d["L"]))[2] < 2.25 ** 2]
     assert nb.tolist() == ref and len(ref) > 10
+
+
+# ----------------------------------------------------------------------------------------
+# analysis of frames: rdf / msd (src/nbody_simulation_result.jl:664-783)
+# ----------------------------------------------------------------------------------------
+def test_rdf_and_msd_c_equals_python():
+    rng = np.random.Generator(np.random.Philox(21))
+    L = 3.0
+    u = F(rng.random((3, 70)) * L * 1.6 - 0.3 * L)  # outside the box too: the wrap loops matter
+    assert np.array_equal(orc.rdf_hist(u, L), np.array(onp.rdf_hist(u, L)))
+    assert np.array_equal(orc.rdf_hist(u[:, :69], L, idx_stride=3), np.array(onp.rdf_hist(u[:, :69], L, idx_stride=3)))
+    u1 = F(u + 0.1 * rng.standard_normal(u.shape))
+    assert orc.msd(u1, u) == onp.msd(u1, u)
+
+
+def test_rdf_counts_every_pair_inside_half_the_box_twice():
+    """Closed form: a pair at distance d < L/2 lands in bin ceil(d / dr) with weight 2; bin 1 is never filled (`bin > 1`,
+    src/nbody_simulation_result.jl:688)."""
+    L = 10.0
+    u = F([[1.0, 1.0 + 3.337, 1.0], [1.0, 1.0, 1.0], [1.0, 1.0, 1.0 + 0.004]])
+    h = orc.rdf_hist(u, L)
+    dr = L / 1000
+    assert h.sum() == 4 and h[math.ceil(3.337 / dr) - 1] == 4  # pairs (0,1) and (1,2) share a bin; (0,2) at 0.004 < dr is dropped
+    rs, gr = orc.rdf_normalise(h, 1, 3, L)
+    assert rs[0] == dr / 2 and gr[0] == 0.0
