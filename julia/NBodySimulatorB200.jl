@@ -150,6 +150,45 @@ function NBodySimulator.run_simulation(s::NBodySimulation, ::B200VelocityVerlet;
     return NBodySimulator.SimulationResult(sol, s)
 end
 
-export B200Context, B200Problem, B200VelocityVerlet
+# ---- (3) frame analysis on the device: rdf / msd (src/nbody_simulation_result.jl:664-783) ------------------------
+# Same return values as NBodySimulator.rdf / msd; the O(frames x N^2) pair loop runs in rdf_kernel (integer histogram,
+# identical counts), the normalisation is the reference's (:695-707).
+function rdf_b200(sr::NBodySimulator.SimulationResult; device::Integer = 0)
+    s = sr.simulation
+    ctx = configure!(B200Context(device), s)
+    L = s.boundary_conditions.L
+    maxbin = 1000
+    check(ctx, ccall((:nbx_rdf_reset, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, maxbin))
+    for t in sr.solution.t
+        cc = Matrix{Float64}(NBodySimulator.get_position(sr, t))
+        check(ctx, ccall((:nbx_rdf_add, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, cc))
+    end
+    hist = zeros(Int64, maxbin)
+    frames = Ref{Int64}(0)
+    check(ctx, ccall((:nbx_rdf_get, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Int64}), ctx.h, hist, maxbin, frames))
+    indlen = length(s.system.bodies)
+    dr = L / maxbin
+    c = 4 / 3 * π * indlen / L^3
+    rs = [(bin - 1) * dr + dr / 2 for bin in 1:maxbin]
+    gr = [(hist[bin] / (frames[] * indlen)) / (c * ((bin * dr)^3 - ((bin - 1) * dr)^3)) for bin in 1:maxbin]
+    return (rs, gr)
+end
+
+function msd_b200(sr::NBodySimulator.SimulationResult; device::Integer = 0)
+    s = sr.simulation
+    ctx = configure!(B200Context(device), s)
+    ts = sr.solution.t
+    cc0 = Matrix{Float64}(NBodySimulator.get_position(sr, ts[1]))
+    dr2 = zeros(length(ts))
+    out = Ref{Float64}(0.0)
+    for (k, t) in enumerate(ts)
+        cc = Matrix{Float64}(NBodySimulator.get_position(sr, t))
+        check(ctx, ccall((:nbx_msd, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}), ctx.h, cc0, cc, out))
+        dr2[k] = out[]
+    end
+    return (ts, dr2)
+end
+
+export B200Context, B200Problem, B200VelocityVerlet, rdf_b200, msd_b200
 
 end # module
