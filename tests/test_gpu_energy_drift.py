@@ -86,3 +86,25 @@ def test_lj_argon_32k_atoms_1000_steps_property():
     assert abs((ek1 + ep1) - (ek0 + ep0)) / abs(ek0 + ep0) < 2e-4
     p = (vg * w["ms"]).sum(axis=1)
     assert np.abs(p).max() < 1e-9 * np.abs(vg * w["ms"]).sum()
+
+
+def test_lj_argon_config3_full_size_1000_steps_drift():
+    """BASELINE config 3 at its full size on one device: 1,048,576 argon atoms, cubic PBC, R = 2.25 sigma, NVE, 1000
+    velocity-Verlet steps of the example's dt.  Energies by the device reductions (the reference's O(N^2) host loops are
+    out of reach here; test_lj_argon_1000_steps ties the reductions to the oracle at 500 atoms): |dE/E| < 1e-4 and the
+    total momentum stays at rounding level."""
+    w = wl.fcc_argon_reduced(64)
+    rng = np.random.Generator(np.random.Philox(65))
+    u = F(w["u"] + 0.03 * rng.standard_normal(w["u"].shape))
+    ctx = make_context(dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"]))
+    ctx.upload(u, w["v"])
+    ek0, ep0, _ = ctx.energy()
+    ctx.step_vv(w["dt"], 1000)
+    ek1, ep1, _ = ctx.energy()
+    _, vg, _ = ctx.download()
+    rebuilds = ctx.info("verlet_rebuilds")
+    ctx.close()
+    assert abs((ek1 + ep1) - (ek0 + ep0)) / abs(ek0 + ep0) < 1e-4
+    assert rebuilds >= 2
+    p = (vg * w["ms"]).sum(axis=1)
+    assert np.abs(p).max() < 1e-9 * np.abs(vg * w["ms"]).sum()
