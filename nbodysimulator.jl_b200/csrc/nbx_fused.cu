@@ -516,7 +516,7 @@ static int fz_ensure(nbx_ctx *c, int C, int64_t ncell, int cap_e)
 }
 
 template <int C>
-static int fz_chain(nbx_ctx *c, const FzArgs &a, bool first)
+static int fz_chain(nbx_ctx *c, const FzArgs &a)
 {
     const int sm = c->sm_count;
     auto grid = [&](int64_t work, int threads) {
@@ -531,7 +531,6 @@ static int fz_chain(nbx_ctx *c, const FzArgs &a, bool first)
     fz_place_kernel<C><<<grid(a.n, 128), 128, 0, c->stream>>>(a);
     fz_build_kernel<C><<<grid(a.cap_slots, 128), 128, 0, c->stream>>>(a);
     timer_end(c, NBX_T_CELL_BUILD);
-    (void)first;
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
 }
@@ -609,7 +608,7 @@ static int fz_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done)
     };
     auto enqueue = [&](int64_t j) -> int {
         const FzArgs s = args_of(j);
-        NBX_TRY(fz_chain<C>(c, s, j == 1));
+        NBX_TRY(fz_chain<C>(c, s));
         return fz_step<C>(c, s, j < nsteps);
     };
 
@@ -618,7 +617,7 @@ static int fz_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done)
     NBX_CUDA(c, cudaMemsetAsync(z.flags + FZ_REQ1, 1, sizeof(int), c->stream)); // != 0: build before step 1
     int64_t j = 1;
     if (c->opt_fused_debug & 4) { // test hook ("fused_debug" bit 2): lists only, the unfused path runs the steps
-        NBX_TRY(fz_chain<C>(c, args_of(1), true));
+        NBX_TRY(fz_chain<C>(c, args_of(1)));
         NBX_CUDA(c, cudaStreamSynchronize(c->stream));
         *steps_done = 0;
         return NBX_OK;

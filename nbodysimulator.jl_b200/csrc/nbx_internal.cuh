@@ -201,7 +201,7 @@ struct nbx_ctx {
     // force loop and per-slot update wait on the same L1/LSU path, so fusing them hides nothing, and cluster lists
     // (C > 1) pay more in issue slots than they save in gathers.  Kept as a tested option ("fused_step").
     int opt_fused = 0;
-    int opt_fused_debug = 0;
+    int opt_fused_debug = 0;       // test hook: bit 2 = build the cluster lists only (tests/test_gpu_fused.py)
     int opt_fused_cluster = 4;     // slots per cluster (1, 2, 4 or 8)
     int64_t fused_min_steps = 16;  // shorter runs stay on the unfused path (every fused run starts with a list build)
     nbx::FusedState fz;

@@ -297,7 +297,8 @@ int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int 
 {
     // variants (option "sym_variant"): T stationary and U travelling bodies per lane, CTAs per SM, ring unroll.
     // Measured on the 262,144-body sphere, equal masses (r01c, ms per launch): <8,2,2,4> 42.7 (default), <8,1,2,2> 43.5,
-    // <8,2,2,2> 44.2, <8,2,2,1> 44.2, <8,4,2,1> 44.9, <8,1,3,4> 46.8, <4,4,3,2> 47.2; ordered kernel 70.8.
+    // <8,2,2,2> 44.2, <8,2,2,1> 44.2, <8,4,2,1> 44.9, <8,1,3,4> 46.8, <4,4,3,2> 47.2; ordered kernel 70.8.  Deeper unrolls
+    // lose: <8,2,2,8> 48.8, <8,2,2,16> 59.1 (instruction cache); <8,1,2,8> 42.7 ties with the default.
     switch (c->opt_sym_variant) {
     case 1:
         if (uniform) return run_sym<4, 4, true, 3, 2>(c, w, wval, scale_kind, scale, acc_out, accumulate);
@@ -317,6 +318,9 @@ int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int 
     case 6:
         if (uniform) return run_sym<8, 4, true, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
         return run_sym<8, 4, false, 2, 1>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+    case 7:
+        if (uniform) return run_sym<8, 1, true, 2, 8>(c, w, wval, scale_kind, scale, acc_out, accumulate);
+        return run_sym<8, 1, false, 2, 8>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     default:
         if (uniform) return run_sym<8, 2, true, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
         return run_sym<8, 2, false, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
