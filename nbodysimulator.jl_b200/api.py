@@ -622,6 +622,105 @@ def msd(sr: SimulationResult, device: int = 0):
     return sr.t.copy(), dr2
 
 
+# ---------------------------------------------------------------------------------------------
+# trajectory output: PDB text (nbody_simulation_result.jl:786-1001).  Host-side formatting of saved frames, as in the
+# reference; nothing here touches the device.
+# ---------------------------------------------------------------------------------------------
+def _julia_float(x: float) -> str:
+    """Julia's string interpolation of a Float64 (shortest round-trip, '5.0e-5' rather than Python's '5e-05')."""
+    r = repr(float(x))
+    if "e" in r:
+        mant, ex = r.split("e")
+        if "." not in mant:
+            mant += ".0"
+        return f"{mant}e{int(ex)}"
+    return r
+
+
+def _hetatm(serial, name, res, resseq, xyz, element):
+    # "HETATM", lpad(serial, 5), "  ", rpad(name, 4), res, lpad(resseq, 6), "    ", 3 x %8.3f, "  1.00", "  0.00", 10 blanks, lpad(element, 2)
+    return ("HETATM" + str(serial).rjust(5) + "  " + name.ljust(4) + res + str(resseq).rjust(6) + "    " +
+            "".join(("%8.3f" % c).rjust(8) for c in xyz) + "1.00".rjust(6) + "0.00".rjust(6) + " " * 10 + element.rjust(2))
+
+
+def write_pdb_data(f, sr: SimulationResult):
+    """write_pdb_data(io, result): :792-865.  Coordinates x 10 (nm -> Angstrom), wrapped into [0, 10 L) with
+    x - L floor(x / L); water keeps every molecule whole (hydrogens placed relative to the wrapped oxygen)."""
+    sim = sr.simulation
+    n = len(sim.system.bodies)
+    L = 10 * sim.boundary_conditions.L
+    water = isinstance(sim.system, WaterSPCFw)
+    for count, t in enumerate(sr.t, start=1):
+        cc0 = 10 * get_position(sr, t)
+        cc = cc0 - L * np.floor(cc0 / L)
+        f.write("MODEL".ljust(10) + str(count) + "\n")
+        if water:
+            for i in range(n):
+                o = 3 * i
+                cc[:, o + 1] = cc[:, o] + cc0[:, o + 1] - cc0[:, o]
+                cc[:, o + 2] = cc[:, o] + cc0[:, o + 2] - cc0[:, o]
+            f.write(f"REMARK 250 time={_julia_float(t)} picoseconds\n")
+            for i in range(n):
+                o = 3 * i
+                f.write(_hetatm(o + 1, "O", "HOH", i + 1, cc[:, o], "O") + "\n")
+                f.write(_hetatm(o + 2, "H1", "HOH", i + 1, cc[:, o + 1], "H") + "\n")
+                f.write(_hetatm(o + 3, "H2", "HOH", i + 1, cc[:, o + 2], "H") + "\n")
+        else:
+            f.write(f"REMARK 250 time={_julia_float(t)} steps\n")
+            for i in range(n):
+                f.write(_hetatm(i + 1, "Ar", "Ar", i + 1, cc[:, i], "Ar") + "\n")
+        f.write("ENDMDL\n")
+
+
+def save_to_pdb(sr: SimulationResult, path):
+    """save_to_pdb(result, path): :881-885."""
+    with open(path, "w") as f:
+        write_pdb_data(f, sr)
+
+
+def extract_from_pdb(file):
+    """extract_from_pdb(io): :912-1001.  Reads the first two MODELs of a water trajectory; the molecules get the
+    positions of the FIRST frame (Angstrom / 10) and zero velocities (the finite-difference velocities the reference
+    computes are overwritten by zeros at :992-994), masses 15.999 / 1.00794."""
+    lines = iter(file.read().split("\n")) if hasattr(file, "read") else iter(file)
+
+    def frame():
+        for ln in lines:
+            if ln[:5] == "MODEL":
+                break
+        else:
+            return None, None
+        parts = next(lines).split()
+        t = float(parts[2][5:])
+        cc = []
+        for ln in lines:
+            if ln[:6] == "ENDMDL":
+                break
+            if len(ln) > 13 and ln[13] == "O":
+                rows = [ln, next(lines), next(lines)]
+                for row in rows:
+                    ps = row.split()
+                    cc.append(np.array([float(ps[5]), float(ps[6]), float(ps[7])]) / 10)
+        return t, cc
+
+    _, cc1 = frame()
+    _, cc2 = frame()
+    if cc1 is None or cc2 is None:
+        raise ValueError("a PDB trajectory with at least two MODEL records is required")
+    zero = np.zeros(3)
+    wms = []
+    for m in range(len(cc2) // 3):
+        wms.append(WaterMolecule(MassBody(cc1[3 * m], zero, 15.999), MassBody(cc1[3 * m + 1], zero, 1.00794),
+                                 MassBody(cc1[3 * m + 2], zero, 1.00794)))
+    return wms
+
+
+def load_water_molecules_from_pdb(path):
+    """load_water_molecules_from_pdb(path): :906-910."""
+    with open(path) as f:
+        return extract_from_pdb(f)
+
+
 def run_simulation(s: NBodySimulation, alg=None, *, dt: Optional[float] = None, saveat: Optional[int] = None,
                    save_everystep: Optional[bool] = None, device: int = 0, seed: int = 0, rtol=1e-6, atol=1e-9):
     """nbody_simulation_result.jl:468-492.  Langevin thermostats run the SDE path (EM), everything else

@@ -126,3 +126,93 @@ def test_cell_node_lattice_matches_reference_rule():
     assert pos.shape == (3, 10)
     assert np.allclose(pos[:, 0], [0.5, 0.5, 0.5]) and np.allclose(pos[:, 1], [0.5, 0.5, 1.5])
     assert np.allclose(pos[:, 3], [0.5, 1.5, 0.5]) and np.allclose(pos[:, 9], [1.5, 0.5, 0.5])
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory text: the PDB writer / loader of the reference-shaped host API (no device involved)
+# ------------------------------------------------------------------------------------------------
+# The fixture of test/water_test.jl:196-219 (the reference's own known-answer input for extract_from_pdb).
+_PDB_FIXTURE = """MODEL     1
+REMARK 250 time=0.0000 picoseconds
+HETATM    1  O   HOH     1      18.642  18.642   0.000  1.00  0.00
+HETATM    2  H1  HOH     1      17.685  18.642   0.000  1.00  0.00
+HETATM    3  H2  HOH     1      18.882  17.715   0.000  1.00  0.00
+HETATM    4  O   HOH     2       0.000   0.000   3.107  1.00  0.00
+HETATM    5  H1  HOH     2       0.957   0.000   3.107  1.00  0.00
+HETATM    6  H2  HOH     2      -0.240   0.927   3.107  1.00  0.00
+HETATM    7  O   HOH     3      18.642  18.642   6.214  1.00  0.00
+HETATM    8  H1  HOH     3      17.685  18.642   6.214  1.00  0.00
+HETATM    9  H2  HOH     3      18.882  17.715   6.214  1.00  0.00
+ENDMDL
+MODEL     2
+REMARK 250 time=0.0005 picoseconds
+HETATM    1  O   HOH     1      18.642  18.642  -0.000  1.00  0.00
+HETATM    2  H1  HOH     1      17.685  18.642   0.000  1.00  0.00
+HETATM    3  H2  HOH     1      18.882  17.715   0.000  1.00  0.00
+HETATM    4  O   HOH     2      -0.000  -0.000   3.107  1.00  0.00
+HETATM    5  H1  HOH     2       0.958  -0.000   3.107  1.00  0.00
+HETATM    6  H2  HOH     2      -0.240   0.928   3.107  1.00  0.00
+HETATM    7  O   HOH     3      18.642  18.642   6.214  1.00  0.00
+HETATM    8  H1  HOH     3      17.685  18.642   6.214  1.00  0.00
+HETATM    9  H2  HOH     3      18.881  17.715   6.214  1.00  0.00
+ENDMDL"""
+
+
+def test_extract_from_pdb_known_answers():
+    """test/water_test.jl:195-248: positions of the first frame / 10, zero velocities."""
+    import io
+
+    from nbody_b200.api import extract_from_pdb
+
+    bodies = extract_from_pdb(io.StringIO(_PDB_FIXTURE))
+    eps = 0.00005
+    assert len(bodies) == 3
+    assert np.allclose(bodies[0].O.r, [1.8642, 1.8642, 0.0], atol=eps)
+    assert np.allclose(bodies[1].H1.r, [0.0957, 0.0, 0.3107], atol=eps)
+    assert np.allclose(bodies[2].H2.r, [1.8882, 1.7715, 0.6214], atol=eps)
+    assert not np.any(bodies[2].H2.v) and bodies[0].O.m == 15.999 and bodies[0].H1.m == 1.00794
+
+
+def test_pdb_writer_layout_and_round_trip():
+    """write_pdb_data (src/nbody_simulation_result.jl:792-865): one MODEL / REMARK 250 / ENDMDL per saved time, one
+    HETATM per atom (test/lennard_jones_test.jl:99-117, test/water_test.jl:173-192), fixed columns, coordinates in
+    Angstrom wrapped into the box with molecules kept whole; the loader reads the writer's output back."""
+    import io
+
+    from nbody_b200.api import (CubicPeriodicBoundaryConditions, ElectrostaticParameters, LennardJonesParameters, MassBody,
+                                NBodySimulation, PotentialNBodySystem, SimulationResult, SPCFwParameters, WaterSPCFw,
+                                extract_from_pdb, write_pdb_data)
+
+    L = 1.5
+    pbc = CubicPeriodicBoundaryConditions(L)
+    atoms = [MassBody([0.1, 0.2, 0.3], [0, 0, 0], 1.0), MassBody([1.6, -0.1, 0.7], [0, 0, 0], 1.0)]
+    sim = NBodySimulation(PotentialNBodySystem(atoms, {"lennard_jones": LennardJonesParameters(1.0, 0.3, 0.7)}), (0.0, 1.0), pbc, 1.0)
+    frames = [np.asfortranarray([[0.1, 1.6], [0.2, -0.1], [0.3, 0.7]]), np.asfortranarray([[0.15, 1.7], [0.2, -0.2], [0.3, 0.7]])]
+    sr = SimulationResult(sim, [0.0, 5e-5], frames, [np.zeros((3, 2))] * 2, 1)
+    out = io.StringIO()
+    write_pdb_data(out, sr)
+    lines = out.getvalue().split("\n")
+    assert sum(ln.startswith("REMARK 250") for ln in lines) == 2 and sum(ln.startswith("HETATM") for ln in lines) == 4
+    assert lines[0] == "MODEL     1" and lines[1] == "REMARK 250 time=0.0 steps" and lines[6] == "REMARK 250 time=5.0e-5 steps"
+    assert lines[2] == "HETATM    1  Ar  Ar     1       1.000   2.000   3.000  1.00  0.00          Ar"
+    assert lines[3] == "HETATM    2  Ar  Ar     2       1.000  14.000   7.000  1.00  0.00          Ar"  # wrapped into [0, 15)
+
+    mols = [MassBody([1.45, 0.5, 0.5], [0, 0, 0], 18.0), MassBody([0.2, 0.9, 1.2], [0, 0, 0], 18.0)]
+    water = WaterSPCFw(mols, 1.00794, 15.999, 0.41, -0.82, LennardJonesParameters(0.65, 0.3165, 0.7),
+                       ElectrostaticParameters(138.9, 0.7), SPCFwParameters(0.1012, 1.976, 443153.0, 317.5))
+    wsim = NBodySimulation(water, (0.0, 1.0), pbc, 1.0)
+    from nbody_b200.api import gather_bodies_initial_coordinates
+
+    u0, v0, _ = gather_bodies_initial_coordinates(wsim)
+    wsr = SimulationResult(wsim, [0.0, 0.0005], [u0, u0 + 0.001], [v0, v0], 1)
+    out = io.StringIO()
+    write_pdb_data(out, wsr)
+    text = out.getvalue()
+    assert text.count("HETATM") == 12 and text.count("picoseconds") == 2
+    first = text.split("\n")[2]
+    assert first == "HETATM    1  O   HOH     1      14.500   5.000   5.000  1.00  0.00           O"
+    back = extract_from_pdb(io.StringIO(text))
+    assert len(back) == 2
+    # H1 of molecule 1 sits at x = 1.45 + 0.1012 = 1.5512 > L: written next to its oxygen (15.512 A), not wrapped away from it
+    assert np.allclose(back[0].H1.r, [1.5512, 0.5, 0.5], atol=5e-4) and np.allclose(back[0].O.r, [1.45, 0.5, 0.5], atol=5e-4)
+    assert np.allclose(back[1].O.r, u0[:, 3], atol=5e-4)
