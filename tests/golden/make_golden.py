@@ -39,11 +39,18 @@ def spec_system(spec, arrays):
                       dipole=spec.get("dipole"), spcfw=spec.get("spcfw"), thermostat=spec.get("thermostat"))
 
 
-def emit(name, spec, arrays, neighbors_R=None, idx_stride=1):
+def emit(name, spec, arrays, neighbors_R=None, idx_stride=1, analysis=False):
     s = spec_system(spec, arrays)
     u, v = arrays["u"], arrays["v"].copy(order="F")
     out = dict(arrays)
     out["dv"] = s.rhs(u, v)
+    if analysis:  # rdf pair histogram of the frame (src/nbody_simulation_result.jl:676-693) and msd against a second frame
+        L = spec["bc"][1]
+        out["rdf_hist"] = orc.rdf_hist(u, L, idx_stride=3 if spec.get("water") else 1)
+        u1 = F(u + 0.02 * L * np.random.Generator(np.random.Philox(7)).standard_normal(u.shape))
+        out["u1"] = u1
+        w = arrays["ms"]
+        out["msd"] = np.array(orc.msd(u1, u, water=bool(spec.get("water")), mO=w[0], mH=w[1] if len(w) > 1 else 0.0))
     out["v_after"] = v  # Nose-Hoover writes v[zeta_ind] (src/thermostats.jl:126)
     if neighbors_R is not None:
         n = len(arrays["ms"])
@@ -79,7 +86,7 @@ def main():
     x = w["u"] + 0.05 * rng.standard_normal(w["u"].shape) + w["L"] * rng.integers(-2, 3, size=w["u"].shape)
     emit("lj_argon_reduced_500_berendsen",
          dict(bc=["cubic", w["L"]], lj=w["lj"], thermostat=dict(kind="berendsen", T=90.0, tau=10 * w["dt"], kB=w["kB"])),
-         dict(u=F(x), v=w["v"], ms=w["ms"]), neighbors_R=w["lj"]["R"])
+         dict(u=F(x), v=w["v"], ms=w["ms"]), neighbors_R=w["lj"]["R"], analysis=True)
 
     # 5. PeriodicBoundaryConditions is NOT a minimum image (src/boundary_conditions.jl:111-136): 64 atoms
     n, L = 64, 4.0
@@ -99,7 +106,7 @@ def main():
     x = F(w["u"] + 0.005 * rng.standard_normal(w["u"].shape))
     lj = dict(w["lj"]); lj["R"] = 0.45
     emit("water_spcfw_27", dict(bc=["cubic", w["L"]], water=True, lj=lj, coulomb=w["coulomb"], spcfw=w["spcfw"]),
-         dict(u=x, v=w["v"], ms=w["ms"], qs=w["qs"]))
+         dict(u=x, v=w["v"], ms=w["ms"], qs=w["qs"]), analysis=True)
 
     # 9. Nose-Hoover: the state carries one extra column (src/nbody_to_ode.jl:6-8, src/thermostats.jl:121-128)
     w = wl.fcc_argon_reduced(3)

@@ -52,3 +52,19 @@ def test_golden_neighbor_lists_match_the_predicate(name):
         ri = [u[k, i] for k in range(3)]
         mine = [j for j in range(n) if j != i and onp.distance(ri, [u[k, j] for k in range(3)], spec["bc"])[2] < R2]
         assert mine == lst[off[i]:off[i + 1]].tolist()
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c in ("lj_argon_reduced_500_berendsen", "water_spcfw_27")])
+def test_golden_rdf_and_msd(name):
+    """rdf pair histogram and msd of the golden frames: the C oracle reproduces them bit for bit, and so does the
+    pure-Python restatement (histogram; atomic msd)."""
+    orc.build()
+    spec, z = load(name)
+    water = bool(spec.get("water"))
+    L = spec["bc"][1]
+    assert np.array_equal(orc.rdf_hist(z["u"], L, idx_stride=3 if water else 1), z["rdf_hist"])
+    assert np.array_equal(np.array(onp.rdf_hist(z["u"], L, idx_stride=3 if water else 1)), z["rdf_hist"])
+    ms = spec["ms"]
+    assert orc.msd(z["u1"], z["u"], water=water, mO=ms[0], mH=ms[1]) == float(z["msd"])
+    if not water:
+        assert onp.msd(z["u1"], z["u"]) == float(z["msd"])

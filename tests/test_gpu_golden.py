@@ -22,6 +22,12 @@ def test_cuda_path_reproduces_golden(name):
     if "nosehoover" in name:
         assert not a[:, n].any()
         assert v[0, n] == pytest.approx(z["v_after"][0, n], rel=1e-13)
+    if "rdf_hist" in z:  # frame analysis: integer histogram count for count, msd to rounding
+        ctx.rdf_reset(1000)
+        ctx.rdf_add(z["u"])
+        hist, frames = ctx.rdf_get()
+        assert frames == 1 and np.array_equal(hist, z["rdf_hist"])
+        assert ctx.msd(z["u"], z["u1"]) == pytest.approx(float(z["msd"]), rel=1e-13)
     if "offsets" in z:
         ctx.upload(z["u"], z["v"])
         off, lst = ctx.neighbors()
