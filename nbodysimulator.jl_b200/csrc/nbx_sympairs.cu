@@ -119,6 +119,21 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     uint32_t parity = 0;
 
     const int nitems = p.NT * p.S;
+    auto kof = [&](int m) { return p.kr0 + m * p.kstride; };
+    // B tile of (tile A, local offset index m) -> stage st
+    auto issue = [&](int A, int m, int st) {
+        const int B0 = ((A + kof(m)) % p.NT) * TS;
+        double *dst = ring + (size_t)st * 4 * TS;
+        mbar_expect_tx(&full[st], STAGE_BYTES);
+        bulk_g2s(dst, p.x + B0, TS * sizeof(double), &full[st]);
+        bulk_g2s(dst + TS, p.y + B0, TS * sizeof(double), &full[st]);
+        bulk_g2s(dst + 2 * TS, p.z + B0, TS * sizeof(double), &full[st]);
+        bulk_g2s(dst + 3 * TS, p.w + B0, TS * sizeof(double), &full[st]);
+    };
+    auto next_live = [&](int A, int m, int mend) { while (m < mend && !sym_live(kof(m), A, p.NT, p.K)) ++m; return m; };
+    int st = 0;              // ring stage of the next tile: runs on across items
+    bool have_first = false; // the previous item already issued this item's first tile (a short segment must not
+                             // expose the copy latency once per item: multi-GPU shares have two offsets per segment)
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int A = item / p.S, seg = item - A * p.S;
         const int m0 = seg * p.seg_len;
@@ -134,24 +149,25 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             fx[t] = fy[t] = fz[t] = 0.0;
         }
 
-        auto kof = [&](int m) { return p.kr0 + m * p.kstride; };
-        auto issue = [&](int m, int st) {
-            const int B0 = ((A + kof(m)) % p.NT) * TS;
-            double *dst = ring + (size_t)st * 4 * TS;
-            mbar_expect_tx(&full[st], STAGE_BYTES);
-            bulk_g2s(dst, p.x + B0, TS * sizeof(double), &full[st]);
-            bulk_g2s(dst + TS, p.y + B0, TS * sizeof(double), &full[st]);
-            bulk_g2s(dst + 2 * TS, p.z + B0, TS * sizeof(double), &full[st]);
-            bulk_g2s(dst + 3 * TS, p.w + B0, TS * sizeof(double), &full[st]);
-        };
-        auto next_live = [&](int m) { while (m < m1 && !sym_live(kof(m), A, p.NT, p.K)) ++m; return m; };
-
-        int m = next_live(m0);
-        int st = 0;
-        if (tid == 0 && m < m1) issue(m, 0);
+        int m = next_live(A, m0, m1);
+        if (!have_first && tid == 0 && m < m1) issue(A, m, st);
+        have_first = false;
         while (m < m1) {
-            const int mn = next_live(m + 1);
-            if (tid == 0 && mn < m1) issue(mn, st ^ 1); // stage st^1 was released by the barrier that ended the previous block
+            const int mn = next_live(A, m + 1, m1);
+            if (mn < m1) {
+                if (tid == 0) issue(A, mn, st ^ 1); // stage st^1 was released by the barrier that ended the previous block
+            } else {
+                const int item2 = item + gridDim.x; // last tile of this item: fetch the first tile of the next one meanwhile
+                if (item2 < nitems) {
+                    const int A2 = item2 / p.S, seg2 = item2 - A2 * p.S;
+                    const int e2 = min((seg2 + 1) * p.seg_len, p.M);
+                    const int m2 = next_live(A2, seg2 * p.seg_len, e2);
+                    if (m2 < e2) {
+                        if (tid == 0) issue(A2, m2, st ^ 1);
+                        have_first = true;
+                    }
+                }
+            }
             mbar_wait(&full[st], (parity >> st) & 1u);
             parity ^= 1u << st;
             const double *bsx = ring + (size_t)st * 4 * TS, *bsy = bsx + TS, *bsz = bsy + TS, *bsw = bsz + TS;

@@ -37,3 +37,22 @@ for uniform in (True, False):
     ms_k, cnt = ctx.timing_get(_lib.T_PAIR_ALLPAIRS)
     print(f"uniform={uniform} ordered kernel_ms={ms_k / cnt:.3f}")
     ctx.close()
+
+# one rank's share under pair sharding (ring offsets k = rank mod world), timed on this device
+for world in (1, 2, 4, 8):
+    ctx = _lib.Context(0)
+    ctx.system(ms)
+    ctx.add_gravity(1.0)
+    ctx.upload(u, v)
+    if world > 1:
+        ctx.shard_pairs(0, world)
+    ctx.vv_begin(0.0)
+    ctx.vv_forces()
+    ctx.timing_reset(); ctx.timing_enable(True)
+    for _ in range(3):
+        ctx.vv_forces()
+    ms_k, cnt = ctx.timing_get(_lib.T_PAIR_ALLPAIRS)
+    ctx.timing_enable(False)
+    ideal = 42.7 * ((0.83 + (128 // world - 1) + 0.5) / 128.33 if world > 1 else 1.0)
+    print(f"rank 0 of {world}: kernel_ms={ms_k / cnt:.3f} segs={ctx.info('allpairs_chunks')} (share of the offsets x 42.7 ms = {ideal:.3f})", flush=True)
+    ctx.close()
