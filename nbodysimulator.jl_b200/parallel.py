@@ -286,6 +286,49 @@ class ShardedStepper:
                 self.dist.all_reduce(s[0:1], op=self.dist.ReduceOp.SUM, group=self.group)
 
 
+class RebuildSchedule:
+    """When do the slabs rebuild their Verlet lists?  Pure host logic (no device, no process group), so it is tested on
+    the CPU (tests/test_parallel_gloo.py).
+
+    Every step k takes a displacement check (soft flag: beyond SOFT x skin/2; hard flag: beyond skin/2 or a list
+    overflow), reduced over all ranks.  The decision for step k reads the flags of step k - lag, so the host never
+    waits for the step it is enqueuing; every rank reads the same reduced flags of the same step, hence all decide
+    alike.  A soft flag taken at or before the last rebuild compares against lists that no longer exist and is ignored.
+    A hard flag of ANY step that did not itself rebuild means forces were computed from a list that was no longer a
+    superset: that raises instead of going unnoticed (the check of a rebuild step precedes the rebuild and is moot)."""
+
+    def __init__(self, lag: int = 2):
+        self.lag = lag
+        self.k = 0               # the step being enqueued
+        self.last_rebuild = -1
+        self.rebuilds = 0
+        self.force = False       # rebuild at the next step whatever the flags say
+        self._recent = []        # the rebuild steps that checks still in flight can refer to
+
+    def due(self, flags_of) -> bool:
+        """flags_of(j) -> (soft, hard) of the check taken at step j (may block until they have arrived)."""
+        want = self.force
+        j = self.k - self.lag
+        if j >= 0 and j not in self._recent:
+            soft, hard = flags_of(j)
+            if j <= self.last_rebuild:
+                soft = 0  # measured against lists that have been replaced since
+            if hard:
+                raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last "
+                                   "rebuild (or a list overflowed) before the collective rebuild could happen; use a larger "
+                                   "verlet_skin_permille, a smaller time step, or verlet_skin_permille = 0")
+            want = want or bool(soft)
+        return want
+
+    def advance(self, rebuilt: bool):
+        if rebuilt:
+            self.last_rebuild = self.k
+            self.force = False
+            self.rebuilds += 1
+            self._recent = [r for r in self._recent if r >= self.k - self.lag] + [self.k]
+        self.k += 1
+
+
 class SlabStepper:
     """Velocity Verlet of a cutoff system over x-slabs, one rank per slab (see the module docstring).
 
@@ -294,7 +337,11 @@ class SlabStepper:
     slab_buffers() -> 4 flat tensors, slab_pack(), slab_unpack() -> counts, slab_download().
     """
 
-    def __init__(self, engine, group=None, direct=True):
+    def __init__(self, engine, group=None, direct=True, soft=None):
+        """soft: fraction of skin/2 at which a collective rebuild is requested (default SOFT = 0.75).  The request is read
+        LAG steps late, so the fastest particle must not cover the remaining (1 - soft) x skin/2 within LAG + 1 steps:
+        hot systems or long time steps want a smaller value (more frequent rebuilds); violations raise, they are never
+        silent."""
         import torch.distributed as dist
 
         self.dist = dist
@@ -318,10 +365,8 @@ class SlabStepper:
         # for those steps.  A hard flag (beyond skin/2, or a list overflow) that was not covered by a rebuild raises.
         self.verlet = bool(hasattr(engine, "slab_verlet") and engine.slab_verlet())
         self.merged = False
-        self.k = 0
-        self.last_rebuild = -1
-        self.rebuilds = 0
-        self.force_rebuild = False
+        self.soft = float(self.SOFT if soft is None else soft)
+        self.sched = RebuildSchedule(self.LAG)
         if self.verlet:
             import torch
 
@@ -353,13 +398,17 @@ class SlabStepper:
 
     LAG, SLOTS, SOFT = 2, 8, 0.75
 
+    @property
+    def rebuilds(self):
+        return self.sched.rebuilds
+
     def _peer(self, r):
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
     def _rebuild_wanted(self):
         """Enqueue this step's displacement check (+ max over the ranks) and return the decision for THIS step from the
         check of LAG steps ago.  Identical on every rank: all read the same reduced flags of the same step."""
-        e, k = self.engine, self.k
+        e, k = self.engine, self.sched.k
         slot = k % self.SLOTS
         if self.merged:  # the position update and the check were enqueued by slab_step_begin
             if self.world > 1:
@@ -371,25 +420,20 @@ class SlabStepper:
         else:
             buf = self._flags_dev[slot]
             buf.zero_()
-            e.slab_verlet_check(buf, self.SOFT)
+            e.slab_verlet_check(buf, self.soft)
             if self.world > 1:
                 self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
             host = self._np_i
             self._host_i[slot].copy_(buf, non_blocking=True)
         self._events[slot].record(self._stream)
-        want = self.force_rebuild
-        j = k - self.LAG
-        if j >= 0 and j > self.last_rebuild:  # a check against the lists that are in use
+
+        def flags_of(j):
             jj = j % self.SLOTS
             if not self._events[jj].query():
                 self._events[jj].synchronize()
-            soft, hard = int(host[jj, 0]), int(host[jj, 1])
-            if hard:
-                raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last "
-                                   "rebuild (or a list overflowed) before the collective rebuild could happen; use a larger "
-                                   "verlet_skin_permille, a smaller time step, or verlet_skin_permille = 0")
-            want = want or bool(soft)
-        return want
+            return int(host[jj, 0]), int(host[jj, 1])
+
+        return self.sched.due(flags_of)
 
     def _exchange(self):
         """send-to-left -> the left neighbour's recv-from-right, send-to-right -> the right neighbour's
@@ -409,7 +453,7 @@ class SlabStepper:
     def _one_step(self, dt):
         e = self.engine
         if self.merged:
-            e.slab_step_begin(dt, self.SOFT)
+            e.slab_step_begin(dt, self.soft)
             if self._rebuild_wanted():
                 e.slab_pack()           # migration round, then the halo round that is remembered (see below)
                 self._exchange()
@@ -419,15 +463,14 @@ class SlabStepper:
                 self._exchange()
                 e.slab_unpack(sync=False)
                 e.slab_mark("slab_rebuild")
-                self.last_rebuild = self.k
-                self.force_rebuild = False
-                self.rebuilds += 1
                 e.slab_step_end(dt, False)
+                self.sched.advance(True)
             else:
                 e.slab_step_end(dt, True)
-            self.k += 1
+                self.sched.advance(False)
             return
         e.vv_begin(dt)
+        rebuilt = False
         if self.verlet and not self._rebuild_wanted():
             e.slab_refresh_send()       # nothing migrates, nothing is renumbered: only the halo positions travel
             self._exchange()
@@ -442,10 +485,8 @@ class SlabStepper:
                 self._exchange()
                 e.slab_unpack(sync=False)
                 e.slab_mark("slab_rebuild")
-                self.last_rebuild = self.k
-                self.force_rebuild = False
-                self.rebuilds += 1
-        self.k += 1
+                rebuilt = True
+        self.sched.advance(rebuilt)
         e.vv_forces()
         e.vv_finish(dt)
         if e.needs_temperature and self.world > 1:

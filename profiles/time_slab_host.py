@@ -44,16 +44,16 @@ torch.cuda.synchronize()
 acc = {"begin": 0.0, "decide": 0.0, "end": 0.0}
 m = 200
 for _ in range(m):
-    a = time.perf_counter(); eng.slab_step_begin(w["dt"], st.SOFT)
+    a = time.perf_counter(); eng.slab_step_begin(w["dt"], st.soft)
     b = time.perf_counter(); want = st._rebuild_wanted()
     c = time.perf_counter()
     if want:
         eng.slab_pack(); eng.slab_unpack(sync=False); eng.slab_mark("slab_record_halo"); eng.slab_pack(); eng.slab_unpack(sync=False)
-        eng.slab_mark("slab_rebuild"); st.last_rebuild = st.k; st.rebuilds += 1
+        eng.slab_mark("slab_rebuild")
         eng.slab_step_end(w["dt"], False)
     else:
         eng.slab_step_end(w["dt"], True)
-    st.k += 1
+    st.sched.advance(want)
     d = time.perf_counter()
     acc["begin"] += b - a; acc["decide"] += c - b; acc["end"] += d - c
     if _ % 4 == 3:

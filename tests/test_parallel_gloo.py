@@ -23,6 +23,55 @@ def test_partition_tiles_the_range():
             assert lo % m == 0 and (hi % m == 0 or hi == n) and hi - lo <= per
 
 
+def test_rebuild_schedule_of_the_slab_verlet_lists():
+    """parallel.RebuildSchedule: decisions come `lag` steps late, flags taken against lists that were rebuilt since are
+    ignored, and a hard flag that no rebuild covered raises."""
+    from nbody_b200.parallel import RebuildSchedule
+
+    flags = {}
+    asked = []
+
+    def flags_of(j):
+        asked.append(j)
+        return flags.get(j, (0, 0))
+
+    s = RebuildSchedule(lag=2)
+    rebuilt_at = []
+    flags[5] = (1, 0)           # at step 5 some particle passed the soft limit
+    flags[6] = (1, 0)           # ... and of course still has at 6 and 7: those checks must not trigger again
+    flags[7] = (1, 1)           # by step 7 it is even past skin/2 relative to the OLD lists -- which step 7 replaced
+    for k in range(14):
+        assert s.k == k
+        due = s.due(flags_of)
+        if due:
+            rebuilt_at.append(k)
+        s.advance(due)
+    assert rebuilt_at == [7]                       # read two steps late; the soft flag of step 6 does not trigger again
+    assert asked == [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11]  # step 7's check preceded its own rebuild: moot
+    assert s.rebuilds == 1 and s.last_rebuild == 7
+
+    s = RebuildSchedule(lag=2)
+    flags.clear()
+    flags[5] = (1, 0)
+    flags[6] = (1, 1)           # step 6 still ran on the old lists and was already past skin/2: must not go unnoticed
+    with pytest.raises(RuntimeError, match="step 6"):
+        for k in range(12):
+            s.advance(s.due(flags_of))
+
+    s = RebuildSchedule(lag=2)
+    s.force = True
+    assert s.due(flags_of) and not s.force is False
+    s.advance(True)
+    assert not s.force and s.last_rebuild == 0
+
+    s = RebuildSchedule(lag=2)
+    flags.clear()
+    flags[3] = (1, 1)           # past skin/2 at a step whose forces came from the lists: not recoverable
+    with pytest.raises(RuntimeError, match="skin/2"):
+        for k in range(8):
+            s.advance(s.due(flags_of))
+
+
 class NumpyEngine:
     """Same duck type as parallel.CudaEngine, on host memory.  targets mode: forces from the CPU oracle;
     pairs mode: this rank's share of the unordered pairs {i, j} ((i + j) % world == rank), partial
