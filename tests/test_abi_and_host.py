@@ -216,3 +216,37 @@ def test_pdb_writer_layout_and_round_trip():
     # H1 of molecule 1 sits at x = 1.45 + 0.1012 = 1.5512 > L: written next to its oxygen (15.512 A), not wrapped away from it
     assert np.allclose(back[0].H1.r, [1.5512, 0.5, 0.5], atol=5e-4) and np.allclose(back[0].O.r, [1.45, 0.5, 0.5], atol=5e-4)
     assert np.allclose(back[1].O.r, u0[:, 3], atol=5e-4)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores only (the CPU restatement of the reference's loop): one JSON line
+    with the keys the driver reads, here with one short step."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "pair-interactions/s" and d["value"] > 1e7
+    assert d["config"]["workload"] == "gravity_plummer_262144" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_bench_own_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback anywhere: without a CUDA device the bench's own arm exits with an error instead of timing
+    something else."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
