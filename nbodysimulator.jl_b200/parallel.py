@@ -378,20 +378,25 @@ class SlabStepper:
             engine.slab_prime()
 
             dev = engine.device
+            cuda = dev.type == "cuda"  # (a host engine -- the gloo tests -- needs neither pinned memory nor events)
             self._flags_dev = torch.zeros((self.SLOTS, 2), dtype=torch.int32, device=dev)
-            self._flags_host = torch.zeros((self.SLOTS, 2), dtype=torch.int32).pin_memory()
-            self._events = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            self._flags_host = torch.zeros((self.SLOTS, 2), dtype=torch.int32)
+            if cuda:
+                self._flags_host = self._flags_host.pin_memory()
+            self._events = [torch.cuda.Event() for _ in range(self.SLOTS)] if cuda else None
             # merged mode (engines with slab_step_begin / slab_step_end, direct exchange or a single slab): two library
             # calls and ONE collective per step -- the sum over the ranks of [sum m v^2, soft flag, hard flag]
-            self.merged = bool(hasattr(engine, "slab_step_begin") and (self.direct or self.world == 1))
-            self._flags_host_d = torch.zeros((self.SLOTS, 2), dtype=torch.float64).pin_memory()
+            self.merged = bool(cuda and hasattr(engine, "slab_step_begin") and (self.direct or self.world == 1))
+            self._flags_host_d = torch.zeros((self.SLOTS, 2), dtype=torch.float64)
+            if cuda:
+                self._flags_host_d = self._flags_host_d.pin_memory()
             self._T_pending = False  # slot 12 holds a local sum that has not been added over the ranks yet
             # views made once: slicing tensors every step costs more host time than the kernels they feed
             self._host_i = [self._flags_host[k] for k in range(self.SLOTS)]
             self._host_d = [self._flags_host_d[k] for k in range(self.SLOTS)]
             self._np_i = self._flags_host.numpy()
             self._np_d = self._flags_host_d.numpy()
-            self._stream = torch.cuda.current_stream(dev)
+            self._stream = torch.cuda.current_stream(dev) if cuda else None
             if self.merged:
                 s = engine.scalars()
                 self._s_flags, self._s_all = s[13:15], s[12:15]
@@ -425,11 +430,12 @@ class SlabStepper:
                 self.dist.all_reduce(buf, op=self.dist.ReduceOp.MAX, group=self.group)
             host = self._np_i
             self._host_i[slot].copy_(buf, non_blocking=True)
-        self._events[slot].record(self._stream)
+        if self._events:
+            self._events[slot].record(self._stream)
 
         def flags_of(j):
             jj = j % self.SLOTS
-            if not self._events[jj].query():
+            if self._events and not self._events[jj].query():
                 self._events[jj].synchronize()
             return int(host[jj, 0]), int(host[jj, 1])
 

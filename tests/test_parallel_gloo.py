@@ -375,6 +375,143 @@ class NumpySlabEngine:
         return self.gid.copy(), self.pos.copy(), self.vel.copy(), self.acc.copy()
 
 
+class NumpyVerletSlabEngine(NumpySlabEngine):
+    """The Verlet-list slab protocol of csrc/nbx_slab.cu on the host: between collective rebuilds the own set and its
+    numbering stay put and only the positions of the halo particles recorded at the rebuild travel; a rebuild is a
+    migration round followed by a halo round that is remembered.  Forces are the oracle's over own + ghosts, i.e. exact
+    as long as the ghost set recorded with the skin still covers everything within the cutoff -- which is what the
+    displacement flags and the collective, lagged rebuild schedule of parallel.SlabStepper have to guarantee."""
+
+    def __init__(self, w, u, v, thermostat=None, skin=0.2):
+        super().__init__(w, u, v, thermostat)
+        self.skin = skin
+        self.nc = int(np.floor(self.L / ((self.R + skin) * (1 + 1e-6))))  # layers of edge >= R + skin
+        self.device = self.torch.device("cpu")
+        self.marks = set()
+        self.ref = None
+        self.halo_idx = [np.zeros(0, dtype=int), np.zeros(0, dtype=int)]
+        self.refreshes = 0
+
+    def slab_verlet(self):
+        return True
+
+    def slab_mark(self, key):
+        self.marks.add(key)
+
+    def _pack(self, init):
+        record = "slab_record_halo" in self.marks
+        self.marks.discard("slab_record_halo")
+        if record:  # where the halo members will sit after the (order-preserving) compaction
+            rel = (self._layer(self.pos[0]) - self.c0) % self.nc
+            stay = rel < (self.c1 - self.c0)
+            new_index = np.cumsum(stay) - 1
+            self.halo_idx = [new_index[stay & (rel == 0)], new_index[stay & (rel == self.c1 - self.c0 - 1)]]
+        super()._pack(init)
+
+    def slab_prime(self):
+        self.ref = self.pos.copy()
+
+    def vv_forces(self):
+        if "slab_rebuild" in self.marks:
+            self.marks.discard("slab_rebuild")
+            self.ref = self.pos.copy()
+        super().vv_forces()
+
+    def slab_verlet_check(self, flags, soft_fraction=0.75):
+        f = flags.numpy()
+        if self.ref is None or self.ref.shape != self.pos.shape:
+            f[0] = 1
+            return
+        lim = 0.5 * self.skin * (1.0 - 1e-9)
+        d2 = ((self.pos - self.ref) ** 2).sum(axis=0)
+        if not (d2 <= (lim * soft_fraction) ** 2).all():
+            f[0] = 1
+        if not (d2 <= lim ** 2).all():
+            f[1] = 1
+
+    def slab_refresh_send(self):
+        self.refreshes += 1
+        for buf, idx in zip(self.bufs[:2], self.halo_idx):
+            hrec = np.concatenate([self.gid[idx][None].astype(float), self.pos[:, idx]]).T.ravel()
+            out = np.concatenate([[0, idx.size], hrec])
+            buf.zero_()
+            buf[:out.size] = self.torch.from_numpy(out)
+
+    def slab_refresh_recv(self):
+        pos, gids = [], []
+        for buf in (self.bufs[2], self.bufs[3]):
+            b = buf.numpy()
+            assert int(b[0]) == 0
+            nh = int(b[1])
+            hrec = b[2:2 + nh * self.HALO].reshape(nh, self.HALO).T
+            gids.append(hrec[0].astype(int))
+            pos.append(hrec[1:4])
+        assert np.array_equal(np.concatenate(gids), self.ghost_gid), "the halo changed without a collective rebuild"
+        self.ghost_pos = np.concatenate(pos, axis=1)
+
+
+def _verlet_slab_worker(rank, world, port, out_dir, thermo):
+    import torch.distributed as dist
+
+    from nbody_b200.parallel import SlabStepper
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    w, u, v, th, dt, steps = _verlet_slab_setup(thermo)
+    eng = NumpyVerletSlabEngine(w, u, v, th, skin=0.2)
+    st = SlabStepper(eng, soft=0.5)
+    assert st.verlet and not st.merged
+    rebuilt_at = []
+    for k in range(steps):
+        before = st.rebuilds
+        st.step(dt, 1)
+        if st.rebuilds > before:
+            rebuilt_at.append(k)
+    ug, vg, ag = st.gather(u.shape[1])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "u.npy"), ug)
+        np.save(os.path.join(out_dir, "v.npy"), vg)
+    np.save(os.path.join(out_dir, f"rebuilt{rank}.npy"), np.array(rebuilt_at))
+    np.save(os.path.join(out_dir, f"stat{rank}.npy"), np.array([eng.refreshes, st.counts[0], st.counts[1]]))
+    dist.destroy_process_group()
+
+
+def _verlet_slab_setup(thermo):
+    import nbody_b200.workloads as wl
+
+    w = wl.fcc_argon_reduced(5)  # 500 atoms, L = 8.55 sigma
+    w["lj"] = dict(w["lj"], R=1.9)  # with the skin of 0.2: 4 layers of edge >= 2.1 -> 2 slabs of 2
+    rng = np.random.Generator(np.random.Philox(9))
+    u = np.asfortranarray(w["u"] + 0.05 * rng.standard_normal(w["u"].shape))
+    v = np.asfortranarray(1.5 * w["v"])
+    th = dict(kind="berendsen", T=90.0, tau=0.05, kB=w["kB"]) if thermo else None
+    return w, u, v, th, 2e-3, 60
+
+
+@pytest.mark.parametrize("thermo", [False, True])
+def test_two_rank_slab_stepper_with_verlet_lists_matches_serial(tmp_path, thermo):
+    """SlabStepper's Verlet-list protocol over gloo: both ranks take the same (lagged) rebuild decisions, only halo
+    positions travel in between, and the trajectory is the serial one -- i.e. no interaction was ever missed."""
+    import torch.multiprocessing as mp
+
+    from oracle import nbody_oracle as orc
+    from tests._common import make_oracle
+
+    world = 2
+    mp.spawn(_verlet_slab_worker, args=(world, _free_port(), str(tmp_path), thermo), nprocs=world, join=True)
+    w, u, v, th, dt, steps = _verlet_slab_setup(thermo)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    if th:
+        spec["thermostat"] = th
+    ur, vr = orc.velocity_verlet(make_oracle(orc, spec), u, v, dt, steps)
+    rebuilt = [np.load(tmp_path / f"rebuilt{r}.npy") for r in range(world)]
+    stat = [np.load(tmp_path / f"stat{r}.npy") for r in range(world)]
+    assert np.array_equal(rebuilt[0], rebuilt[1]) and 2 <= len(rebuilt[0]) < steps // 2   # collective, and not every step
+    assert all(s[0] == steps - len(rebuilt[0]) for s in stat)                             # every other step only refreshed
+    assert sum(s[1] for s in stat) == u.shape[1] and all(s[2] > 0 for s in stat)
+    assert np.allclose(np.load(tmp_path / "u.npy"), ur, rtol=1e-11, atol=1e-13)
+    assert np.allclose(np.load(tmp_path / "v.npy"), vr, rtol=1e-10, atol=1e-12)
+
+
 def _slab_setup(thermo):
     import nbody_b200.workloads as wl
 
