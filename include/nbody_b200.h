@@ -13,8 +13,8 @@
  *     (x1 y1 z1 x2 y2 z2 ...).  They are caller-owned and only read/written during the call.
  *     ncols == n, except with the Nose-Hoover thermostat where ncols == n + 1
  *     (src/nbody_to_ode.jl:6-8).  Indices are 0-based everywhere in this ABI.
- *   - One context == one simulation on one GPU.  Calls on a context are blocking and must
- *     not be issued concurrently (the reference's RHS is called from one Julia task).
+ *   - One context == one simulation on one GPU (nbx_create) or on several (nbx_create_multi).  Calls on a
+ *     context are blocking and must not be issued concurrently (the reference's RHS is called from one Julia task).
  *   - There is NO CPU fallback: without a CUDA device nbx_create fails with NBX_ERR_CUDA.
  */
 #ifndef NBODY_B200_H
@@ -65,6 +65,14 @@ enum { NBX_T_PAIR_ALLPAIRS = 0,  /* tiled all-pairs kernel (gravity / Coulomb / 
 /* One context per NBodySimulation (src/nbody_simulation.jl:42-54).  `device` is the CUDA
  * ordinal.  Fails loudly (NBX_ERR_CUDA) when no sm_100 device is present. */
 NBX_API int nbx_create(nbx_ctx **out, int device);
+/* ONE handle for ndev GPUs of this process (SURVEY.md 8(b) "Proposed C ABI": nbx_create(nbx_ctx**, int ndev, const int* devs)).
+ * The handle takes the same calls as a single-GPU context -- nbx_system, nbx_boundary, nbx_add_*, nbx_thermostat,
+ * nbx_accel, nbx_upload, nbx_step_vv, nbx_step_em, nbx_download, nbx_energy -- and fans them out: the target loop of
+ * soode_system! (src/nbody_to_ode.jl:474-488, :502-532) is split over the devices (pair sharding for unbounded gravity /
+ * Coulomb, x-slabs for cutoff Lennard-Jones / Coulomb in a cubic box, target blocks otherwise; option "group_mode"), all
+ * exchanges run device to device over NVLink peer memory inside the step kernels, and one blocking call from one
+ * host thread (a Julia task) drives all GPUs.  devs may repeat a device (several members on one GPU: testing). */
+NBX_API int nbx_create_multi(nbx_ctx **out, int ndev, const int *devs);
 NBX_API int nbx_destroy(nbx_ctx *ctx);
 /* Message of the last failing call on ctx (ctx == NULL: of the last failing nbx_create). */
 NBX_API const char *nbx_last_error(const nbx_ctx *ctx);
@@ -236,6 +244,25 @@ NBX_API int nbx_slab_buffer(nbx_ctx *ctx, int which, void **ptr, int64_t *ndoubl
  * (any pointer may be NULL; capacity: the full system's column count). */
 NBX_API int nbx_slab_download(nbx_ctx *ctx, int64_t *n_own, int32_t *gid, double *u, double *v, double *dv);
 
+/* ---- groups across processes (one context per process and GPU; nbx_create_multi does the same inside one process) ----
+ * No reference equivalent (the reference is serial).  Every rank describes and uploads the FULL system, then:
+ *   nbx_group_init(ctx, rank, nranks, mode)   mode 0: chosen from the potentials; 1: pair sharding (unbounded gravity /
+ *       Coulomb: ring offsets of the Newton's-third-law kernel, partial accelerations pushed to their owners); 2: target
+ *       blocks [lo, hi) of the columns (any potential; water keeps molecules whole); 3: x-slabs (cutoff systems, cubic box)
+ *   nbx_group_export(ctx, kind, &ptr, handle64)   kind 0: the rank's window (flags + scalars), 1: slab receive area, 2: SoA
+ *       position rows, 3: staging area of partial accelerations; a kind the decomposition does not use gives NULL / zeros
+ *   (host: all-gather the 4 x 64-byte handles of every rank -- MPI, torch.distributed, a file: any bootstrap will do)
+ *   nbx_group_connect(ctx, handles[nranks][4][64], ptrs[nranks][4])   maps the peers' memory (CUDA IPC over NVLink)
+ *   (host: barrier)   nbx_group_start(ctx)   (slabs: the initial distribution; enqueues only)   nbx_slab_check / nbx_synchronize
+ * From then on nbx_accel (own block of u up, all-gather over NVLink, own columns of dv back; other columns untouched),
+ * nbx_step_vv, nbx_step_em, nbx_download (all positions; velocities / accelerations of the own columns), nbx_energy
+ * (kinetic part: the own block's share) act on the group: every rank makes the same calls, the exchanges happen inside
+ * the kernels (peer stores + flags, 10 s time-out -> NBX_ERR_CUDA, never a hang), and a step is replayed as a CUDA graph. */
+NBX_API int nbx_group_init(nbx_ctx *ctx, int rank, int nranks, int mode);
+NBX_API int nbx_group_export(nbx_ctx *ctx, int kind, void **ptr, void *ipc_handle64);
+NBX_API int nbx_group_connect(nbx_ctx *ctx, const void *handles, void *const *ptrs);
+NBX_API int nbx_group_start(nbx_ctx *ctx);
+
 /* ---- plumbing for the host layer ------------------------------------------------------- */
 /* CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on; NULL = the context's own
  * non-blocking stream (the default).  To share the legacy default stream pass cudaStreamLegacy
@@ -266,17 +293,16 @@ NBX_API int nbx_timing_reset(nbx_ctx *ctx);
  *                       "prefilter" (1: fp32 candidate scan before the exact fp64 predicate),
  *                       "verlet_skin_permille" (100: Verlet lists with skin = 0.1 R; 0: rescan the cells every evaluation),
  *                       "verlet_lanes" (0: lanes per target chosen from the system size; 1, 2, 4, 8),
- *                       "tiles" (0) / "tiles_min_n": list kernel over shared-memory staged candidate rows,
- *                       "fused_step" (0) / "fused_cluster" (4) / "fused_min_steps" (16): one kernel per step (nbx_fused.cu),
+ *   groups            : "group_mode" (leader of nbx_create_multi; 0), "pin_host" (0; 1: page-lock the caller's u / v / dv buffers
+ *                       the first time nbx_accel sees them -- the caller must keep them alive until nbx_destroy / nbx_system),
  *   nbx_step_vv       : "graph" (1: two-step CUDA graph), "graph_if_nodes" (1: rebuild chain as the body of an IF node),
  *                       "fuse_update" (1: position update + displacement check + record refresh in one kernel),
  *   all-pairs         : "symmetric_pairs" (1: Newton's-third-law kernel), "symmetric_min_n" (8192), "sym_variant" (0),
  *                       "uniform_weights" (0 forgets that all masses / charges are equal),
  *   slab driver       : "slab_record_halo", "slab_rebuild", "temperature_slot" (see the slab section above).
  * nbx_get_info keys: "n", "npad", "ncols", "water", "sm_count", "cells_lj", "cells_el", "verlet_lj", "verlet_el",
- * "verlet_overflow", "verlet_rebuilds", "tiles_lj", "tiles_el", "graph_if_nodes", "fused_steps", "fused_disabled",
- * "fused_list_cap", "allpairs_grid", "allpairs_chunks", "slab_own", "slab_ghost", "slab_layer_lo", "slab_layer_hi",
- * "slab_layers", "slab_verlet". */
+ * "verlet_overflow", "verlet_rebuilds", "graph_if_nodes", "allpairs_grid", "allpairs_chunks", "slab_own", "slab_ghost", "slab_layer_lo", "slab_layer_hi",
+ * "slab_layers", "slab_verlet", "group_mode", "group_rank", "group_size", "shard_lo", "shard_hi", "graph_cached". */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, int64_t value);
 NBX_API int nbx_get_info(nbx_ctx *ctx, const char *key, int64_t *value);
 /* DFMA-saturation microbenchmark: the measured FP64 roofline denominator (TFLOP/s). */
@@ -296,12 +322,6 @@ NBX_API int nbx_rdf_reset(nbx_ctx *ctx, int maxbin);
 NBX_API int nbx_rdf_add(nbx_ctx *ctx, const double *u);
 NBX_API int nbx_rdf_get(nbx_ctx *ctx, int64_t *hist, int64_t cap, int64_t *frames);
 NBX_API int nbx_msd(nbx_ctx *ctx, const double *u0, const double *u, double *out);
-/* Diagnostics for the tests: copies an internal device array of the fused cutoff step (csrc/nbx_fused.cu) to the
- * host.  name: "start" (ncell+1 int32 padded cell starts), "pid", "scell", "nlist" (int32 per slot), "list"
- * (cap_e x cap_slots int32), "x" (4 doubles per slot; which: position buffer 0/1).  *count receives the element
- * count; dst may be NULL to query it; cap = capacity of dst in elements.  Not part of the reference-facing API. */
-NBX_API int nbx_debug_fetch(nbx_ctx *ctx, const char *name, int which, void *dst, int64_t cap, int64_t *count);
-
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,11 @@ _i64 = C.c_int64
 # name -> (restype, argtypes); must list every NBX_API symbol of include/nbody_b200.h
 SIGNATURES = {
     "nbx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "nbx_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(C.c_int)]),
+    "nbx_group_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "nbx_group_export": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _vp]),
+    "nbx_group_connect": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "nbx_group_start": (C.c_int, [_vp]),
     "nbx_destroy": (C.c_int, [_vp]),
     "nbx_last_error": (C.c_char_p, [_vp]),
     "nbx_version": (C.c_int, []),
@@ -84,7 +89,6 @@ SIGNATURES = {
     "nbx_rdf_add": (C.c_int, [_vp, _dp]),
     "nbx_rdf_get": (C.c_int, [_vp, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
     "nbx_msd": (C.c_int, [_vp, _dp, _dp, _dp]),
-    "nbx_debug_fetch": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, _i64, C.POINTER(_i64)]),
 }
 
 _lib = None
@@ -129,13 +133,23 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
-class Context:
-    """One nbx_ctx: one simulation on one GPU."""
+GROUP_AUTO, GROUP_PAIRS, GROUP_TARGETS, GROUP_SLABS = 0, 1, 2, 3
 
-    def __init__(self, device: int = 0):
+
+class Context:
+    """One nbx_ctx: one simulation on one GPU, or -- ``device`` a list -- on several GPUs of this process
+    (nbx_create_multi: the same calls, fanned out by the library; a device may repeat)."""
+
+    def __init__(self, device=0):
         self.lib = load()
         h = _vp()
-        rc = self.lib.nbx_create(C.byref(h), int(device))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.nbx_create_multi(C.byref(h), len(device), devs)
+            self.group_size = len(device)
+        else:
+            rc = self.lib.nbx_create(C.byref(h), int(device))
+            self.group_size = 1
         if rc != NBX_OK:
             raise NbxError(rc, self.lib.nbx_last_error(None).decode())
         self.h = h
@@ -251,9 +265,10 @@ class Context:
         self._ck(self.lib.nbx_set_seed(self.h, int(seed)))
 
     def download(self, want_u=True, want_v=True, want_dv=False):
-        u = np.empty((3, self.ncols), order="F") if want_u else None
-        v = np.empty((3, self.ncols), order="F") if want_v else None
-        dv = np.empty((3, self.ncols), order="F") if want_dv else None
+        # (a group member fills only its own columns of v and dv: the others stay zero)
+        u = np.zeros((3, self.ncols), order="F") if want_u else None
+        v = np.zeros((3, self.ncols), order="F") if want_v else None
+        dv = np.zeros((3, self.ncols), order="F") if want_dv else None
         self._ck(self.lib.nbx_download(self.h, _p(u), _p(v), _p(dv)))
         return u, v, dv
 
@@ -270,6 +285,35 @@ class Context:
         self._ck(self.lib.nbx_neighbors(self.h, offsets.ctypes.data_as(C.POINTER(_i64)),
                                         lst.ctypes.data_as(C.POINTER(C.c_int32)), cap))
         return offsets, lst[: offsets[-1]]
+
+    # -- groups across processes / contexts (nbx_group_*) ------------------------------------------
+    def group_init(self, rank, nranks, mode=GROUP_AUTO):
+        self._ck(self.lib.nbx_group_init(self.h, int(rank), int(nranks), int(mode)))
+
+    def group_export(self, want_handles=True):
+        """(pointers[4], handles: 4 x 64 bytes or None) of the memory the peers map: window, slab receive area,
+        position rows, staging area."""
+        ptrs, blob = [], b""
+        for kind in range(4):
+            p = _vp()
+            h = C.create_string_buffer(64) if want_handles else None
+            self._ck(self.lib.nbx_group_export(self.h, kind, C.byref(p), h))
+            ptrs.append(int(p.value or 0))
+            if want_handles:
+                blob += h.raw
+        return ptrs, (blob if want_handles else None)
+
+    def group_connect(self, handles=None, ptrs=None):
+        """handles: bytes of nranks x 4 x 64 (other processes); ptrs: nranks x 4 device pointers (this process)."""
+        hb = C.create_string_buffer(handles, len(handles)) if handles is not None else None
+        pa = None
+        if ptrs is not None:
+            flat = [int(x) for row in ptrs for x in row]
+            pa = (_vp * len(flat))(*[_vp(x) if x else None for x in flat])
+        self._ck(self.lib.nbx_group_connect(self.h, hb, pa))
+
+    def group_start(self):
+        self._ck(self.lib.nbx_group_start(self.h))
 
     # -- slab decomposition ------------------------------------------------------------------------
     def slab_init(self, rank, nranks):
@@ -398,14 +442,6 @@ class Context:
         out = C.c_double()
         self._ck(self.lib.nbx_msd(self.h, _p(_f(u0, self.ncols)), None if u is None else _p(_f(u, self.ncols)), C.byref(out)))
         return out.value
-
-    def debug_fetch(self, name, which=0):
-        """Internal array of the fused cutoff step (diagnostics for the tests)."""
-        cnt = _i64()
-        self._ck(self.lib.nbx_debug_fetch(self.h, name.encode(), int(which), None, 0, C.byref(cnt)))
-        out = np.empty(cnt.value, dtype=np.float64 if name == "x" else np.int32)
-        self._ck(self.lib.nbx_debug_fetch(self.h, name.encode(), int(which), out.ctypes.data_as(_vp), out.size, C.byref(cnt)))
-        return out
 
     def measure_hbm_peak(self):
         g = C.c_double()

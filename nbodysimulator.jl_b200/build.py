@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libnbody_b200.so")
-SOURCES = ["nbx_api.cu", "nbx_allpairs.cu", "nbx_sympairs.cu", "nbx_cells.cu", "nbx_fused.cu", "nbx_slab.cu", "nbx_bonded.cu", "nbx_integrate.cu", "nbx_energy.cu", "nbx_analysis.cu"]
-HEADERS = [os.path.join(CSRC, "nbx_internal.cuh"), os.path.join(HERE, "..", "include", "nbody_b200.h")]
+SOURCES = ["nbx_api.cu", "nbx_allpairs.cu", "nbx_sympairs.cu", "nbx_cells.cu", "nbx_slab.cu", "nbx_multi.cu", "nbx_group.cu", "nbx_bonded.cu", "nbx_integrate.cu", "nbx_energy.cu", "nbx_analysis.cu"]
+HEADERS = [os.path.join(CSRC, "nbx_internal.cuh"), os.path.join(CSRC, "nbx_graph.inl"), os.path.join(HERE, "..", "include", "nbody_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-Xptxas", "-v",

@@ -185,11 +185,16 @@ static void free_system(nbx_ctx *c)
     c->aos_u = c->aos_v = c->aos_dv = c->opos = c->oacc = nullptr;
     cells_free(&c->cl_lj);
     cells_free(&c->cl_el);
-    fused_free(c);
     analysis_free(c);
-    c->fz = FusedState();
     c->T_slot = 0;
     slab_free(c);
+    comm_free(c);
+    graph_drop(c);
+    c->tgt_lo = c->tgt_hi = 0;
+    c->pair_rank = 0; c->pair_nranks = 1;
+    for (auto &e : c->pinned) cudaHostUnregister(const_cast<void *>(e.first));
+    c->pinned.clear();
+    cudaGetLastError();
     c->resident = false;
 }
 
@@ -262,6 +267,17 @@ static int accel_from_staging(nbx_ctx *c, bool have_v)
 
 using namespace nbx;
 
+// leader of a single-process group (nbx_create_multi): configuration calls go to every member
+#define NBX_FANOUT(c, expr)                                              \
+    if ((c) && (c)->is_group) {                                          \
+        for (nbx_ctx *m__ : (c)->members) {                              \
+            nbx_ctx *x = m__;                                            \
+            const int rc__ = (expr);                                     \
+            if (rc__ != NBX_OK) { (c)->err = x->err; return rc__; }      \
+        }                                                                \
+        return NBX_OK;                                                   \
+    }
+
 extern "C" {
 
 int nbx_version(void) { return 100; }
@@ -302,9 +318,12 @@ int nbx_create(nbx_ctx **out, int device)
     return NBX_OK;
 }
 
+int nbx_create_multi(nbx_ctx **out, int ndev, const int *devs) { return leader_create(out, ndev, devs); }
+
 int nbx_destroy(nbx_ctx *c)
 {
     if (!c) return NBX_OK;
+    if (c->is_group) return leader_destroy(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_system(c);
@@ -320,6 +339,7 @@ int nbx_destroy(nbx_ctx *c)
 
 int nbx_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const double *mm, int water)
 {
+    if (c && c->is_group) return leader_system(c, n, m, q, mm, water);
     NBX_TRY(guard(c));
     if (n <= 0 || n > (int64_t)1 << 30) return fail(c, NBX_ERR_INVALID, "nbx_system: n = %lld out of range", (long long)n);
     if (!m) return fail(c, NBX_ERR_INVALID, "nbx_system: masses are required");
@@ -378,7 +398,9 @@ int nbx_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const do
 
 int nbx_boundary(nbx_ctx *c, int kind, const double *b)
 {
+    NBX_FANOUT(c, nbx_boundary(x, kind, b));
     NBX_TRY(guard(c));
+    graph_drop(c);
     if (kind == NBX_BC_INFINITE) { c->bc_kind = kind; return NBX_OK; }
     if (!b) return fail(c, NBX_ERR_INVALID, "nbx_boundary: box is NULL");
     if (kind == NBX_BC_CUBIC) {
@@ -400,15 +422,19 @@ int nbx_boundary(nbx_ctx *c, int kind, const double *b)
 
 int nbx_add_gravity(nbx_ctx *c, double G)
 {
+    NBX_FANOUT(c, nbx_add_gravity(x, G));
     NBX_TRY(guard(c));
+    graph_drop(c);
     c->has_grav = true; c->G = G;
     return NBX_OK;
 }
 
 int nbx_add_lj(nbx_ctx *c, double eps, double sigma, double R)
 {
+    NBX_FANOUT(c, nbx_add_lj(x, eps, sigma, R));
     NBX_TRY(guard(c));
     if (!(R > 0.0)) return fail(c, NBX_ERR_INVALID, "nbx_add_lj: R must be > 0");
+    graph_drop(c);
     c->has_lj = true; c->lj_eps = eps;
     c->lj_sigma2 = sigma * sigma; // LennardJonesParameters caches sigma^2 and R^2 (src/basic_potentials.jl:67-69)
     c->lj_R = R; c->lj_R2 = R * R;
@@ -417,16 +443,19 @@ int nbx_add_lj(nbx_ctx *c, double eps, double sigma, double R)
 
 int nbx_add_coulomb(nbx_ctx *c, double k, double R)
 {
+    NBX_FANOUT(c, nbx_add_coulomb(x, k, R));
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_add_coulomb"));
     if (!c->has_q) return fail(c, NBX_ERR_INVALID, "nbx_add_coulomb: the system has no charges");
     if (!(R > 0.0)) return fail(c, NBX_ERR_INVALID, "nbx_add_coulomb: R must be > 0 (Inf allowed)");
+    graph_drop(c);
     c->has_coul = true; c->el_k = k; c->el_R = R; c->el_R2 = R * R;
     return NBX_OK;
 }
 
 int nbx_add_dipole(nbx_ctx *c, double mu_4pi)
 {
+    NBX_FANOUT(c, nbx_add_dipole(x, mu_4pi));
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_add_dipole"));
     if (!c->has_mm) return fail(c, NBX_ERR_INVALID, "nbx_add_dipole: the system has no magnetic moments");
@@ -436,6 +465,7 @@ int nbx_add_dipole(nbx_ctx *c, double mu_4pi)
 
 int nbx_add_spcfw(nbx_ctx *c, double rOH, double aHOH, double kb, double ka)
 {
+    NBX_FANOUT(c, nbx_add_spcfw(x, rOH, aHOH, kb, ka));
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_add_spcfw"));
     if (!c->water) return fail(c, NBX_ERR_INVALID, "nbx_add_spcfw: the system is not water (O,H1,H2 triples)");
@@ -445,6 +475,7 @@ int nbx_add_spcfw(nbx_ctx *c, double rOH, double aHOH, double kb, double ka)
 
 int nbx_clear_potentials(nbx_ctx *c)
 {
+    NBX_FANOUT(c, nbx_clear_potentials(x));
     NBX_TRY(guard(c));
     c->has_grav = c->has_lj = c->has_coul = c->has_dip = c->has_spcfw = false;
     return NBX_OK;
@@ -452,10 +483,12 @@ int nbx_clear_potentials(nbx_ctx *c)
 
 int nbx_thermostat(nbx_ctx *c, int kind, double T0, double param, double kB, int64_t N, int64_t Nc)
 {
+    NBX_FANOUT(c, nbx_thermostat(x, kind, T0, param, kB, N, Nc));
     NBX_TRY(guard(c));
     if (kind < NBX_THERMO_NONE || kind > NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_thermostat: kind %d", kind);
     if (kind != NBX_THERMO_NONE && (3 * N - Nc <= 0 || !(kB > 0.0)))
         return fail(c, NBX_ERR_INVALID, "nbx_thermostat: needs 3N - Nc > 0 and kB > 0");
+    graph_drop(c);
     c->thermo = kind; c->T0 = T0; c->tparam = param; c->kB = kB; c->thN = N; c->thNc = Nc;
     if (c->n > 0) c->ncols = c->n + (kind == NBX_THERMO_NOSEHOOVER ? 1 : 0);
     return NBX_OK;
@@ -625,16 +658,47 @@ int nbx_slab_download(nbx_ctx *c, int64_t *n_own, int32_t *gid, double *u, doubl
     return NBX_OK;
 }
 
-int nbx_set_stream(nbx_ctx *c, void *stream)
+int nbx_group_init(nbx_ctx *c, int rank, int nranks, int mode)
 {
     NBX_TRY(guard(c));
+    if (c->is_group) return fail(c, NBX_ERR_INVALID, "nbx_group_init: the handle is a group leader (nbx_create_multi joins its members itself)");
+    NBX_TRY(need_system(c, "nbx_group_init"));
+    if (mode < 0 || mode > 3) return fail(c, NBX_ERR_INVALID, "nbx_group_init: mode 0 .. 3");
+    return group_init(c, rank, nranks, mode);
+}
+
+int nbx_group_export(nbx_ctx *c, int kind, void **ptr, void *ipc_handle64)
+{
+    NBX_TRY(guard(c));
+    return group_export(c, kind, ptr, ipc_handle64);
+}
+
+int nbx_group_connect(nbx_ctx *c, const void *handles, void *const *ptrs)
+{
+    NBX_TRY(guard(c));
+    return group_connect(c, handles, ptrs);
+}
+
+int nbx_group_start(nbx_ctx *c)
+{
+    NBX_TRY(guard(c));
+    NBX_TRY(need_system(c, "nbx_group_start"));
+    return group_start(c);
+}
+
+int nbx_set_stream(nbx_ctx *c, void *stream)
+{
+    NBX_FANOUT(c, nbx_set_stream(x, stream));
+    NBX_TRY(guard(c));
     cudaStreamSynchronize(c->stream);
+    graph_drop(c);
     c->stream = stream ? (cudaStream_t)stream : c->own_stream;
     return NBX_OK;
 }
 
 int nbx_synchronize(nbx_ctx *c)
 {
+    NBX_FANOUT(c, nbx_synchronize(x));
     NBX_TRY(guard(c));
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     return NBX_OK;
@@ -652,8 +716,14 @@ static int finish_and_check(nbx_ctx *c)
 int nbx_accel(nbx_ctx *c, const double *u, double *v, double t, double *dv)
 {
     (void)t;
+    if (c && c->is_group) return leader_accel(c, u, v, dv);
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_accel"));
+    if (c->comm.on) { // group member: upload the own block, all-gather over NVLink, return the own columns of dv
+        if (!u || !dv) return fail(c, NBX_ERR_INVALID, "nbx_accel: u and dv are required");
+        NBX_TRY(multi_accel_enqueue(c, u, v));
+        return multi_accel_finish(c, dv);
+    }
     NBX_TRY(no_slab(c, "nbx_accel"));
     if (!u || !dv) return fail(c, NBX_ERR_INVALID, "nbx_accel: u and dv are required");
     const bool have_v = needs_velocity(c);
@@ -717,9 +787,12 @@ int nbx_accel_device(nbx_ctx *c, const double *u_dev, double *v_dev, double t, d
 
 int nbx_upload(nbx_ctx *c, const double *u, const double *v)
 {
+    if (c && c->is_group) return leader_upload(c, u, v);
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_upload"));
     NBX_TRY(no_slab(c, "nbx_upload"));
+    if (c->comm.on) return fail(c, NBX_ERR_INVALID, "nbx_upload: the context belongs to a group (nbx_system starts over)");
+    graph_drop(c);
     if (!u || !v) return fail(c, NBX_ERR_INVALID, "nbx_upload: u and v are required");
     const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
     NBX_CUDA(c, cudaMemcpyAsync(c->aos_u, u, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -788,8 +861,13 @@ int nbx_vv_finish(nbx_ctx *c, double dt)
 
 int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
 {
+    if (c && c->is_group) return leader_step_vv(c, dt, nsteps);
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_step_vv"));
+    if (c->comm.on) { // group member (pairs / targets / slabs): the distributed loop, exchanges over peer memory
+        NBX_TRY(multi_enqueue_vv(c, dt, nsteps));
+        return multi_finish(c);
+    }
     NBX_TRY(no_slab(c, "nbx_step_vv"));
     if (c->tgt_lo != 0 || c->tgt_hi != c->n)
         return fail(c, NBX_ERR_INVALID, "nbx_step_vv: sharded context; drive nbx_vv_begin / all-gather / nbx_vv_finish");
@@ -798,14 +876,6 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     if (c->thermo == NBX_THERMO_LANGEVIN)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
     int64_t s = 0;
-    bool skip_pos = false;
-    // One cutoff potential in a cubic box: one fused kernel per step over the state in cell order (nbx_fused.cu).
-    // A cluster-list overflow hands the rest of the run back to the kernels below, positions already advanced.
-    if (fused_eligible(c, nsteps)) {
-        NBX_TRY(fused_run(c, dt, nsteps, &s));
-        if (s >= nsteps) return NBX_OK;
-        skip_pos = true;
-    }
     // one cutoff potential over Verlet lists: the position update also checks the displacements and refreshes the
     // cell-order records (vv_pos_lists_kernel); decided per step, the first evaluation after a (re)configuration is plain
     const bool one_cutoff = !c->water && !c->has_grav && !c->has_dip && !c->has_spcfw && c->tgt_lo == 0 && c->tgt_hi == c->n &&
@@ -813,18 +883,14 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     CellList *ucl = c->has_lj ? &c->cl_lj : &c->cl_el;
     const double *uw = c->has_lj ? nullptr : c->charge;
     auto one_step = [&]() -> int {
-        if (!skip_pos) {
-            if (one_cutoff && lists_can_fuse_update(c, ucl, c->pos)) NBX_TRY(launch_vv_pos_lists(c, ucl, uw, dt));
-            else NBX_TRY(launch_vv_pos(c, dt));
-        }
-        skip_pos = false;
+        if (one_cutoff && lists_can_fuse_update(c, ucl, c->pos)) NBX_TRY(launch_vv_pos_lists(c, ucl, uw, dt));
+        else NBX_TRY(launch_vv_pos(c, dt));
         double *t = c->acc_old; c->acc_old = c->acc; c->acc = t;
         NBX_TRY(compute_pairs(c));
         NBX_TRY(launch_vv_vel(c, dt, true));
         if (c->thermo == NBX_THERMO_ANDERSEN) NBX_TRY(launch_andersen(c, dt));
         return NBX_OK;
     };
-    if (skip_pos) { NBX_TRY(one_step()); ++s; }
     // Long runs replay a CUDA graph of TWO steps (the acc / acc_old swap has period two): every decision inside a
     // step (Verlet rebuild, overflow fallback) is taken on the device, so the launch sequence is the same for all
     // steps.  Andersen draws from a host-side step counter and the phase timers record events: both stay eager.
@@ -876,6 +942,7 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
 
 int nbx_set_seed(nbx_ctx *c, uint64_t seed)
 {
+    NBX_FANOUT(c, nbx_set_seed(x, seed));
     NBX_TRY(guard(c));
     c->seed = seed; c->rng_step = 0;
     return NBX_OK;
@@ -883,12 +950,17 @@ int nbx_set_seed(nbx_ctx *c, uint64_t seed)
 
 int nbx_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
 {
+    if (c && c->is_group) return leader_step_em(c, dt, nsteps, seed);
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_step_em"));
     NBX_TRY(no_slab(c, "nbx_step_em"));
     if (c->thermo != NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_step_em: needs the Langevin thermostat");
     if (c->water) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_em: the water SDE variant (src/nbody_to_ode.jl:600-680) is not built");
     if (seed) c->seed = seed;
+    if (c->comm.on) {
+        NBX_TRY(multi_enqueue_em(c, dt, nsteps));
+        return multi_finish(c);
+    }
     for (int64_t s = 0; s < nsteps; ++s) {
         if (s > 0) NBX_TRY(compute_accel(c)); // a(x_s); the first one is resident already
         NBX_TRY(launch_em_step(c, dt));
@@ -900,9 +972,25 @@ int nbx_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
 
 int nbx_download(nbx_ctx *c, double *u, double *v, double *dv)
 {
+    if (c && c->is_group) return leader_download(c, u, v, dv);
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_download"));
     NBX_TRY(no_slab(c, "nbx_download"));
+    if (c->comm.on) { // group member: all positions are here, velocities and accelerations of the own block only
+        const int64_t lo = c->tgt_lo, cnt = c->tgt_hi - lo;
+        if (u) {
+            NBX_TRY(launch_soa_to_aos(c, c->pos, c->aos_u, c->n, c->n, 0, c->n));
+            NBX_CUDA(c, cudaMemcpyAsync(u, c->aos_u, sizeof(double) * 3 * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+        }
+        double *const rows[2] = {c->vel, c->acc}, *const stage[2] = {c->aos_v, c->aos_dv}, *const host[2] = {v, dv};
+        for (int k = 0; k < 2; ++k) {
+            if (!host[k] || cnt <= 0) continue;
+            NBX_TRY(launch_soa_to_aos(c, rows[k] + lo, stage[k] + 3 * lo, cnt, cnt, 0, cnt));
+            NBX_CUDA(c, cudaMemcpyAsync(host[k] + 3 * lo, stage[k] + 3 * lo, sizeof(double) * 3 * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream));
+        }
+        NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+        return NBX_OK;
+    }
     const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
     const bool nose = c->thermo == NBX_THERMO_NOSEHOOVER;
     if (u) {
@@ -925,8 +1013,21 @@ int nbx_download(nbx_ctx *c, double *u, double *v, double *dv)
 
 int nbx_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature)
 {
+    if (c && c->is_group) return leader_energy(c, ekin, epot, temperature);
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_energy"));
+    if (c->slab.on && c->slab.started && !epot) {
+        // a started slab keeps the sum m v^2 over ALL ranks in the scalar block after nbx_group_start / nbx_step_vv
+        double mv2 = 0.0;
+        NBX_CUDA(c, cudaMemcpyAsync(&mv2, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (ekin) *ekin = 0.5 * mv2;
+        if (temperature) {
+            const int64_t N = c->thN > 0 ? c->thN : c->slab.n_total;
+            *temperature = mv2 / ((c->kB != 0.0 ? c->kB : 1.0) * (double)(3 * N - c->thNc));
+        }
+        return NBX_OK;
+    }
     NBX_TRY(no_slab(c, "nbx_energy"));
     if (ekin || temperature) NBX_TRY(reduce_kinetic(c, ekin, temperature));
     if (epot) NBX_TRY(reduce_potential(c, epot));
@@ -935,6 +1036,13 @@ int nbx_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature)
 
 int nbx_neighbors(nbx_ctx *c, int64_t *offsets, int32_t *list, int64_t cap)
 {
+    if (c && c->is_group) {
+        if (!c->g_ready || c->members[0]->comm.mode == 3)
+            return fail(c, NBX_ERR_UNSUPPORTED, "nbx_neighbors: needs a group whose members hold all positions (modes 1, 2) with a resident state");
+        const int rc = nbx_neighbors(c->members[0], offsets, list, cap);
+        if (rc != NBX_OK) c->err = c->members[0]->err;
+        return rc;
+    }
     NBX_TRY(guard(c));
     NBX_TRY(need_resident(c, "nbx_neighbors"));
     NBX_TRY(no_slab(c, "nbx_neighbors"));
@@ -968,6 +1076,7 @@ int nbx_device_ptr(nbx_ctx *c, int which, void **ptr, int64_t *ld)
 
 int nbx_timing_enable(nbx_ctx *c, int enable)
 {
+    NBX_FANOUT(c, nbx_timing_enable(x, enable));
     NBX_TRY(guard(c));
     c->timing = enable != 0;
     return NBX_OK;
@@ -975,6 +1084,18 @@ int nbx_timing_enable(nbx_ctx *c, int enable)
 
 int nbx_timing_get(nbx_ctx *c, int phase, double *total_ms, int64_t *count)
 {
+    if (c && c->is_group) { // the slowest member
+        double best = 0.0; int64_t cnt = 0;
+        for (nbx_ctx *x : c->members) {
+            double t = 0.0; int64_t k = 0;
+            const int rc = nbx_timing_get(x, phase, &t, &k);
+            if (rc != NBX_OK) { c->err = x->err; return rc; }
+            if (t >= best) { best = t; cnt = k; }
+        }
+        if (total_ms) *total_ms = best;
+        if (count) *count = cnt;
+        return NBX_OK;
+    }
     NBX_TRY(guard(c));
     if (phase < 0 || phase >= NBX_T_COUNT) return fail(c, NBX_ERR_INVALID, "nbx_timing_get: phase %d", phase);
     timer_flush(c, c->timers[phase]);
@@ -985,6 +1106,7 @@ int nbx_timing_get(nbx_ctx *c, int phase, double *total_ms, int64_t *count)
 
 int nbx_timing_reset(nbx_ctx *c)
 {
+    NBX_FANOUT(c, nbx_timing_reset(x));
     NBX_TRY(guard(c));
     for (auto &t : c->timers) { timer_flush(c, t); t.total_ms = 0.0; t.count = 0; }
     return NBX_OK;
@@ -992,8 +1114,17 @@ int nbx_timing_reset(nbx_ctx *c)
 
 int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
 {
+    if (c && c->is_group) {
+        if (key && !strcmp(key, "group_mode")) {
+            if (value < 0 || value > 3) return fail(c, NBX_ERR_INVALID, "group_mode: 0 (chosen from the potentials), 1 pairs, 2 targets, 3 slabs");
+            c->opt_group_mode = (int)value;
+            return NBX_OK;
+        }
+        NBX_FANOUT(c, nbx_set_option(x, key, value));
+    }
     NBX_TRY(guard(c));
     if (!key) return fail(c, NBX_ERR_INVALID, "nbx_set_option: key is NULL");
+    graph_drop(c);
     if (!strcmp(key, "cell_list")) c->opt_cell_list = (int)value;
     else if (!strcmp(key, "prefilter")) c->opt_prefilter = (int)value;
     else if (!strcmp(key, "verlet_skin_permille")) {
@@ -1001,10 +1132,9 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         c->opt_verlet_permille = (int)value;
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
-    else if (!strcmp(key, "tiles")) c->opt_tiles = (int)value;
+    else if (!strcmp(key, "pin_host")) c->opt_pin_host = (int)value;
     else if (!strcmp(key, "fuse_update")) c->opt_fuse_update = (int)value;
     else if (!strcmp(key, "graph_if_nodes")) { c->opt_cond_nodes = (int)value; if (value) c->cond_fail = false; }
-    else if (!strcmp(key, "tiles_min_n")) c->tiles_min_n = value;
     else if (!strcmp(key, "temperature_slot")) {
         if (value != 0 && value != 12) return fail(c, NBX_ERR_INVALID, "temperature_slot: 0 or 12");
         c->T_slot = (int)value;
@@ -1015,13 +1145,6 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "verlet_lanes: 0, 1, 2, 4 or 8");
         c->opt_verlet_lanes = (int)value;
     }
-    else if (!strcmp(key, "fused_step")) { c->opt_fused = (int)value; if (value) c->fz.disabled = false; }
-    else if (!strcmp(key, "fused_cluster")) {
-        if (value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "fused_cluster: 1, 2, 4 or 8");
-        c->opt_fused_cluster = (int)value;
-    }
-    else if (!strcmp(key, "fused_debug")) c->opt_fused_debug = (int)value;
-    else if (!strcmp(key, "fused_min_steps")) c->fused_min_steps = value < 2 ? 2 : value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
     else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;
@@ -1032,6 +1155,27 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
 
 int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
 {
+    if (c && c->is_group) { // the members are alike: answer for member `group_member` (default 0); "group_size" for the leader
+        if (!key || !value) return fail(c, NBX_ERR_INVALID, "nbx_get_info: NULL argument");
+        if (!strcmp(key, "group_size")) { *value = (int64_t)c->members.size(); return NBX_OK; }
+        if (!strcmp(key, "n")) { *value = c->n; return NBX_OK; }
+        if (!strcmp(key, "ncols")) { *value = c->ncols; return NBX_OK; }
+        if (!strcmp(key, "verlet_rebuilds") || !strcmp(key, "slab_own") || !strcmp(key, "slab_ghost")) { // max / sum over the members
+            int64_t acc = 0;
+            for (nbx_ctx *x : c->members) {
+                int64_t t = 0;
+                const int rc = nbx_get_info(x, key, &t);
+                if (rc != NBX_OK) { c->err = x->err; return rc; }
+                acc = !strcmp(key, "verlet_rebuilds") ? std::max(acc, t) : acc + t;
+            }
+            *value = acc;
+            return NBX_OK;
+        }
+        nbx_ctx *x = c->members[0];
+        const int rc = nbx_get_info(x, key, value);
+        if (rc != NBX_OK) c->err = x->err;
+        return rc;
+    }
     NBX_TRY(guard(c));
     if (!key || !value) return fail(c, NBX_ERR_INVALID, "nbx_get_info: NULL argument");
     if (!strcmp(key, "n")) *value = c->n;
@@ -1045,6 +1189,12 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "slab_layer_hi")) *value = c->slab.c1;
     else if (!strcmp(key, "slab_layers")) *value = c->slab.nc;
     else if (!strcmp(key, "slab_verlet")) *value = (c->slab.on && c->slab.verlet) ? 1 : 0;
+    else if (!strcmp(key, "group_mode")) *value = c->comm.on ? c->comm.mode : 0;
+    else if (!strcmp(key, "group_rank")) *value = c->comm.on ? c->comm.rank : 0;
+    else if (!strcmp(key, "group_size")) *value = c->comm.on ? c->comm.nranks : 1;
+    else if (!strcmp(key, "shard_lo")) *value = c->tgt_lo;
+    else if (!strcmp(key, "shard_hi")) *value = c->tgt_hi;
+    else if (!strcmp(key, "graph_cached")) *value = c->mg_exec ? 1 : 0;
     else if (!strcmp(key, "verlet_overflow") || !strcmp(key, "verlet_rebuilds")) {
         // device flags of the LJ list (synchronises): [1] sticky overflow, [2] rebuilds so far
         int h[4] = {0, 0, 0, 0};
@@ -1052,14 +1202,9 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
             NBX_CUDA(c, cudaMemcpyAsync(h, c->cl_lj.v_flags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
             NBX_CUDA(c, cudaStreamSynchronize(c->stream));
         }
-        *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2] + c->fz.rebuilds_total;
+        *value = !strcmp(key, "verlet_overflow") ? h[1] : h[2];
     }
     else if (!strcmp(key, "graph_if_nodes")) *value = (c->opt_cond_nodes && !c->cond_fail) ? 1 : 0;
-    else if (!strcmp(key, "fused_steps")) *value = c->fz.steps_total;
-    else if (!strcmp(key, "fused_disabled")) *value = c->fz.disabled ? 1 : 0;
-    else if (!strcmp(key, "fused_list_cap")) *value = c->fz.cap_e;
-    else if (!strcmp(key, "tiles_lj")) *value = (c->cl_lj.v_valid && c->cl_lj.v_tiles) ? 1 : 0;
-    else if (!strcmp(key, "tiles_el")) *value = (c->cl_el.v_valid && c->cl_el.v_tiles) ? 1 : 0;
     else if (!strcmp(key, "verlet_lj")) *value = c->cl_lj.v_valid ? c->cl_lj.v_cap : 0;
     else if (!strcmp(key, "verlet_el")) *value = c->cl_el.v_valid ? c->cl_el.v_cap : 0;
     else if (!strcmp(key, "cells_lj")) *value = c->cl_lj.grid.valid ? c->cl_lj.grid.ncell : 0;
@@ -1107,30 +1252,6 @@ int nbx_msd(nbx_ctx *c, const double *u0, const double *u, double *out)
     NBX_TRY(guard(c));
     NBX_TRY(need_system(c, "nbx_msd"));
     return analysis_msd(c, u0, u, out);
-}
-
-int nbx_debug_fetch(nbx_ctx *c, const char *name, int which, void *dst, int64_t cap, int64_t *count)
-{
-    NBX_TRY(guard(c));
-    if (!name || !count) return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: NULL argument");
-    const FusedState &z = c->fz;
-    if (!z.flags) return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: the fused step has not run on this context");
-    const void *src = nullptr;
-    int64_t cnt = 0;
-    size_t elem = sizeof(int);
-    if (!strcmp(name, "start")) { src = z.start; cnt = z.ncell + 1; }
-    else if (!strcmp(name, "pid")) { src = z.pid; cnt = z.cap_slots; }
-    else if (!strcmp(name, "scell")) { src = z.scell; cnt = z.cap_slots; }
-    else if (!strcmp(name, "nlist")) { src = z.nlist; cnt = z.cap_slots; }
-    else if (!strcmp(name, "list")) { src = z.list; cnt = (int64_t)z.cap_e * z.cap_slots; }
-    else if (!strcmp(name, "x")) { src = z.x[which & 1]; cnt = 4 * z.cap_slots; elem = sizeof(double); }
-    else return fail(c, NBX_ERR_INVALID, "nbx_debug_fetch: unknown array '%s'", name);
-    *count = cnt;
-    if (!dst) return NBX_OK;
-    if (cap < cnt) return fail(c, NBX_ERR_CAPACITY, "nbx_debug_fetch: %lld elements needed", (long long)cnt);
-    NBX_CUDA(c, cudaMemcpyAsync(dst, src, elem * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream));
-    NBX_CUDA(c, cudaStreamSynchronize(c->stream));
-    return NBX_OK;
 }
 
 } // extern "C"

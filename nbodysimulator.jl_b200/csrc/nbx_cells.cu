@@ -755,189 +755,6 @@ static void launch_verlet_force(nbx_ctx *c, const CellPairArgs &a, const VerletA
 #undef NBX_VF
 }
 
-// ------------------------------------------------------------------------------------------------
-// tile kernels: the list kernel's gathers taken off the L1 tag path
-// ------------------------------------------------------------------------------------------------
-// verlet_force_kernel is bound by the L1 rate of one 32-byte sector gather per clock and SM.  Here a CTA owns the
-// targets of W consecutive cells of one x-row of the grid.  Everything those targets can list lies in 9 x-rows x
-// (W + 2) cells = at most 27 CONTIGUOUS slot ranges of the cell order (main range + the two periodic wrap cells per
-// row); the CTA copies them, coalesced, into shared memory as SoA x / y / z (/ w) and the lists hold 16-bit indices
-// into that staging area instead of global slots.  A gather becomes three 8-byte shared loads (about 18 LSU
-// cycles per warp instead of 32), and the list stream halves.  Entry order, predicate and arithmetic are those of
-// verlet_build_slot / verlet_force_kernel: the results are bit-identical.
-constexpr int kTileCap = 1536; // staged records per CTA (36 KB of coordinates: six CTAs per SM)
-
-struct TileArgs {
-    unsigned short *tlist; // [cap][stride]
-    int W, chunks;         // cells per CTA along x, CTAs per x-row
-};
-
-struct TileTable {
-    int begin[27], end[27], off[27]; // slot range and staging offset of (row r = 0..8, kind q: main / left wrap / right wrap) at 3 r + q
-    int total, tb, te;               // staged records; target slots [tb, te)
-};
-
-__device__ __forceinline__ void tile_setup(const CellPairArgs &a, const TileArgs &ta, TileTable *t)
-{
-    const int nc = a.nc;
-    const int row = blockIdx.x / ta.chunks, chunk = blockIdx.x - row * ta.chunks;
-    const int cx0 = chunk * ta.W, cx1 = min(cx0 + ta.W, nc);
-    const int cy = row % nc, cz = row / nc;
-    if (threadIdx.x < 32) {
-        const int l = threadIdx.x;
-        int len = 0, b = 0;
-        if (l < 27) {
-            const int r = l / 3, q = l - 3 * r;
-            int z = cz + r / 3 - 1, y = cy + (r - (r / 3) * 3) - 1;
-            z = z < 0 ? z + nc : (z >= nc ? z - nc : z);
-            y = y < 0 ? y + nc : (y >= nc ? y - nc : y);
-            const int rr = (z * nc + y) * nc;
-            if (q == 0) { b = a.start[rr + max(cx0 - 1, 0)]; len = a.start[rr + min(cx1, nc - 1) + 1] - b; }
-            else if (q == 1) { if (cx0 == 0) { b = a.start[rr + nc - 1]; len = a.start[rr + nc] - b; } }
-            else if (cx1 == nc) { b = a.start[rr]; len = a.start[rr + 1] - b; }
-        }
-        int s = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, s, o);
-            if (l >= o) s += u;
-        }
-        if (l < 27) { t->begin[l] = b; t->end[l] = b + len; t->off[l] = s - len; }
-        if (l == 26) t->total = s;
-        if (l == 0) { t->tb = a.start[row * nc + cx0]; t->te = a.start[row * nc + cx1]; }
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(128) tile_build_kernel(const CellPairArgs a, const VerletArgs v, const TileArgs ta)
-{
-    __shared__ TileTable t;
-    if (!v.flags[0] || v.flags[1]) return;
-    tile_setup(a, ta, &t);
-    if (t.total > kTileCap) { // a region far denser than the average: the scan-per-step path takes over (sticky)
-        if (threadIdx.x == 0) v.flags[1] = 1;
-        return;
-    }
-    const int nc = a.nc;
-    const float fnc = (float)nc;
-    const int row = blockIdx.x / ta.chunks;
-    const int cy = row % nc, cz = row / nc;
-    for (int k = t.tb + threadIdx.x; k < t.te; k += 128) {
-        const float4 me = a.sl4[k];
-        const int key = __float_as_int(me.w);
-        const int cx = a.scell[k] % nc;
-        int cnt = 0;
-        bool over = false;
-        auto scan = [&](int b, int e, int base, float tx, float ty, float tz) {
-            for (int m = b; m < e; ++m) {
-                const float4 cj = __ldg(&a.sl4[m]);
-                const float dx = tx - cj.x, dy = ty - cj.y, dz = tz - cj.z;
-                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (r2 < a.R2f && __float_as_int(cj.w) != key) {
-                    if (cnt < v.cap) ta.tlist[(size_t)cnt * v.stride + k] = (unsigned short)(base + (m - b));
-                    else over = true;
-                    ++cnt;
-                }
-            }
-        };
-#pragma unroll 1
-        for (int r = 0; r < 9; ++r) {
-            const int dz = r / 3 - 1, dy = r - (r / 3) * 3 - 1;
-            int z = cz + dz, y = cy + dy;
-            float tz = me.z, ty = me.y;
-            if (z < 0) { z += nc; tz += fnc; } else if (z >= nc) { z -= nc; tz -= fnc; }
-            if (y < 0) { y += nc; ty += fnc; } else if (y >= nc) { y -= nc; ty -= fnc; }
-            const int rr = (z * nc + y) * nc;
-            const int xa = cx > 0 ? cx - 1 : 0, xb = cx < nc - 1 ? cx + 1 : nc - 1;
-            const int b = a.start[rr + xa];
-            scan(b, a.start[rr + xb + 1], t.off[3 * r] + (b - t.begin[3 * r]), me.x, ty, tz);
-            if (cx == 0) scan(a.start[rr + nc - 1], a.start[rr + nc], t.off[3 * r + 1], me.x + fnc, ty, tz);
-            else if (cx == nc - 1) scan(a.start[rr], a.start[rr + 1], t.off[3 * r + 2], me.x - fnc, ty, tz);
-        }
-        v.nlist[k] = cnt < v.cap ? cnt : v.cap;
-        if (over) v.flags[1] = 1;
-    }
-}
-
-template <int POT>
-__global__ void __launch_bounds__(128) tile_force_kernel(const CellPairArgs a, const VerletArgs v, const TileArgs ta, double scale,
-                                                         const double *__restrict__ mass, int mstride,
-                                                         const double *__restrict__ charge, int lo, int hi,
-                                                         double *__restrict__ acc, int64_t ld, int accumulate)
-{
-    extern __shared__ __align__(16) double tile_sm[];
-    __shared__ TileTable t;
-    if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
-    tile_setup(a, ta, &t);
-    if (t.total > kTileCap) return;
-    double *sx = tile_sm, *sy = tile_sm + kTileCap, *sz = tile_sm + 2 * kTileCap, *sw = tile_sm + 3 * kTileCap;
-    for (int q = 0; q < 27; ++q) {
-        const int b = t.begin[q], len = t.end[q] - b, off = t.off[q];
-        for (int idx = threadIdx.x; idx < len; idx += 128) {
-            const double4 p = load_rec(a.sp4 + b + idx);
-            sx[off + idx] = p.x; sy[off + idx] = p.y; sz[off + idx] = p.z;
-            if (POT == 1) sw[off + idx] = p.w;
-        }
-    }
-    __syncthreads();
-    for (int k = t.tb + threadIdx.x; k < t.te; k += 128) {
-        const int i = a.sorted_idx[k];
-        if (i < lo || i >= hi) continue;
-        const double4 pi = a.sp4[k];
-        const int cnt = v.nlist[k];
-        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-        auto pair = [&](int s) {
-            double rx = __dsub_rn(pi.x, sx[s]), ry = __dsub_rn(pi.y, sy[s]), rz = __dsub_rn(pi.z, sz[s]);
-            const int hx = __double2hiint(rx) & 0x7fffffff, hy = __double2hiint(ry) & 0x7fffffff,
-                      hz = __double2hiint(rz) & 0x7fffffff;
-            if (max(hx, max(hy, hz)) >= a.hi_radius) {
-                rx = wrap_cubic(rx, a.radius, a.L);
-                ry = wrap_cubic(ry, a.radius, a.L);
-                rz = wrap_cubic(rz, a.radius, a.L);
-            }
-            const double r2 = r2_unfused(rx, ry, rz);
-            if (__double_as_longlong(r2) < __double_as_longlong(a.R2)) {
-                double f;
-                if (POT == 0) {
-                    const double inv = rcp_fast(r2);
-                    const double qq = a.sigma2 * inv;
-                    const double s6 = qq * qq * qq;
-                    f = (s6 * inv) * fma(2.0, s6, -1.0);
-                } else {
-                    f = w_rinv3(r2, sw[s]);
-                }
-                f0 = fma(f, rx, f0);
-                f1 = fma(f, ry, f1);
-                f2 = fma(f, rz, f2);
-            }
-        };
-        // the 16-bit entries stream from DRAM: eight of them are in flight ahead of the batch being evaluated
-        const unsigned short *lp = ta.tlist + k;
-        int s0[4], s1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) s0[u] = u < cnt ? lp[(size_t)u * v.stride] : 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) s1[u] = 4 + u < cnt ? lp[(size_t)(4 + u) * v.stride] : 0;
-        for (int e = 0; e < cnt; e += 4) {
-            int s2[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s2[u] = e + 8 + u < cnt ? lp[(size_t)(e + 8 + u) * v.stride] : 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (e + u < cnt) pair(s0[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { s0[u] = s1[u]; s1[u] = s2[u]; }
-        }
-        double coeff = scale / mass[(size_t)i * mstride];
-        if (POT == 1) coeff *= charge[i];
-        if (accumulate) {
-            acc[i] += coeff * f0; acc[ld + i] += coeff * f1; acc[2 * ld + i] += coeff * f2;
-        } else {
-            acc[i] = coeff * f0; acc[ld + i] = coeff * f1; acc[2 * ld + i] = coeff * f2;
-        }
-    }
-}
-
 // Position update of velocity Verlet fused with the two O(N) passes the lists need on every evaluation: the
 // displacement check against the build-time positions (-> rebuild request) and the refresh of the cell-order record
 // (through the inverse permutation slot_of).  Same arithmetic as vv_pos_kernel / verlet_check_kernel /
@@ -988,13 +805,8 @@ __global__ void cond_set_kernel(cudaGraphConditionalHandle h, const int *__restr
     cudaGraphSetConditional(h, flag[0] != 0 ? 1u : 0u);
 }
 
-struct CondScope {
-    bool active = false;
-    cudaStream_t saved = nullptr;
-};
-
 // From here to cond_scope_end the launches on c->stream land in the IF node's body graph.  No-op outside a capture.
-static int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
+int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
 {
     sc->active = false;
     if (!c->cond_capture || c->cond_fail || !c->aux_stream) return NBX_OK;
@@ -1030,7 +842,7 @@ static int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
     return NBX_OK;
 }
 
-static int cond_scope_end(nbx_ctx *c, CondScope *sc)
+int cond_scope_end(nbx_ctx *c, CondScope *sc)
 {
     if (!sc->active) return NBX_OK;
     sc->active = false;
@@ -1134,20 +946,8 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     const double expect = (double)nplan / (L * L * L) * 4.18879020478639 * (R + skin) * (R + skin) * (R + skin);
     int cap = (int)(1.5 * expect) + 24;
     if (cap > ni - 1) cap = ni > 1 ? ni - 1 : 1;
-    // tile kernels (lists of shared-memory indices): whole system in one context, big enough to fill the machine
-    TileArgs ta{};
-    {
-        const double mean = (double)nplan / (double)cl->grid.ncell;
-        int W = (int)(112.0 / (mean > 0.25 ? mean : 0.25));
-        if (W > cl->grid.nc[0]) W = cl->grid.nc[0];
-        while (W > 1 && 9.0 * (W + 2) * mean * 1.6 > (double)kTileCap) --W;
-        if (W < 1) W = 1;
-        ta.W = W;
-        ta.chunks = (cl->grid.nc[0] + W - 1) / W;
-    }
-    const bool tiles = c->opt_tiles && !slabv && n >= c->tiles_min_n && 9.0 * 3.0 * (double)nplan / (double)cl->grid.ncell * 1.2 < (double)kTileCap;
     const bool same = cl->v_valid && cl->v_n == n && (slabv || cl->v_px == px) && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
-                      cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap && cl->v_tiles == tiles;
+                      cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap;
     if (!same) {
         if (cl->v_cap_alloc < (int64_t)cap * cl->cap_n) {
             NBX_TRY(dev_alloc(c, &cl->v_list, (size_t)cap * (size_t)cl->cap_n));
@@ -1158,11 +958,6 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
             NBX_TRY(dev_alloc(c, &cl->v_nlist, (size_t)cl->cap_n));
             cl->v_ref_n = cl->cap_n;
         }
-        if (tiles && cl->t_cap_alloc < (int64_t)cap * cl->cap_n) {
-            NBX_TRY(dev_alloc(c, &cl->t_list, (size_t)cap * (size_t)cl->cap_n));
-            cl->t_cap_alloc = (int64_t)cap * cl->cap_n;
-        }
-        cl->v_tiles = tiles;
         if (!cl->v_flags) NBX_TRY(dev_alloc(c, &cl->v_flags, (size_t)4));
         NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 0, sizeof(int) * 4, c->stream));
         NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream)); // [0] != 0: build now
@@ -1178,8 +973,10 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin));
         VerletArgs v{};
         v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = c->dyn;
-        if (c->slab.rebuild_now) {
-            NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream));
+        // phase 1 / 2 (slab_enqueue): the rebuild chain and the evaluation are enqueued separately, and whether the chain
+        // RUNS is decided on the device (slab.cond == v_flags: every kernel of it returns at once unless flags[0] is set)
+        if (c->slab.phase != 2 && c->slab.rebuild_now) {
+            if (!c->slab.cond) NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream));
             NBX_TRY(cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags));
             timer_begin(c, NBX_T_CELL_BUILD);
             verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
@@ -1187,6 +984,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
             timer_end(c, NBX_T_CELL_BUILD);
             c->slab.rebuild_now = false;
         }
+        if (c->slab.phase == 1) { NBX_CUDA(c, cudaGetLastError()); return NBX_OK; }
         timer_begin(c, NBX_T_CELL_BUILD);
         verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, c->dyn);
         timer_end(c, NBX_T_CELL_BUILD);
@@ -1217,18 +1015,9 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin)); // scan threshold of the list build
     VerletArgs v{};
     v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = nullptr;
-    v.consume = (pre && !tiles) ? 1 : 0;
-    ta.tlist = cl->t_list;
-    const unsigned tile_grid = (unsigned)(cl->grid.nc[0] * cl->grid.nc[0] * ta.chunks);
-    const size_t tile_smem = sizeof(double) * kTileCap * (pot == 0 ? 3 : 4);
-    if (tiles && !c->tiles_attr_set) {
-        NBX_CUDA(c, cudaFuncSetAttribute(tile_force_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTileCap * 3)));
-        NBX_CUDA(c, cudaFuncSetAttribute(tile_force_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTileCap * 4)));
-        c->tiles_attr_set = true;
-    }
+    v.consume = pre ? 1 : 0;
     timer_begin(c, NBX_T_CELL_BUILD);
-    if (tiles) tile_build_kernel<<<tile_grid, 128, 0, c->stream>>>(a, v, ta);
-    else verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
+    verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);
     verlet_ref_kernel<<<map_grid(c, ni, 256), 256, 0, c->stream>>>(px, ld, cl->v_ref, cl->cap_n, ni, cl->v_flags, nullptr);
     NBX_TRY(cond_scope_end(c, &scope));
     if (!v.consume) verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, nullptr);
@@ -1236,15 +1025,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     a = make_args(c, cl, R2);
     const int acc_flag = accumulate ? 1 : 0;
     timer_begin(c, NBX_T_PAIR_CELLS);
-    if (tiles) {
-        if (pot == 0)
-            tile_force_kernel<0><<<tile_grid, 128, tile_smem, c->stream>>>(a, v, ta, 24.0 * c->lj_eps, c->mass, mstride, c->charge,
-                                                                          (int)lo, (int)hi, acc_out, ld_out, acc_flag);
-        else
-            tile_force_kernel<1><<<tile_grid, 128, tile_smem, c->stream>>>(a, v, ta, c->el_k, c->mass, 1, c->charge, (int)lo,
-                                                                          (int)hi, acc_out, ld_out, acc_flag);
-    }
-    else if (pot == 0) launch_verlet_force<0>(c, a, v, 24.0 * c->lj_eps, mstride, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
+    if (pot == 0) launch_verlet_force<0>(c, a, v, 24.0 * c->lj_eps, mstride, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
     else launch_verlet_force<1>(c, a, v, c->el_k, 1, (int)lo, (int)hi, acc_out, ld_out, acc_flag);
     timer_end(c, NBX_T_PAIR_CELLS);
     NBX_CUDA(c, cudaGetLastError());
@@ -1350,8 +1131,6 @@ int cells_neighbors(nbx_ctx *c, CellList *cl, const double *px, int64_t n, int64
 
 void cells_free(CellList *cl)
 {
-    cudaFree(cl->t_list);
-    cl->t_list = nullptr; cl->t_cap_alloc = 0;
     cudaFree(cl->cell_of); cudaFree(cl->count); cudaFree(cl->start); cudaFree(cl->sums);
     cudaFree(cl->arrival); cudaFree(cl->tmp_idx); cudaFree(cl->tmp_key);
     cudaFree(cl->v_list); cudaFree(cl->v_nlist); cudaFree(cl->v_ref); cudaFree(cl->v_flags);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nbody_b200.h"
@@ -58,34 +59,6 @@ struct CellList {
     const double *v_px = nullptr;
     double v_R = 0, v_skin = 0, v_L = 0;
     int v_key_div = 0, v_nc = 0, v_cap = 0;
-    // tile kernels (nbx_cells.cu): the same lists as 16-bit indices into a CTA's shared-memory staging area
-    unsigned short *t_list = nullptr;
-    int64_t t_cap_alloc = 0;
-    bool v_tiles = false;
-};
-
-// Fused cutoff step (nbx_fused.cu): the state in padded cell order ("slots"), cluster lists, device flags
-struct FusedState {
-    bool disabled = false;     // a list overflowed once: the context stays on the unfused path
-    int C = 0;                 // cluster size the buffers were laid out for
-    int64_t n = 0, ncell = 0;  // system / grid the buffers were sized for
-    int64_t cap_slots = 0;     // bound on the padded slot count (multiple of 128)
-    int cap_e = 0;             // list entries per slot
-    double4 *x[2] = {nullptr, nullptr}; // [cap_slots] x, y, z (unwrapped), w = charge; read/write alternate every step
-    double4 *vm = nullptr;     // [cap_slots] vx, vy, vz, mass
-    double *sa = nullptr;      // [3][cap_slots] acceleration
-    double *ref = nullptr;     // [3][cap_slots] positions the lists were built from
-    float4 *sl = nullptr;      // [cap_slots] wrapped coordinates in cell units + exclusion key (list build prefilter)
-    int *pid = nullptr;        // [cap_slots] particle index of a slot, -1: padding
-    int *scell = nullptr;      // [cap_slots] cell of a slot
-    int *cell_of = nullptr, *arrival = nullptr, *tmp_idx = nullptr; // [n]
-    int *count = nullptr, *start = nullptr, *sums = nullptr;        // [ncell + 1] members / padded starts / scan scratch
-    int *list = nullptr;       // [cap_e][cap_slots]
-    int *nlist = nullptr;      // [cap_slots]
-    int *flags = nullptr;      // [16] device flags (nbx_fused.cu)
-    double *partial = nullptr; // [cap_slots / 128] block partials of sum m v^2, then the sums of groups of blocks
-    int *gcount = nullptr;     // arrivals per group
-    int64_t steps_total = 0, rebuilds_total = 0; // diagnostics (nbx_get_info "fused_steps", "verlet_rebuilds")
 };
 
 // slab decomposition state (nbx_slab.cu)
@@ -113,6 +86,44 @@ struct SlabState {
     bool rebuild_now = true;   // the host's decision for the next force evaluation (set after a migration round)
     bool record_halo = false;  // the next pack records the halo index lists (second round of a rebuild)
     int *halo_idx[2] = {nullptr, nullptr}; // [capH] local indices of the own boundary-layer particles, message order
+    // nbx_step_vv on a slab (slab_run): the rebuild decision is taken on the device (peer-memory all-reduce of the
+    // displacement flags), so a step is one fixed launch sequence -- capturable, no host in the loop
+    int phase = 0;             // cells_pairs: 0 rebuild (if rebuild_now) + refresh + forces, 1 rebuild chain only, 2 refresh + forces only
+    const int *cond = nullptr; // device flag while slab_run enqueues: the rebuild chain runs iff cond[0] != 0, the halo refresh iff == 0
+    bool started = false;      // nbx_slab_start distributed the particles and built the first lists
+    bool scal0_global = true;  // d_scal[0] holds the sum over ALL ranks (after an upload / at the end of a run), not the local one
+};
+
+// Peer-memory communicator (nbx_multi.cu): every rank owns a small WINDOW in device memory that all ranks map (CUDA IPC
+// between processes, plain pointers + peer access inside one process).  Kernels post into the peers' windows with
+// system-scope stores and spin on their own window: scalar all-reduces, "positions of step k have landed" and "partial
+// accelerations of step k are complete" flags.  No collective library and no host in the loop.
+constexpr int kMaxRanks = 16;
+constexpr int kWinScal = 64;                        // [2 parities][kMaxRanks][4] doubles: seq, v0, v1, v2
+constexpr int kWinPos = kWinScal + 2 * kMaxRanks * 4;  // [kMaxRanks] int64: positions of sequence number s have landed
+constexpr int kWinAcc = kWinPos + kMaxRanks;           // [kMaxRanks] int64: partial accelerations s are staged
+constexpr int kWinDoubles = kWinAcc + kMaxRanks + 32;
+enum { SEQ_SCAL = 0, SEQ_POS = 1, SEQ_ACC = 2, SEQ_TICKET = 3, SEQ_TIMEOUT = 4, SEQ_TICKET2 = 5, SEQ_N = 8 };
+
+struct CommDev { // what the kernels need (passed by value)
+    double *win[kMaxRanks];
+    int rank, nranks;
+    int *seq; // device counters [SEQ_N]
+};
+
+struct Comm {
+    bool on = false;
+    int rank = 0, nranks = 1;
+    double *win = nullptr;                 // own window [kWinDoubles]
+    double *peer_win[kMaxRanks] = {};      // every rank's window (own included)
+    double *peer_pos[kMaxRanks] = {};      // every rank's SoA position rows (all-pairs modes: push all-gather)
+    double *stage = nullptr;               // [nranks][3][per] partial accelerations pushed by the peers (pair sharding)
+    double *peer_stage[kMaxRanks] = {};
+    int64_t per = 0, stage_doubles = 0;    // block size of the partition (equal blocks, the last may be short)
+    int *d_seq = nullptr;
+    std::vector<void *> ipc_opened;
+    int mode = 0;                          // 0 none, 1 pair sharding, 2 target blocks, 3 slabs
+    bool pos_global = true;                // every rank holds all positions (after an upload)
 };
 
 } // namespace nbx
@@ -162,6 +173,23 @@ struct nbx_ctx {
     int64_t tgt_lo = 0, tgt_hi = 0;
     int *gid = nullptr;        // slab decomposition: global particle id per local column (nullptr: identity)
     nbx::SlabState slab;
+    nbx::Comm comm;
+    // single-process group (nbx_create_multi): the leader holds no state of its own, calls fan out over the members
+    bool is_group = false;
+    std::vector<nbx_ctx *> members;
+    nbx_ctx *leader = nullptr;
+    std::vector<double> g_m, g_q, g_mm;  // leader: the system description (a re-upload rebuilds the members' systems)
+    int g_water = 0;
+    bool g_ready = false;                // leader: the members are initialised, connected and started
+    int opt_group_mode = 0;              // 0: chosen from the potentials, 1 pairs, 2 targets, 3 slabs
+    // CUDA graph of two velocity-Verlet steps of the distributed loops (nbx_multi.cu / slab_run), kept across calls
+    cudaGraphExec_t mg_exec = nullptr;
+    double mg_dt = 0.0;
+    double *mg_acc0 = nullptr;
+    int mg_kind = 0;
+    // pinned-host registration cache (option "pin_host"): caller buffers seen by nbx_accel are page-locked once
+    int opt_pin_host = 0;
+    std::vector<std::pair<const void *, size_t>> pinned;
     // slab mode: the particle counts live on the device ([0] own, [1] ghosts) so that a step needs no host
     // round trip; n / tgt_hi then are launch BOUNDS and every kernel clamps to the device counts
     const int *dyn = nullptr;
@@ -182,10 +210,6 @@ struct nbx_ctx {
     int opt_prefilter = 1;
     int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
-    // list kernel over shared-memory staged candidate rows (tile_force_kernel, nbx_cells.cu).  OFF by default: bit-identical
-    // to verlet_force_kernel but measured 0.44 ms against 0.21 ms at 1,048,576 argon atoms (r01c) -- the staging area
-    // limits the SM to 16-24 warps and the 8-byte shared gathers conflict 3-fold; kept as a tested option ("tiles").
-    int opt_tiles = 0;
     // CUDA graph of nbx_step_vv: the conditional rebuild chain (nine launches that return at once) becomes the body of
     // an IF node decided by one single-thread kernel (cudaGraphSetConditional); falls back to plain capture if the
     // runtime refuses
@@ -193,18 +217,7 @@ struct nbx_ctx {
     bool cond_capture = false, cond_fail = false;
     cudaStream_t aux_stream = nullptr;
     int opt_fuse_update = 1;       // nbx_step_vv: position update + displacement check + record refresh in one kernel
-    int64_t tiles_min_n = 200000;
-    bool tiles_attr_set = false;
     int opt_verlet_lanes = 0;      // lanes per target of the Verlet force kernel (0: chosen from the system size; 1, 2, 4, 8)
-    // nbx_step_vv: one fused kernel per step for single cutoff potentials (nbx_fused.cu).  OFF by default: measured on
-    // B200 at 1,048,576 argon atoms the fused step costs the SUM of its parts (0.36 ms vs 0.285 ms unfused, r01c):
-    // force loop and per-slot update wait on the same L1/LSU path, so fusing them hides nothing, and cluster lists
-    // (C > 1) pay more in issue slots than they save in gathers.  Kept as a tested option ("fused_step").
-    int opt_fused = 0;
-    int opt_fused_debug = 0;       // test hook: bit 2 = build the cluster lists only (tests/test_gpu_fused.py)
-    int opt_fused_cluster = 4;     // slots per cluster (1, 2, 4 or 8)
-    int64_t fused_min_steps = 16;  // shorter runs stay on the unfused path (every fused run starts with a list build)
-    nbx::FusedState fz;
     int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
     int64_t sym_min_n = 8192;
     int opt_sym_variant = 0;
@@ -289,10 +302,6 @@ int analysis_rdf_add(nbx_ctx *c, const double *u_host);
 int analysis_rdf_get(nbx_ctx *c, int64_t *hist, int64_t cap, int64_t *frames);
 int analysis_msd(nbx_ctx *c, const double *u0_host, const double *u_host, double *out);
 void analysis_free(nbx_ctx *c);
-// nbx_fused.cu
-bool fused_eligible(nbx_ctx *c, int64_t nsteps);
-int fused_run(nbx_ctx *c, double dt, int64_t nsteps, int64_t *steps_done); // *steps_done < nsteps: continue unfused, positions already advanced
-void fused_free(nbx_ctx *c);
 // nbx_slab.cu
 int slab_init(nbx_ctx *c, int rank, int nranks);
 int slab_pack(nbx_ctx *c);
@@ -303,6 +312,38 @@ int slab_refresh_send(nbx_ctx *c);
 int slab_refresh_recv(nbx_ctx *c);
 int slab_verlet_check(nbx_ctx *c, double soft_fraction, int *out2_dev, double *out2_dbl);
 void slab_free(nbx_ctx *c);
+int slab_start(nbx_ctx *c);
+int slab_enqueue(nbx_ctx *c, double dt, int64_t nsteps); // nbx_step_vv of a slab: enqueues, does not synchronise
+int slab_finish(nbx_ctx *c);
+// nbx_multi.cu
+CommDev comm_dev(const nbx_ctx *c);
+int comm_allreduce3(nbx_ctx *c, const double *in3, int in0_rank0_only, double *out3, int *flag_out);
+int comm_alloc(nbx_ctx *c);
+void comm_free(nbx_ctx *c);
+int multi_enqueue_vv(nbx_ctx *c, double dt, int64_t nsteps);
+int multi_enqueue_em(nbx_ctx *c, double dt, int64_t nsteps);
+int multi_finish(nbx_ctx *c);
+int multi_accel_enqueue(nbx_ctx *c, const double *u, const double *v);
+int multi_accel_finish(nbx_ctx *c, double *dv);
+int group_init(nbx_ctx *c, int rank, int nranks, int mode);
+int group_export(nbx_ctx *c, int kind, void **ptr, void *handle64);
+int group_connect(nbx_ctx *c, const void *handles, void *const *ptrs);
+int group_start(nbx_ctx *c);
+// nbx_group.cu: the leader of a single-process group (nbx_create_multi)
+int leader_create(nbx_ctx **out, int ndev, const int *devs);
+int leader_destroy(nbx_ctx *c);
+int leader_system(nbx_ctx *c, int64_t n, const double *m, const double *q, const double *mm, int water);
+int leader_upload(nbx_ctx *c, const double *u, const double *v);
+int leader_accel(nbx_ctx *c, const double *u, double *v, double *dv);
+int leader_step_vv(nbx_ctx *c, double dt, int64_t nsteps);
+int leader_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed);
+int leader_download(nbx_ctx *c, double *u, double *v, double *dv);
+int leader_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature);
+void graph_drop(nbx_ctx *c);
+// nbx_cells.cu: the launches between begin and end become the body of a graph IF node on flag[0] while capturing
+struct CondScope { bool active = false; cudaStream_t saved = nullptr; };
+int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc);
+int cond_scope_end(nbx_ctx *c, CondScope *sc);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);
 // nbx_integrate.cu

@@ -84,11 +84,14 @@ __device__ __forceinline__ unsigned slab_classify(double x, const SlabGeom &g)
     return (1u << CAT_MIGR) | (dr > g.wR ? 256u : 0u);
 }
 
+// cond (all kernels of the migration round): run iff cond == nullptr or cond[0] != 0 -- the collective rebuild decision taken
+// on the device (slab_enqueue); skip (the halo refresh kernels): return iff skip && skip[0] != 0
 __global__ void __launch_bounds__(kSlabBlock) slab_count_kernel(const double *__restrict__ px, int n, SlabGeom g,
                                                                 int *__restrict__ blockcnt, int *__restrict__ dn,
-                                                                const int *__restrict__ dyn)
+                                                                const int *__restrict__ dyn, const int *__restrict__ cond)
 {
     __shared__ int cnt[CAT_N];
+    if (cond && !cond[0]) return;
     n = dyn_own(dyn, n);
     if (threadIdx.x < CAT_N) cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -106,8 +109,9 @@ __global__ void __launch_bounds__(kSlabBlock) slab_count_kernel(const double *__
 
 // exclusive scan over the blocks, one warp per category; totals -> counts[0..4]
 __global__ void slab_scan_kernel(const int *__restrict__ blockcnt, int *__restrict__ blockoff, int nb,
-                                 int *__restrict__ counts)
+                                 int *__restrict__ counts, const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return;
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= CAT_N) return;
     int carry = 0;
@@ -144,10 +148,12 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
                                                                double *__restrict__ sendR, int capM, int capH,
                                                                int *__restrict__ dn, const int *__restrict__ dyn,
                                                                double *peerL, double *peerR, int64_t msg_doubles,
-                                                               int *__restrict__ halo_idxL, int *__restrict__ halo_idxR)
+                                                               int *__restrict__ halo_idxL, int *__restrict__ halo_idxR,
+                                                               const int *__restrict__ cond)
 {
     __shared__ int wcnt[kSlabBlock / 32][CAT_N];
     __shared__ int last_block;
+    if (cond && !cond[0]) return;
     n = dyn_own(dyn, n);
     const int msg = dn[DN_MSG] + 1; // number of the message this kernel produces (the last block publishes it)
     double *remL = peerL ? rx_msg(peerL, 1, msg & 1, msg_doubles) : nullptr;
@@ -261,9 +267,10 @@ __global__ void __launch_bounds__(kSlabBlock) slab_halo_send_kernel(SlabArrays s
                                                                     const int *__restrict__ idxR, int *__restrict__ dn,
                                                                     double *__restrict__ sendL, double *__restrict__ sendR,
                                                                     int capM, int capH, double *peerL, double *peerR,
-                                                                    int64_t msg_doubles)
+                                                                    int64_t msg_doubles, const int *__restrict__ skip)
 {
     __shared__ int last_block;
+    if (skip && skip[0]) return;
     const int msg = dn[DN_MSG] + 1;
     double *outL = peerL ? rx_msg(peerL, 1, msg & 1, msg_doubles) : sendL;
     double *outR = peerR ? rx_msg(peerR, 0, msg & 1, msg_doubles) : sendR;
@@ -296,8 +303,9 @@ __global__ void __launch_bounds__(kSlabBlock) slab_halo_send_kernel(SlabArrays s
 
 // the ghost slots were laid down by the rebuild's unpack: halos from the left, then from the right, after the own
 __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restrict__ dn, double *rx, int64_t msg_doubles,
-                                      int direct, int capM, int capH)
+                                      int direct, int capM, int capH, const int *__restrict__ skip)
 {
+    if (skip && skip[0]) return;
     const int msg = dn[DN_MSG];
     if (direct && !slab_wait_messages(rx, msg)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) dn[DN_TIMEOUT] = 1;
@@ -342,8 +350,9 @@ __global__ void slab_verlet_check_kernel(const double *__restrict__ px, int64_t 
 __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
                                    int *__restrict__ dn, const double *__restrict__ sendL,
                                    const double *__restrict__ sendR, double *rx, int64_t msg_doubles, int direct,
-                                   int capM, int capH)
+                                   int capM, int capH, const int *__restrict__ cond)
 {
+    if (cond && !cond[0]) return;
     // direct mode: the neighbours store into this rank's receive area and raise its flags (message number)
     const int msg = dn[DN_MSG];
     if (direct && !slab_wait_messages(rx, msg)) {
@@ -444,12 +453,13 @@ static int run_pack(nbx_ctx *c, int init)
     int *gid_dst = c->gid == s.gid_a ? s.gid_b : s.gid_a;
     const SlabArrays src = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     const SlabArrays dst = arrays(s.pos2, s.vel2, s.acc2, s.mass2, c->charge ? s.charge2 : nullptr, gid_dst);
-    slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_n, dyn);
-    slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts);
+    slab_count_kernel<<<nb, kSlabBlock, 0, c->stream>>>(c->pos, n, g, s.blockcnt, s.d_n, dyn, s.cond);
+    slab_scan_kernel<<<1, 32 * CAT_N, 0, c->stream>>>(s.blockcnt, s.blockoff, nb, s.d_counts, s.cond);
     slab_pack_kernel<<<nb, kSlabBlock, 0, c->stream>>>(src, dst, c->npad, n, g, s.blockoff, s.d_counts, s.msg[0], s.msg[1],
                                                       (int)s.capM, (int)s.capH, s.d_n, dyn, s.direct ? s.peer[0] : nullptr,
                                                       s.direct ? s.peer[1] : nullptr, s.msg_doubles,
-                                                      s.record_halo ? s.halo_idx[0] : nullptr, s.record_halo ? s.halo_idx[1] : nullptr);
+                                                      s.record_halo ? s.halo_idx[0] : nullptr, s.record_halo ? s.halo_idx[1] : nullptr,
+                                                      s.cond);
     NBX_CUDA(c, cudaGetLastError());
     s.record_halo = false;
     // the compacted state is the state from here on (stream-ordered: later kernels see the new pointers)
@@ -595,7 +605,7 @@ int slab_refresh_send(nbx_ctx *c)
     const SlabArrays src = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_halo_send_kernel<<<(unsigned)((threads + kSlabBlock - 1) / kSlabBlock), kSlabBlock, 0, c->stream>>>(
         src, c->npad, s.halo_idx[0], s.halo_idx[1], s.d_n, s.msg[0], s.msg[1], (int)s.capM, (int)s.capH,
-        s.direct ? s.peer[0] : nullptr, s.direct ? s.peer[1] : nullptr, s.msg_doubles);
+        s.direct ? s.peer[0] : nullptr, s.direct ? s.peer[1] : nullptr, s.msg_doubles, s.cond);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = true;
     return NBX_OK;
@@ -608,7 +618,7 @@ int slab_refresh_recv(nbx_ctx *c)
     const int64_t threads = 2 * s.capH;
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_halo_recv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.d_n, s.rx, s.msg_doubles,
-                                                                                  s.direct ? 1 : 0, (int)s.capM, (int)s.capH);
+                                                                                  s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return NBX_OK;
@@ -671,10 +681,125 @@ int slab_unpack(nbx_ctx *c, int64_t *out)
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.cap_loc, s.d_counts, s.d_n,
                                                                               s.msg[0], s.msg[1], s.rx, s.msg_doubles,
-                                                                              s.direct ? 1 : 0, (int)s.capM, (int)s.capH);
+                                                                              s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return out ? slab_check(c, out) : NBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the slab step loop behind nbx_step_vv: no host decision, no collective library
+// ------------------------------------------------------------------------------------------------
+int compute_pairs(nbx_ctx *c); // nbx_api.cu
+
+// Initial distribution: the first pack selects the own particles out of the full upload, the neighbours' messages lay the
+// ghosts down; with Verlet lists a second round records the halo index lists and the lists are built from the
+// distributed positions right away.  Enqueues only (the kernels wait for the neighbours on the device): synchronise
+// with nbx_slab_check once every rank has made the call.
+int slab_start(nbx_ctx *c)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.first) return fail(c, NBX_ERR_INVALID, "nbx_group_start: the slab was started already");
+    if (s.nranks > 1 && !s.direct) return fail(c, NBX_ERR_INVALID, "nbx_group_start: connect the neighbours first (nbx_group_connect)");
+    NBX_TRY(slab_pack(c));
+    NBX_TRY(slab_unpack(c, nullptr));
+    if (s.verlet) {
+        s.record_halo = true;
+        NBX_TRY(slab_pack(c));
+        NBX_TRY(slab_unpack(c, nullptr));
+        s.rebuild_now = true;
+        std::swap(c->acc, c->acc_old); // cells and lists get built, a(t) stays what it is
+        const int rc = compute_pairs(c);
+        std::swap(c->acc, c->acc_old);
+        if (rc != NBX_OK) return rc;
+    }
+    if (c->T_slot != 12) { // the sum of the upload is the global one
+        NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 12, c->d_scal, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        c->T_slot = 12;
+    }
+    s.scal0_global = true;
+    s.started = true;
+    return NBX_OK;
+}
+
+// One velocity-Verlet step of the slab as a fixed launch sequence.  With Verlet lists: position update, displacement
+// check against the build-time positions, ONE peer-memory all-reduce of (sum m v^2, moved-too-far flags) that every rank
+// evaluates identically; the migration + halo-recording rounds and the cell / list rebuild run iff the reduced flag is
+// set (each kernel of the chain returns at once otherwise; while a graph is captured the chain is the body of an IF
+// node), the plain halo refresh iff it is not.  Same criterion, same step as a single context: with the bit-identical
+// cell order (ranked by global id) the trajectory IS the single-context trajectory.
+static int slab_one_step(nbx_ctx *c, double dt)
+{
+    SlabState &s = c->slab;
+    CellList *cl = c->has_lj ? &c->cl_lj : &c->cl_el;
+    const bool needT = c->thermo == NBX_THERMO_BERENDSEN;
+    NBX_TRY(launch_vv_pos(c, dt));
+    NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
+    if (s.verlet) {
+        NBX_TRY(slab_verlet_check(c, 1.0, nullptr, c->d_scal + 13));
+        NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, cl->v_flags));
+        s.scal0_global = false;
+        s.cond = cl->v_flags;
+        CondScope scope;
+        NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope));
+        int rc = slab_pack(c);                         // migration round
+        if (rc == NBX_OK) rc = slab_unpack(c, nullptr);
+        s.record_halo = true;                          // halo round incl. the arrivals, remembered
+        if (rc == NBX_OK) rc = slab_pack(c);
+        if (rc == NBX_OK) rc = slab_unpack(c, nullptr);
+        s.rebuild_now = true;
+        s.phase = 1;                                   // cells + lists, no evaluation
+        if (rc == NBX_OK) { std::swap(c->acc, c->acc_old); rc = compute_pairs(c); std::swap(c->acc, c->acc_old); }
+        s.phase = 0;
+        const int rc2 = cond_scope_end(c, &scope);
+        if (rc != NBX_OK || rc2 != NBX_OK) { s.cond = nullptr; return rc != NBX_OK ? rc : rc2; }
+        rc = slab_refresh_send(c);                     // (skipped on the device when the rebuild ran)
+        if (rc == NBX_OK) rc = slab_refresh_recv(c);
+        s.cond = nullptr;
+        NBX_TRY(rc);
+        s.phase = 2;
+    } else {
+        if (needT) { NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, nullptr)); s.scal0_global = false; }
+        NBX_TRY(slab_pack(c));
+        NBX_TRY(slab_unpack(c, nullptr));
+    }
+    std::swap(c->acc, c->acc_old);
+    const int rc = compute_pairs(c);
+    s.phase = 0;
+    NBX_TRY(rc);
+    return launch_vv_vel(c, dt, true);
+}
+
+} // namespace nbx
+
+#include "nbx_graph.inl"
+
+namespace nbx {
+
+int slab_enqueue(nbx_ctx *c, double dt, int64_t nsteps)
+{
+    SlabState &s = c->slab;
+    if (!s.on || !s.started) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: start the slab decomposition first (nbx_group_start)");
+    if (s.packed) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: a pack is waiting for nbx_slab_unpack");
+    if (s.nranks > 1 && !s.direct) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: the slabs are not connected (nbx_group_connect); drive the exchange from the host");
+    if (c->thermo == NBX_THERMO_ANDERSEN || c->thermo == NBX_THERMO_LANGEVIN || c->thermo == NBX_THERMO_NOSEHOOVER)
+        return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: slabs run NVE or with the Berendsen thermostat");
+    NBX_TRY(steps_graphed(c, 13, dt, nsteps, true, [&]() { return slab_one_step(c, dt); }));
+    // leave the scalar block as a single context does: [0] = the sum over all ranks
+    NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
+    NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, nullptr));
+    NBX_CUDA(c, cudaMemcpyAsync(c->d_scal, c->d_scal + 12, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    s.scal0_global = true;
+    return NBX_OK;
+}
+
+int slab_finish(nbx_ctx *c)
+{
+    NBX_TRY(slab_check(c, nullptr));
+    int h[SEQ_N] = {0};
+    if (c->comm.d_seq) NBX_CUDA(c, cudaMemcpy(h, c->comm.d_seq, sizeof h, cudaMemcpyDeviceToHost));
+    if (h[SEQ_TIMEOUT]) return fail(c, NBX_ERR_CUDA, "slab step: timed out waiting for a peer's flags (a rank did not make the same call?)");
+    return NBX_OK;
 }
 
 } // namespace nbx

@@ -532,6 +532,45 @@ class SlabStepper:
         return out
 
 
+def join_group_local(contexts, mode=0):
+    """Join single-GPU contexts of THIS process into one group (what nbx_create_multi does inside the library; the tests
+    use it to drive every member from its own thread).  Every context holds the full uploaded system."""
+    world = len(contexts)
+    for r, ctx in enumerate(contexts):
+        ctx.group_init(r, world, mode)
+    ptrs = [ctx.group_export(want_handles=False)[0] for ctx in contexts]
+    for ctx in contexts:
+        ctx.group_connect(ptrs=ptrs)
+    for ctx in contexts:
+        ctx.group_start()
+    for ctx in contexts:
+        if ctx.info("group_mode") == 3:
+            ctx.slab_check()
+        else:
+            ctx.synchronize()
+
+
+def join_group_dist(ctx, group=None, mode=0):
+    """Join the contexts of a torch.distributed process group (one process per GPU) into one libnbody_b200 group:
+    torch.distributed only carries the CUDA IPC handles (bootstrap) -- afterwards nbx_accel / nbx_step_vv / nbx_step_em
+    exchange everything device to device over NVLink peer memory, with no collective library call per step."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ctx.group_init(rank, world, mode)
+    _, blob = ctx.group_export(want_handles=True)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob, group=group)
+    ctx.group_connect(handles=b"".join(blobs))
+    dist.barrier(group=group)   # every window is mapped before anyone stores into one
+    ctx.group_start()
+    if ctx.info("group_mode") == 3:
+        ctx.slab_check()
+    else:
+        ctx.synchronize()
+    dist.barrier(group=group)
+
+
 def numpy_reference_partition_check(n, world, multiple=1):
     """All ranks' ranges tile [0, n) exactly (host-logic self check used by the CPU tests)."""
     covered = np.zeros(n, dtype=np.int32)

@@ -16,7 +16,7 @@ for skin in (100, 70, 50, 35):
     ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
     ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 10 * w["dt"], w["kB"], n, 0)
     ctx.set_stream(side.cuda_stream)
-    ctx.set_option("fused_step", 0); ctx.set_option("verlet_skin_permille", skin)
+    ctx.set_option("verlet_skin_permille", skin)
     ctx.upload(u, w["v"])
     ctx.step_vv(w["dt"], 300)
     r0 = ctx.info("verlet_rebuilds")

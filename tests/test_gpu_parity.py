@@ -402,34 +402,6 @@ def test_verlet_force_lanes_per_target(oracle, lanes):
     ctx.close()
 
 
-@pytest.mark.parametrize("cells,drift", [(6, False), (8, True), (16, False)])
-def test_tile_list_kernels_are_bit_identical_to_the_list_kernels(oracle, cells, drift):
-    """The tile kernels (a CTA stages its candidate rows in shared memory, the lists hold 16-bit staging indices)
-    produce the same entries in the same order and apply the same arithmetic as verlet_build_slot /
-    verlet_force_kernel: accelerations and an 80-step hot trajectory (several on-device rebuilds) are equal bit for bit,
-    and both equal the oracle.  4 cells per dimension (every cell touches the periodic faces), drifted coordinates,
-    and 11 cells per dimension (several CTAs per x-row)."""
-    w, u = _fcc(cells, 0.05, 37, drift)
-    v = F(3.0 * w["v"])
-    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
-    out = {}
-    for tiles in (0, 1):
-        ctx = make_context(spec)
-        ctx.set_option("tiles", tiles)
-        ctx.set_option("tiles_min_n", 0)
-        ctx.set_option("verlet_lanes", 1)
-        a0 = ctx.accel(u).copy()
-        assert ctx.info("tiles_lj") == tiles and ctx.info("verlet_overflow") == 0
-        ctx.upload(u, v)
-        ctx.step_vv(2e-3, 80)
-        out[tiles] = (a0,) + tuple(ctx.download(want_dv=True))
-        assert ctx.info("verlet_rebuilds") >= 3 and ctx.info("verlet_overflow") == 0
-        ctx.close()
-    for a, b in zip(out[1], out[0]):
-        assert np.array_equal(a, b)
-    _check(out[1][0], make_oracle(oracle, spec).rhs(u, w["v"], NT))
-
-
 @pytest.mark.parametrize("thermo", [None, "berendsen"])
 def test_fused_position_update_is_bit_identical(oracle, thermo):
     """nbx_step_vv with one cutoff potential: the position update also checks the displacements and refreshes the
@@ -456,27 +428,6 @@ def test_fused_position_update_is_bit_identical(oracle, thermo):
     for key in ((1, 1), (1, 0)):
         for a, b in zip(out[key], out[(0, 1)]):
             assert np.array_equal(a, b)
-
-
-def test_tile_list_kernels_coulomb(oracle):
-    rng = np.random.Generator(np.random.Philox(53))
-    m, L = 16, 16.0
-    n = m ** 3
-    g = (np.arange(m) + 0.5) * (L / m)
-    u = F(np.stack(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1) + 0.1 * rng.standard_normal((3, n)))
-    qs = np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * (0.5 + rng.random(n))
-    spec = dict(ms=rng.random(n) + 1.0, qs=qs, bc=("cubic", L), coulomb=dict(k=0.7, R=2.4))  # 6 cells per dimension
-    res = []
-    for tiles in (0, 1):
-        ctx = make_context(spec)
-        ctx.set_option("tiles", tiles)
-        ctx.set_option("tiles_min_n", 0)
-        ctx.set_option("verlet_lanes", 1)
-        res.append(ctx.accel(u).copy())
-        assert ctx.info("tiles_el") == tiles
-        ctx.close()
-    assert np.array_equal(res[0], res[1])
-    _check(res[1], make_oracle(oracle, spec).rhs(u, np.zeros_like(u), NT))
 
 
 def test_lj_verlet_rhs_dropin_with_arbitrary_positions(oracle):
