@@ -300,7 +300,7 @@ NBX_API int nbx_timing_reset(nbx_ctx *ctx);
  *   all-pairs         : "symmetric_pairs" (1: Newton's-third-law kernel), "symmetric_min_n" (8192), "sym_variant" (0),
  *                       "uniform_weights" (0 forgets that all masses / charges are equal),
  *   slab driver       : "slab_record_halo", "slab_rebuild", "temperature_slot" (see the slab section above).
- * nbx_get_info keys: "n", "npad", "ncols", "water", "sm_count", "cells_lj", "cells_el", "verlet_lj", "verlet_el",
+ * nbx_get_info keys: "n", "npad", "ncols", "water", "sm_count", "thermostat", "cells_lj", "cells_el", "verlet_lj", "verlet_el",
  * "verlet_overflow", "verlet_rebuilds", "graph_if_nodes", "allpairs_grid", "allpairs_chunks", "slab_own", "slab_ghost", "slab_layer_lo", "slab_layer_hi",
  * "slab_layers", "slab_verlet", "group_mode", "group_rank", "group_size", "shard_lo", "shard_hi", "graph_cached". */
 NBX_API int nbx_set_option(nbx_ctx *ctx, const char *key, int64_t value);

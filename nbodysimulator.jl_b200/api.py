@@ -440,20 +440,29 @@ def get_accelerating_function(parameters: PotentialParameters, simulation: NBody
         raise TypeError("no B200 kernel for this PotentialParameters subtype; define its closure on the host "
                         "as in test/shared/custom_potential_body.jl")
     ctx = _configure_context(simulation, device, only=name)
-    cache = {"key": None, "dv": None, "last_i": -1}
+    cache = {"key": None, "dv": None, "last_i": -1, "sum": None}
+    n = ctx.n
 
     def acceleration(dv, u, v, t, i):
-        # a sweep visits i in ascending order (nbody_to_ode.jl:475): an index that does not increase,
-        # another array or another time starts a new sweep -> one device evaluation for all particles
-        key = (u.ctypes.data, float(t))
-        if cache["key"] != key or i <= cache["last_i"]:
-            cache["dv"] = ctx.accel(u)
+        # a sweep visits i in ascending order (nbody_to_ode.jl:475): an index that does not increase, another array,
+        # another time or other CONTENTS (a buffer mutated in place, or a freed one reused at the same address: a cheap
+        # checksum of the positions guards against serving stale columns) starts a new sweep -> one device evaluation
+        # for all particles.  With the Nose-Hoover thermostat the reference passes n + 1 columns (nbody_to_ode.jl:6-8):
+        # the potential closures only ever look at the first n.
+        key = (u.ctypes.data, float(t), u.shape[1])
+        if cache["key"] != key or i <= cache["last_i"] or cache["sum"] != float(u[:, :n].sum()):
+            cache["dv"] = ctx.accel(u[:, :n] if u.shape[1] != n else u)
             cache["key"] = key
+            cache["sum"] = float(u[:, :n].sum())
         cache["last_i"] = i
         dv += cache["dv"][:, i]
         return dv
 
+    def invalidate():
+        cache["key"] = None
+
     acceleration.context = ctx
+    acceleration.invalidate = invalidate
     return acceleration
 
 
@@ -735,6 +744,11 @@ def run_simulation(s: NBodySimulation, alg=None, *, dt: Optional[float] = None, 
     ctx = prob.context
     t0, t1 = s.tspan
     if isinstance(alg, Tsit5):
+        if isinstance(s.thermostat, AndersenThermostat):
+            # the reference attaches the collision DiscreteCallback to ANY algorithm (nbody_simulation_result.jl:482-485);
+            # the host-side adaptive path here only evaluates the RHS, so the thermostat would be dropped silently
+            raise TypeError("an AndersenThermostat simulation needs a fixed-step algorithm here (VelocityVerlet(), dt=...): the "
+                            "collisions are applied by the device stepper after every step")
         return _run_host_adaptive(s, prob, rtol, atol)
     if dt is None:
         raise ValueError("fixed-step algorithms need dt")

@@ -314,6 +314,7 @@ int nbx_create(nbx_ctx **out, int device)
         return rc;
     }
     c->stream = c->own_stream;
+    preload_multi(); preload_slab(); preload_cells(); preload_integrate();
     *out = c;
     return NBX_OK;
 }
@@ -721,7 +722,9 @@ int nbx_accel(nbx_ctx *c, const double *u, double *v, double t, double *dv)
     NBX_TRY(need_system(c, "nbx_accel"));
     if (c->comm.on) { // group member: upload the own block, all-gather over NVLink, return the own columns of dv
         if (!u || !dv) return fail(c, NBX_ERR_INVALID, "nbx_accel: u and dv are required");
+        maybe_pin(c, dv, sizeof(double) * 3 * (size_t)c->ncols);
         NBX_TRY(multi_accel_enqueue(c, u, v));
+        NBX_TRY(multi_accel_exchange(c));
         return multi_accel_finish(c, dv);
     }
     NBX_TRY(no_slab(c, "nbx_accel"));
@@ -1133,6 +1136,10 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     }
     else if (!strcmp(key, "graph")) c->opt_graph = (int)value;
     else if (!strcmp(key, "pin_host")) c->opt_pin_host = (int)value;
+    else if (!strcmp(key, "spin_timeout_ms")) {
+        if (value < 1 || value > 600000) return fail(c, NBX_ERR_INVALID, "spin_timeout_ms: 1 .. 600000");
+        c->spin_timeout_ms = value;
+    }
     else if (!strcmp(key, "fuse_update")) c->opt_fuse_update = (int)value;
     else if (!strcmp(key, "graph_if_nodes")) { c->opt_cond_nodes = (int)value; if (value) c->cond_fail = false; }
     else if (!strcmp(key, "temperature_slot")) {
@@ -1189,6 +1196,7 @@ int nbx_get_info(nbx_ctx *c, const char *key, int64_t *value)
     else if (!strcmp(key, "slab_layer_hi")) *value = c->slab.c1;
     else if (!strcmp(key, "slab_layers")) *value = c->slab.nc;
     else if (!strcmp(key, "slab_verlet")) *value = (c->slab.on && c->slab.verlet) ? 1 : 0;
+    else if (!strcmp(key, "thermostat")) *value = c->thermo;
     else if (!strcmp(key, "group_mode")) *value = c->comm.on ? c->comm.mode : 0;
     else if (!strcmp(key, "group_rank")) *value = c->comm.on ? c->comm.rank : 0;
     else if (!strcmp(key, "group_size")) *value = c->comm.on ? c->comm.nranks : 1;

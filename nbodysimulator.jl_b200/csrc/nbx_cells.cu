@@ -1138,4 +1138,35 @@ void cells_free(CellList *cl)
     *cl = CellList{};
 }
 
+// CUDA loads kernels lazily, at their first launch, and loading may synchronise the context: a kernel that is first
+// launched while another member's kernel spins on a flag would deadlock the pair (CUDA programming guide, "Lazy
+// Loading": concurrent execution).  Every kernel of the distributed loops is therefore loaded when a context is created.
+void preload_cells()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, cell_id_kernel);
+    cudaFuncGetAttributes(&a, scan_block_kernel);
+    cudaFuncGetAttributes(&a, scan_sums_kernel);
+    cudaFuncGetAttributes(&a, scan_add_kernel);
+    cudaFuncGetAttributes(&a, scatter_kernel);
+    cudaFuncGetAttributes(&a, rank_gather_kernel);
+    cudaFuncGetAttributes(&a, cell_pairs2_kernel<0, 0>);
+    cudaFuncGetAttributes(&a, cell_pairs2_kernel<1, 0>);
+    cudaFuncGetAttributes(&a, verlet_check_kernel);
+    cudaFuncGetAttributes(&a, verlet_build_kernel);
+    cudaFuncGetAttributes(&a, verlet_ref_kernel);
+    cudaFuncGetAttributes(&a, verlet_refresh_kernel);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<0, 1>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<0, 2>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<0, 4>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<0, 8>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<1, 1>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<1, 2>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<1, 4>);
+    cudaFuncGetAttributes(&a, verlet_force_kernel<1, 8>);
+    cudaFuncGetAttributes(&a, vv_pos_lists_kernel);
+    cudaFuncGetAttributes(&a, cond_set_kernel);
+    cudaGetLastError();
+}
+
 } // namespace nbx

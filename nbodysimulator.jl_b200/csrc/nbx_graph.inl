@@ -4,18 +4,21 @@
 
 namespace nbx {
 
-// Two eager steps (they also take care of the first step's "the sum in d_scal[0] is already global"), then a CUDA graph of
-// two steps (the acc / acc_old swap has period two), kept for later calls with the same dt.
+// nsteps of a fixed launch sequence.  The buffer pointers a step sees rotate on the host with a fixed PERIOD (2: the acc /
+// acc_old swap; 6 for list-less slabs, whose per-step compaction also rotates a third acceleration buffer and swaps the
+// position buffers).  One period is captured once -- after two eager steps, which let every buffer and kernel attribute
+// settle outside the capture -- and kept for later calls with the same dt; a call then is nsteps / period graph launches
+// (eager steps first until the rotation is back where the capture started).
 template <class F>
-static int steps_graphed(nbx_ctx *c, int kind, double dt, int64_t nsteps, bool allow_graph, F one_step)
+static int steps_graphed(nbx_ctx *c, int kind, double dt, int64_t nsteps, bool allow_graph, int period, F one_step)
 {
     int64_t s = 0;
-    const bool graphable = allow_graph && c->opt_graph && !c->timing && nsteps >= 8 && c->stream != nullptr &&
+    const bool graphable = allow_graph && c->opt_graph && !c->timing && nsteps >= 2 + period && c->stream != nullptr &&
                            c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
     if (graphable) {
-        for (int w = 0; w < 2; ++w, ++s) NBX_TRY(one_step());
-        if (!(c->mg_exec && c->mg_kind == kind && c->mg_dt == dt && c->mg_acc0 == c->acc)) {
+        if (!(c->mg_exec && c->mg_kind == kind && c->mg_dt == dt)) {
             graph_drop(c);
+            for (int w = 0; w < 2; ++w, ++s) NBX_TRY(one_step());
             if (c->opt_cond_nodes && !c->cond_fail && !c->aux_stream &&
                 cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { c->aux_stream = nullptr; cudaGetLastError(); }
             cudaGraph_t graph = nullptr;
@@ -27,8 +30,8 @@ static int steps_graphed(nbx_ctx *c, int kind, double dt, int64_t nsteps, bool a
                 double *acc0 = c->acc, *acc_old0 = c->acc_old;
                 e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (e != cudaSuccess) { c->cond_capture = false; break; }
-                int rc = one_step();
-                if (rc == NBX_OK) rc = one_step();
+                int rc = NBX_OK;
+                for (int k = 0; k < period && rc == NBX_OK; ++k) rc = one_step();
                 c->cond_capture = false;
                 c->stream = main_stream;
                 e = cudaStreamEndCapture(c->stream, &graph);
@@ -44,10 +47,14 @@ static int steps_graphed(nbx_ctx *c, int kind, double dt, int64_t nsteps, bool a
             }
             if (graph) cudaGraphDestroy(graph);
             if (e != cudaSuccess) { c->mg_exec = nullptr; return cuda_fail(c, e, "CUDA graph of the distributed velocity-Verlet step"); }
-            if (c->mg_exec) { c->mg_kind = kind; c->mg_dt = dt; c->mg_acc0 = c->acc; }
+            if (c->mg_exec) { c->mg_kind = kind; c->mg_dt = dt; c->mg_acc0 = c->acc; c->mg_pos0 = c->pos; }
         }
-        if (c->mg_exec)
-            for (; s + 2 <= nsteps; s += 2) NBX_CUDA(c, cudaGraphLaunch(c->mg_exec, c->stream));
+        if (c->mg_exec) {
+            auto aligned = [&]() { return c->acc == c->mg_acc0 && c->pos == c->mg_pos0; };
+            for (int k = 0; k < period && !aligned() && s < nsteps; ++k, ++s) NBX_TRY(one_step()); // back to the captured rotation
+            if (aligned())
+                for (; s + period <= nsteps; s += period) NBX_CUDA(c, cudaGraphLaunch(c->mg_exec, c->stream));
+        }
     }
     for (; s < nsteps; ++s) NBX_TRY(one_step());
     return NBX_OK;

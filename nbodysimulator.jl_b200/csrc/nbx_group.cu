@@ -136,7 +136,13 @@ int leader_accel(nbx_ctx *c, const double *u, double *v, double *dv)
         }
         NBX_TRY(leader_join(c, mode));
     }
+    // page-locking (option pin_host) is an allocation-class call: before anything is enqueued, never between two members' launches
+    const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
+    maybe_pin(c->members[0], u, bytes);
+    maybe_pin(c->members[0], dv, bytes);
+    if (v) maybe_pin(c->members[0], v, bytes);
     for (nbx_ctx *x : c->members) NBX_MEMBER(c, x, (cudaSetDevice(x->device), multi_accel_enqueue(x, u, v)));
+    for (nbx_ctx *x : c->members) NBX_MEMBER(c, x, (cudaSetDevice(x->device), multi_accel_exchange(x)));
     for (nbx_ctx *x : c->members) NBX_MEMBER(c, x, (cudaSetDevice(x->device), multi_accel_finish(x, dv)));
     return NBX_OK;
 }
@@ -146,7 +152,11 @@ int leader_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     if (!c->g_ready || !c->members[0]->resident) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: no resident state (call nbx_upload)");
     // every member's kernels wait for the other members' kernels: enqueue in bounded chunks, member after member, so
     // that no launch queue fills up while its device waits for work that has not been enqueued yet
-    const int64_t chunk = 64;
+    // (graph replay: a chunk is a few dozen launches per member; eager -- option graph = 0, timers on, Andersen --: a step is
+    // some 25 launches, so the chunks are short)
+    const nbx_ctx *m0 = c->members[0];
+    const bool eager = !m0->opt_graph || m0->timing || m0->thermo == NBX_THERMO_ANDERSEN;
+    const int64_t chunk = eager ? 2 : 64;
     for (int64_t done = 0; done < nsteps; done += chunk) {
         const int64_t k = std::min(chunk, nsteps - done);
         for (nbx_ctx *x : c->members) NBX_MEMBER(c, x, (cudaSetDevice(x->device), multi_enqueue_vv(x, dt, k)));
@@ -163,7 +173,7 @@ int leader_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
         if (x->water) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_em: the water SDE variant (src/nbody_to_ode.jl:600-680) is not built");
         if (seed) x->seed = seed;
     }
-    const int64_t chunk = 16;
+    const int64_t chunk = 4;
     for (int64_t done = 0; done < nsteps; done += chunk) {
         const int64_t k = std::min(chunk, nsteps - done);
         for (nbx_ctx *x : c->members) NBX_MEMBER(c, x, (cudaSetDevice(x->device), multi_enqueue_em(x, dt, k)));

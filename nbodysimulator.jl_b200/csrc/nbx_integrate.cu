@@ -147,7 +147,7 @@ __global__ void mv2_partial_kernel(const double *__restrict__ vel, const double 
     if (threadIdx.x == 0) partial[blockIdx.x] = b;
 }
 
-static int ensure_red(nbx_ctx *c)
+int ensure_red(nbx_ctx *c)
 {
     if (c->d_red) return NBX_OK;
     c->red_cap = kRedBlocksMax * 4;
@@ -577,6 +577,28 @@ int measure_hbm_peak(nbx_ctx *c, double *gbs)
     NBX_CUDA(c, cudaGetLastError());
     if (gbs) *gbs = best;
     return NBX_OK;
+}
+
+// CUDA loads kernels lazily, at their first launch, and loading may synchronise the context: a kernel that is first
+// launched while another member's kernel spins on a flag would deadlock the pair (CUDA programming guide, "Lazy
+// Loading": concurrent execution).  Every kernel of the distributed loops is therefore loaded when a context is created.
+void preload_integrate()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, aos_to_soa_kernel);
+    cudaFuncGetAttributes(&a, soa_to_aos_kernel);
+    cudaFuncGetAttributes(&a, fill_kernel);
+    cudaFuncGetAttributes(&a, final_sum_kernel);
+    cudaFuncGetAttributes(&a, mv2_partial_kernel);
+    cudaFuncGetAttributes(&a, berendsen_kernel);
+    cudaFuncGetAttributes(&a, vv_pos_kernel);
+    cudaFuncGetAttributes(&a, vv_vel_kernel<true>);
+    cudaFuncGetAttributes(&a, vv_vel_kernel<false>);
+    cudaFuncGetAttributes(&a, em_kernel);
+    cudaFuncGetAttributes(&a, andersen_kernel);
+    cudaFuncGetAttributes(&a, finite_kernel);
+    cudaFuncGetAttributes(&a, ekin_partial_kernel);
+    cudaGetLastError();
 }
 
 } // namespace nbx

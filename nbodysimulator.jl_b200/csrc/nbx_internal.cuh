@@ -103,12 +103,13 @@ constexpr int kWinScal = 64;                        // [2 parities][kMaxRanks][4
 constexpr int kWinPos = kWinScal + 2 * kMaxRanks * 4;  // [kMaxRanks] int64: positions of sequence number s have landed
 constexpr int kWinAcc = kWinPos + kMaxRanks;           // [kMaxRanks] int64: partial accelerations s are staged
 constexpr int kWinDoubles = kWinAcc + kMaxRanks + 32;
-enum { SEQ_SCAL = 0, SEQ_POS = 1, SEQ_ACC = 2, SEQ_TICKET = 3, SEQ_TIMEOUT = 4, SEQ_TICKET2 = 5, SEQ_N = 8 };
+enum { SEQ_SCAL = 0, SEQ_POS = 1, SEQ_ACC = 2, SEQ_TICKET = 3, SEQ_TIMEOUT = 4, SEQ_TICKET2 = 5, SEQ_GLOBAL0 = 6, SEQ_N = 8 };
 
 struct CommDev { // what the kernels need (passed by value)
     double *win[kMaxRanks];
     int rank, nranks;
-    int *seq; // device counters [SEQ_N]
+    int *seq; // device counters [SEQ_N]; [SEQ_GLOBAL0] != 0: the next all-reduce takes its first value from rank 0 only
+    unsigned long long timeout_ns;
 };
 
 struct Comm {
@@ -123,7 +124,8 @@ struct Comm {
     int *d_seq = nullptr;
     std::vector<void *> ipc_opened;
     int mode = 0;                          // 0 none, 1 pair sharding, 2 target blocks, 3 slabs
-    bool pos_global = true;                // every rank holds all positions (after an upload)
+    bool warm = false;                     // the sharded evaluation has run once: every buffer it needs is allocated
+                                           // (an allocation between two members' launches would serialise their streams)
 };
 
 } // namespace nbx
@@ -185,10 +187,11 @@ struct nbx_ctx {
     // CUDA graph of two velocity-Verlet steps of the distributed loops (nbx_multi.cu / slab_run), kept across calls
     cudaGraphExec_t mg_exec = nullptr;
     double mg_dt = 0.0;
-    double *mg_acc0 = nullptr;
+    double *mg_acc0 = nullptr, *mg_pos0 = nullptr;
     int mg_kind = 0;
     // pinned-host registration cache (option "pin_host"): caller buffers seen by nbx_accel are page-locked once
     int opt_pin_host = 0;
+    int64_t spin_timeout_ms = 10000;     // device-side waits for a peer give up after this long (error, never a hang)
     std::vector<std::pair<const void *, size_t>> pinned;
     // slab mode: the particle counts live on the device ([0] own, [1] ghosts) so that a step needs no host
     // round trip; n / tgt_hi then are launch BOUNDS and every kernel clamps to the device counts
@@ -315,15 +318,24 @@ void slab_free(nbx_ctx *c);
 int slab_start(nbx_ctx *c);
 int slab_enqueue(nbx_ctx *c, double dt, int64_t nsteps); // nbx_step_vv of a slab: enqueues, does not synchronise
 int slab_finish(nbx_ctx *c);
+// kernel preloading (see preload_multi in nbx_multi.cu)
+void preload_multi();
+void preload_slab();
+void preload_cells();
+void preload_integrate();
 // nbx_multi.cu
 CommDev comm_dev(const nbx_ctx *c);
-int comm_allreduce3(nbx_ctx *c, const double *in3, int in0_rank0_only, double *out3, int *flag_out);
+int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out);
+int ensure_red(nbx_ctx *c);
+void maybe_pin(nbx_ctx *c, const void *p, size_t bytes);
 int comm_alloc(nbx_ctx *c);
 void comm_free(nbx_ctx *c);
 int multi_enqueue_vv(nbx_ctx *c, double dt, int64_t nsteps);
 int multi_enqueue_em(nbx_ctx *c, double dt, int64_t nsteps);
 int multi_finish(nbx_ctx *c);
 int multi_accel_enqueue(nbx_ctx *c, const double *u, const double *v);
+int multi_accel_exchange(nbx_ctx *c);
+int comm_arm_global0(nbx_ctx *c);
 int multi_accel_finish(nbx_ctx *c, double *dv);
 int group_init(nbx_ctx *c, int rank, int nranks, int mode);
 int group_export(nbx_ctx *c, int kind, void **ptr, void *handle64);

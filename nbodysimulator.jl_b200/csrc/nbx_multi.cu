@@ -25,23 +25,23 @@ int compute_pairs(nbx_ctx *c); // nbx_api.cu
 // device side
 // ------------------------------------------------------------------------------------------------
 // spin until *flag >= want; bounded by 10 s of %globaltimer (a dead peer must not hang the GPU)
-__device__ __forceinline__ bool spin_ge(const volatile long long *flag, long long want)
+__device__ __forceinline__ bool spin_ge(const volatile long long *flag, long long want, unsigned long long timeout_ns)
 {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*flag < want) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 10000000000ull) return false;
+        if (t1 - t0 > timeout_ns) return false;
     }
     return true;
 }
-__device__ __forceinline__ bool spin_ge_d(const volatile double *flag, double want)
+__device__ __forceinline__ bool spin_ge_d(const volatile double *flag, double want, unsigned long long timeout_ns)
 {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*flag < want) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 10000000000ull) return false;
+        if (t1 - t0 > timeout_ns) return false;
     }
     return true;
 }
@@ -49,11 +49,13 @@ __device__ __forceinline__ bool spin_ge_d(const volatile double *flag, double wa
 // Sum over the ranks of three doubles, identical on every rank (added in rank order): every rank stores its values and a
 // sequence number into slot [parity][rank] of EVERY window, then waits for the nranks slots of its own window.  Double
 // buffered by the parity of the sequence number: a peer can be at most one exchange ahead.
-//   in0 (nullable; rank 0 only when in0_rank0_only: the value is already global), in12 (nullable: two values)
-//   out0, out12 (nullable); flag_out[0] = (sum of in12[0..1] != 0) -- the collective rebuild decision
-__global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, int in0_rank0_only, const double *in12, double *out0,
-                                       double *out12, int *flag_out)
+//   in0 (nullable; taken from rank 0 only while seq[SEQ_GLOBAL0] is set -- the value is then already the global one: the sum
+//   m v^2 of an upload or of the end of a run; the flag is consumed here, so every step is the same launch sequence),
+//   in12 (nullable: two values); out0, out12 (nullable); flag_out[0] = (sum of in12[0..1] != 0): the collective rebuild decision
+__global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, const double *in12, double *out0, double *out12,
+                                       int *flag_out)
 {
+    const int in0_rank0_only = cd.seq[SEQ_GLOBAL0];
     __shared__ double v[kMaxRanks][3];
     __shared__ int bad;
     const int t = threadIdx.x;
@@ -69,7 +71,7 @@ __global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, int in0_ra
         __threadfence_system();
         slot[0] = (double)s;
         const volatile double *mine = cd.win[cd.rank] + kWinScal + ((s & 1) * kMaxRanks + t) * 4;
-        if (!spin_ge_d(mine, (double)s)) bad = 1;
+        if (!spin_ge_d(mine, (double)s, cd.timeout_ns)) bad = 1;
         __threadfence_system();
         v[t][0] = mine[1]; v[t][1] = mine[2]; v[t][2] = mine[3];
     }
@@ -82,6 +84,7 @@ __global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, int in0_ra
         if (out12) { out12[0] = s1; out12[1] = s2; }
         if (flag_out) flag_out[0] = (s1 != 0.0 || s2 != 0.0) ? 1 : 0;
         cd.seq[SEQ_SCAL] = s;
+        cd.seq[SEQ_GLOBAL0] = 0;
     }
 }
 
@@ -137,7 +140,7 @@ __global__ void comm_wait_kernel(CommDev cd, int win_off, int seq_slot)
     const int t = threadIdx.x;
     if (t < cd.nranks) {
         const long long want = cd.seq[seq_slot];
-        if (!spin_ge(reinterpret_cast<const volatile long long *>(cd.win[cd.rank] + win_off) + t, want)) cd.seq[SEQ_TIMEOUT] = 1;
+        if (!spin_ge(reinterpret_cast<const volatile long long *>(cd.win[cd.rank] + win_off) + t, want, cd.timeout_ns)) cd.seq[SEQ_TIMEOUT] = 1;
         __threadfence_system();
     }
 }
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) acc_sum_kernel(CommDev cd, const double *
         const long long want = cd.seq[SEQ_ACC];
         const volatile long long *f = reinterpret_cast<const volatile long long *>(cd.win[cd.rank] + kWinAcc);
         for (int r = 0; r < cd.nranks; ++r)
-            if (!spin_ge(f + r, want)) bad = 1;
+            if (!spin_ge(f + r, want, cd.timeout_ns)) bad = 1;
         __threadfence_system();
         if (bad) cd.seq[SEQ_TIMEOUT] = 1;
     }
@@ -191,6 +194,7 @@ CommDev comm_dev(const nbx_ctx *c)
     const Comm &m = c->comm;
     for (int r = 0; r < kMaxRanks; ++r) cd.win[r] = m.peer_win[r];
     cd.rank = m.rank; cd.nranks = m.nranks; cd.seq = m.d_seq;
+    cd.timeout_ns = (unsigned long long)(c->spin_timeout_ms > 0 ? c->spin_timeout_ms : 1) * 1000000ull;
     return cd;
 }
 
@@ -233,11 +237,22 @@ void graph_drop(nbx_ctx *c)
     c->mg_kind = 0;
 }
 
-int comm_allreduce3(nbx_ctx *c, const double *in0, int in0_rank0_only, double *out3, int *flag_out)
+// sum over the ranks of (in0[0], d_scal[13], d_scal[14]) -> (out0[0], d_scal[13], d_scal[14]); flag_out[0] = any of the two flags.
+// While the host knows that in0 already holds the global value (slab.scal0_global) it raises the device flag first.
+int comm_arm_global0(nbx_ctx *c)
 {
-    // convention: in12 = d_scal + 13 (two flags as doubles, zero when unused), out0 = out3, out12 = d_scal + 13
     NBX_TRY(comm_alloc(c));
-    comm_allreduce3_kernel<<<1, 32, 0, c->stream>>>(comm_dev(c), in0, in0_rank0_only, c->d_scal + 13, out3, c->d_scal + 13, flag_out);
+    if (c->slab.scal0_global) {
+        NBX_CUDA(c, cudaMemsetAsync(c->comm.d_seq + SEQ_GLOBAL0, 1, sizeof(int), c->stream));
+        c->slab.scal0_global = false;
+    }
+    return NBX_OK;
+}
+
+int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out)
+{
+    NBX_TRY(comm_arm_global0(c)); // (a replayed graph never comes through here: the step loops arm the flag before they enqueue)
+    comm_allreduce3_kernel<<<1, 32, 0, c->stream>>>(comm_dev(c), in0, c->d_scal + 13, out0, c->d_scal + 13, flag_out);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
 }
@@ -296,8 +311,18 @@ int group_init(nbx_ctx *c, int rank, int nranks, int mode)
     m.rank = rank; m.nranks = nranks; m.mode = mode;
     for (int r = 0; r < kMaxRanks; ++r) { m.peer_win[r] = nullptr; m.peer_pos[r] = nullptr; m.peer_stage[r] = nullptr; }
     m.peer_win[rank] = m.win; m.peer_pos[rank] = c->pos; m.peer_stage[rank] = m.stage;
-    m.pos_global = true;
+    m.warm = false;
     m.on = true;
+    NBX_TRY(ensure_red(c));
+    if (mode != 3 && c->resident) {
+        // one sharded evaluation now, into the spare rows: every buffer the step loop needs exists before the first
+        // kernel waits for a peer (an allocation between two members' launches would serialise their streams)
+        std::swap(c->acc, c->acc_old);
+        const int rc = compute_pairs(c);
+        std::swap(c->acc, c->acc_old);
+        NBX_TRY(rc);
+        m.warm = true;
+    }
     if (c->thermo == NBX_THERMO_BERENDSEN && mode != 3 && c->T_slot != 12) { // the summed sum m v^2 lives in slot 12
         NBX_CUDA(c, cudaMemcpyAsync(c->d_scal + 12, c->d_scal, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         c->T_slot = 12;
@@ -442,7 +467,7 @@ static bool needs_T(const nbx_ctx *c) { return c->thermo == NBX_THERMO_BERENDSEN
 static int sum_T(nbx_ctx *c, bool to_slot0)
 {
     NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
-    NBX_TRY(comm_allreduce3(c, c->d_scal, c->slab.scal0_global ? 1 : 0, c->d_scal + 12, nullptr));
+    NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, nullptr));
     if (to_slot0) NBX_CUDA(c, cudaMemcpyAsync(c->d_scal, c->d_scal + 12, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->slab.scal0_global = to_slot0;
     return NBX_OK;
@@ -474,8 +499,9 @@ int multi_enqueue_vv(nbx_ctx *c, double dt, int64_t nsteps)
     if (c->thermo == NBX_THERMO_LANGEVIN)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: the Langevin thermostat is an SDE (use nbx_step_em), as in run_simulation");
     if (m.nranks > 1 && !m.peer_pos[(m.rank + 1) % m.nranks]) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: call nbx_group_connect first");
+    if (needs_T(c)) NBX_TRY(comm_arm_global0(c));
     // Andersen draws from a host-side step counter: eager
-    NBX_TRY(steps_graphed(c, 10 + m.mode, dt, nsteps, c->thermo != NBX_THERMO_ANDERSEN, [&]() { return group_vv_step(c, dt); }));
+    NBX_TRY(steps_graphed(c, 10 + m.mode, dt, nsteps, c->thermo != NBX_THERMO_ANDERSEN, 2, [&]() { return group_vv_step(c, dt); }));
     if (needs_T(c)) NBX_TRY(sum_T(c, true)); // leave the scalar block as a single context does: [0] = the global sum
     return NBX_OK;
 }
@@ -515,50 +541,69 @@ int multi_finish(nbx_ctx *c)
 // RHS drop-in over the group: soode_system!(dv, v, u, p, t) with HOST u, v; every rank uploads only its own block,
 // the blocks are all-gathered over NVLink by the push kernel, and only the own columns of dv go back to the host
 // ------------------------------------------------------------------------------------------------
-static const void *maybe_pin(nbx_ctx *c, const void *p, size_t bytes)
+void maybe_pin(nbx_ctx *c, const void *p, size_t bytes)
 {
-    if (!c->opt_pin_host || !p) return p;
+    if (!c->opt_pin_host || !p) return;
+    if (c->leader && c != c->leader->members[0]) return; // one registration (portable) serves every member of a leader
     for (auto &e : c->pinned)
-        if (e.first == p && e.second >= bytes) return p;
+        if (e.first == p && e.second >= bytes) return;
     if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) c->pinned.emplace_back(p, bytes);
     else cudaGetLastError();
-    return p;
 }
 
+// Warm: the own block of u goes up, the push kernel all-gathers it.  Cold (the first call of a group that has not evaluated
+// anything yet): every rank uploads ALL of u and evaluates before any kernel waits for a peer, then synchronises -- the
+// evaluation allocates its buffers, and an allocation between two members' launches would serialise their streams.
 int multi_accel_enqueue(nbx_ctx *c, const double *u, const double *v)
 {
     Comm &m = c->comm;
     if (m.mode == 3) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_accel: the context is slab-decomposed (group mode 2 serves the RHS drop-in of cutoff systems)");
-    const int64_t lo = c->tgt_lo, hi = c->tgt_hi, cnt = hi - lo;
+    const bool cold = !m.warm;
+    const int64_t lo = cold ? 0 : c->tgt_lo, hi = cold ? c->n : c->tgt_hi, cnt = hi - lo;
     const bool have_v = c->thermo == NBX_THERMO_BERENDSEN;
     if (have_v && !v) return fail(c, NBX_ERR_INVALID, "nbx_accel: this thermostat needs v");
     const size_t bytes = sizeof(double) * 3 * (size_t)c->ncols;
     maybe_pin(c, u, bytes);
+    if (have_v) maybe_pin(c, v, bytes);
     if (cnt > 0) {
         NBX_CUDA(c, cudaMemcpyAsync(c->aos_u + 3 * lo, u + 3 * lo, sizeof(double) * 3 * (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
         NBX_TRY(launch_aos_to_soa(c, c->aos_u + 3 * lo, c->pos + lo, cnt));
         NBX_TRY(check_finite(c, c->pos + lo, cnt));
     }
-    NBX_TRY(push_positions(c, 0.0, 0));
+    if (!cold) NBX_TRY(push_positions(c, 0.0, 0));
+    if (have_v && c->tgt_hi > c->tgt_lo) {
+        const int64_t vlo = c->tgt_lo, vcnt = c->tgt_hi - vlo;
+        NBX_CUDA(c, cudaMemcpyAsync(c->aos_v + 3 * vlo, v + 3 * vlo, sizeof(double) * 3 * (size_t)vcnt, cudaMemcpyHostToDevice, c->stream));
+        NBX_TRY(launch_aos_to_soa(c, c->aos_v + 3 * vlo, c->vel + vlo, vcnt));
+    }
+    NBX_TRY(compute_pairs(c));
+    if (have_v) NBX_TRY(launch_sum_mv2(c, c->vel, c->tgt_lo, c->tgt_hi));
+    if (cold) {
+        NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+        m.warm = true;
+    }
+    return NBX_OK;
+}
+
+// second half: everything that waits for the peers (a leader enqueues the first half of EVERY member before this one)
+int multi_accel_exchange(nbx_ctx *c)
+{
+    Comm &m = c->comm;
+    const bool have_v = c->thermo == NBX_THERMO_BERENDSEN;
+    if (m.mode == 1) {
+        const PushArgs pa = push_args(c, m.peer_stage);
+        acc_push_kernel<<<red_grid(c, c->n), 256, 0, c->stream>>>(pa, c->acc, c->npad, c->n, m.per);
+        acc_sum_kernel<<<red_grid(c, c->tgt_hi - c->tgt_lo), 256, 0, c->stream>>>(comm_dev(c), m.stage, m.per, c->acc, c->npad, c->tgt_lo,
+                                                                                c->tgt_hi);
+        NBX_CUDA(c, cudaGetLastError());
+    }
     if (have_v) {
-        maybe_pin(c, v, bytes);
-        if (cnt > 0) {
-            NBX_CUDA(c, cudaMemcpyAsync(c->aos_v + 3 * lo, v + 3 * lo, sizeof(double) * 3 * (size_t)cnt, cudaMemcpyHostToDevice, c->stream));
-            NBX_TRY(launch_aos_to_soa(c, c->aos_v + 3 * lo, c->vel + lo, cnt));
-        }
-        NBX_TRY(launch_sum_mv2(c, c->vel, lo, hi));
         c->slab.scal0_global = false;
-        NBX_TRY(sum_T(c, true));
+        NBX_TRY(sum_T(c, true));   // d_scal[0] = the sum over the ranks, which the RHS term reads
+        NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel));
     }
-    NBX_TRY(group_forces(c));
-    if (have_v) {
-        const int slot = c->T_slot; // the RHS term reads d_scal[0] (= the global sum, see sum_T)
-        c->T_slot = 0;
-        const int rc = launch_thermostat_rhs(c, c->acc, c->vel);
-        c->T_slot = slot;
-        if (rc != NBX_OK) return rc;
-    }
-    if (cnt > 0) NBX_TRY(launch_soa_to_aos(c, c->acc + lo, c->aos_dv + 3 * lo, cnt, cnt, 0, cnt));
+    const int64_t olo = c->tgt_lo, ocnt = c->tgt_hi - olo;
+    if (ocnt > 0) NBX_TRY(launch_soa_to_aos(c, c->acc + olo, c->aos_dv + 3 * olo, ocnt, ocnt, 0, ocnt));
     c->resident = false;
     return NBX_OK;
 }
@@ -566,7 +611,6 @@ int multi_accel_enqueue(nbx_ctx *c, const double *u, const double *v)
 int multi_accel_finish(nbx_ctx *c, double *dv)
 {
     const int64_t lo = c->tgt_lo, cnt = c->tgt_hi - lo;
-    maybe_pin(c, dv, sizeof(double) * 3 * (size_t)c->ncols);
     if (cnt > 0)
         NBX_CUDA(c, cudaMemcpyAsync(dv + 3 * lo, c->aos_dv + 3 * lo, sizeof(double) * 3 * (size_t)cnt, cudaMemcpyDeviceToHost, c->stream));
     int flag[2] = {0, 0};
@@ -574,6 +618,20 @@ int multi_accel_finish(nbx_ctx *c, double *dv)
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     if (flag[0]) return fail(c, NBX_ERR_NONFINITE, "non-finite coordinate in u (the reference's wrap loop would not terminate)");
     return multi_finish(c);
+}
+
+// CUDA loads kernels lazily, at their first launch, and loading may synchronise the context: a kernel that is first
+// launched while another member's kernel spins on a flag would deadlock the pair (CUDA programming guide, "Lazy
+// Loading": concurrent execution).  Every kernel of the distributed loops is therefore loaded when a context is created.
+void preload_multi()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, comm_allreduce3_kernel);
+    cudaFuncGetAttributes(&a, vv_pos_push_kernel);
+    cudaFuncGetAttributes(&a, comm_wait_kernel);
+    cudaFuncGetAttributes(&a, acc_push_kernel);
+    cudaFuncGetAttributes(&a, acc_sum_kernel);
+    cudaGetLastError();
 }
 
 } // namespace nbx

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kSlabBlock) slab_pack_kernel(SlabArrays src, S
 
 // direct mode: wait until both neighbours have published message `msg` in this rank's receive area (thread 0 of every
 // block spins, bounded by 10 s of %globaltimer: a dead neighbour must not hang the GPU).  Returns false on a timeout.
-__device__ __forceinline__ bool slab_wait_messages(double *rx, int msg)
+__device__ __forceinline__ bool slab_wait_messages(double *rx, int msg, unsigned long long timeout_ns)
 {
     __shared__ int timed_out;
     if (threadIdx.x == 0) {
@@ -251,7 +251,7 @@ __device__ __forceinline__ bool slab_wait_messages(double *rx, int msg)
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while (flag[0] < msg || flag[1] < msg) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 10000000000ull) { timed_out = 1; break; }
+            if (t1 - t0 > timeout_ns) { timed_out = 1; break; }
         }
         __threadfence_system();
     }
@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(kSlabBlock) slab_halo_send_kernel(SlabArrays s
 
 // the ghost slots were laid down by the rebuild's unpack: halos from the left, then from the right, after the own
 __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restrict__ dn, double *rx, int64_t msg_doubles,
-                                      int direct, int capM, int capH, const int *__restrict__ skip)
+                                      int direct, int capM, int capH, const int *__restrict__ skip, unsigned long long timeout_ns)
 {
     if (skip && skip[0]) return;
     const int msg = dn[DN_MSG];
-    if (direct && !slab_wait_messages(rx, msg)) {
+    if (direct && !slab_wait_messages(rx, msg, timeout_ns)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) dn[DN_TIMEOUT] = 1;
         return;
     }
@@ -350,12 +350,12 @@ __global__ void slab_verlet_check_kernel(const double *__restrict__ px, int64_t 
 __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols, int *__restrict__ counts,
                                    int *__restrict__ dn, const double *__restrict__ sendL,
                                    const double *__restrict__ sendR, double *rx, int64_t msg_doubles, int direct,
-                                   int capM, int capH, const int *__restrict__ cond)
+                                   int capM, int capH, const int *__restrict__ cond, unsigned long long timeout_ns)
 {
     if (cond && !cond[0]) return;
     // direct mode: the neighbours store into this rank's receive area and raise its flags (message number)
     const int msg = dn[DN_MSG];
-    if (direct && !slab_wait_messages(rx, msg)) {
+    if (direct && !slab_wait_messages(rx, msg, timeout_ns)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { dn[DN_TIMEOUT] = 1; dn[DN_OWN] = 0; dn[DN_GHOST] = 0; }
         return;
     }
@@ -618,7 +618,8 @@ int slab_refresh_recv(nbx_ctx *c)
     const int64_t threads = 2 * s.capH;
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_halo_recv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.d_n, s.rx, s.msg_doubles,
-                                                                                  s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond);
+                                                                                  s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond,
+                                                                                  (unsigned long long)c->spin_timeout_ms * 1000000ull);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return NBX_OK;
@@ -681,7 +682,8 @@ int slab_unpack(nbx_ctx *c, int64_t *out)
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_unpack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.cap_loc, s.d_counts, s.d_n,
                                                                               s.msg[0], s.msg[1], s.rx, s.msg_doubles,
-                                                                              s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond);
+                                                                              s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond,
+                                                                              (unsigned long long)c->spin_timeout_ms * 1000000ull);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return out ? slab_check(c, out) : NBX_OK;
@@ -737,8 +739,7 @@ static int slab_one_step(nbx_ctx *c, double dt)
     NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
     if (s.verlet) {
         NBX_TRY(slab_verlet_check(c, 1.0, nullptr, c->d_scal + 13));
-        NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, cl->v_flags));
-        s.scal0_global = false;
+        NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, cl->v_flags));
         s.cond = cl->v_flags;
         CondScope scope;
         NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope));
@@ -759,7 +760,7 @@ static int slab_one_step(nbx_ctx *c, double dt)
         NBX_TRY(rc);
         s.phase = 2;
     } else {
-        if (needT) { NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, nullptr)); s.scal0_global = false; }
+        if (needT) NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, nullptr));
         NBX_TRY(slab_pack(c));
         NBX_TRY(slab_unpack(c, nullptr));
     }
@@ -784,10 +785,11 @@ int slab_enqueue(nbx_ctx *c, double dt, int64_t nsteps)
     if (s.nranks > 1 && !s.direct) return fail(c, NBX_ERR_INVALID, "nbx_step_vv: the slabs are not connected (nbx_group_connect); drive the exchange from the host");
     if (c->thermo == NBX_THERMO_ANDERSEN || c->thermo == NBX_THERMO_LANGEVIN || c->thermo == NBX_THERMO_NOSEHOOVER)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: slabs run NVE or with the Berendsen thermostat");
-    NBX_TRY(steps_graphed(c, 13, dt, nsteps, true, [&]() { return slab_one_step(c, dt); }));
+    NBX_TRY(comm_arm_global0(c));
+    NBX_TRY(steps_graphed(c, 13, dt, nsteps, true, s.verlet ? 2 : 6, [&]() { return slab_one_step(c, dt); }));
     // leave the scalar block as a single context does: [0] = the sum over all ranks
     NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
-    NBX_TRY(comm_allreduce3(c, c->d_scal, s.scal0_global ? 1 : 0, c->d_scal + 12, nullptr));
+    NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, nullptr));
     NBX_CUDA(c, cudaMemcpyAsync(c->d_scal, c->d_scal + 12, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     s.scal0_global = true;
     return NBX_OK;
@@ -800,6 +802,22 @@ int slab_finish(nbx_ctx *c)
     if (c->comm.d_seq) NBX_CUDA(c, cudaMemcpy(h, c->comm.d_seq, sizeof h, cudaMemcpyDeviceToHost));
     if (h[SEQ_TIMEOUT]) return fail(c, NBX_ERR_CUDA, "slab step: timed out waiting for a peer's flags (a rank did not make the same call?)");
     return NBX_OK;
+}
+
+// CUDA loads kernels lazily, at their first launch, and loading may synchronise the context: a kernel that is first
+// launched while another member's kernel spins on a flag would deadlock the pair (CUDA programming guide, "Lazy
+// Loading": concurrent execution).  Every kernel of the distributed loops is therefore loaded when a context is created.
+void preload_slab()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, slab_count_kernel);
+    cudaFuncGetAttributes(&a, slab_scan_kernel);
+    cudaFuncGetAttributes(&a, slab_pack_kernel);
+    cudaFuncGetAttributes(&a, slab_halo_send_kernel);
+    cudaFuncGetAttributes(&a, slab_halo_recv_kernel);
+    cudaFuncGetAttributes(&a, slab_verlet_check_kernel);
+    cudaFuncGetAttributes(&a, slab_unpack_kernel);
+    cudaGetLastError();
 }
 
 } // namespace nbx

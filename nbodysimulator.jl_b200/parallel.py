@@ -55,7 +55,8 @@ class CudaEngine:
         self.ctx = ctx
         self.n = ctx.n
         self.device = torch.device("cuda", device_index)
-        self.needs_temperature = False
+        # thermostats with an RHS term read the GLOBAL sum m v^2: the steppers all-reduce the shard's sum when this is set
+        self.needs_temperature = ctx.info("thermostat") in (1, 2)  # NBX_THERMO_BERENDSEN, NBX_THERMO_NOSEHOOVER
         # run the library on torch's current stream so NCCL calls issued by torch are ordered with it
         # (torch's default stream has handle 0 == "own stream" in the C ABI; 0x1 is cudaStreamLegacy)
         ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
@@ -511,6 +512,23 @@ class SlabStepper:
             self._T_pending = False
         if check:
             self.counts = self.engine.slab_check()
+            self._drain_schedule()
+
+    def _drain_schedule(self):
+        """The flags are read LAG steps late: the checks of the last LAG steps have not been looked at when step()
+        returns.  A hard flag among them (a step computed from a stale list) must raise here, not go unnoticed."""
+        if not self.verlet or not self._events:
+            return
+        host = self._np_d if self.merged else self._np_i
+        k = self.sched.k
+        for j in range(max(0, k - self.sched.lag), k):
+            if j in self.sched._recent:   # that step rebuilt: its check preceded the rebuild and is moot
+                continue
+            jj = j % self.SLOTS
+            self._events[jj].synchronize()
+            if int(host[jj, 1]):
+                raise RuntimeError(f"slab Verlet lists: at step {j} a particle had moved more than skin/2 since the last rebuild "
+                                   "(or a list overflowed); the run ended before the collective rebuild")
 
     def gather(self, n_total: int):
         """(u, v, dv) of the whole system in the original column order, on every rank (host arrays;

@@ -411,6 +411,95 @@ ORC_API void orc_gravity_targets_ld(const double *rs, const double *ms, int64_t 
     (void)nthreads;
 }
 
+/* ---- extended-precision referee for ALL pair potentials of a system (long double arithmetic and accumulation).
+ * The PAIR SET is the reference's: the cutoff predicate is evaluated exactly as above (fp64, un-fused); only the
+ * force arithmetic of the accepted pairs is carried in long double, from the SAME wrapped displacement.  Used by the
+ * tests to judge both the fp64 restatement and the GPU result where a body's net acceleration nearly cancels
+ * (alternating charges on a lattice, r^-14 terms of both signs): neither side is allowed more than 1e-12 / twice the
+ * restatement's own distance from the referee.  Not a restatement of the reference: test infrastructure only. ---- */
+ORC_API void orc_accel_targets_ld(const orc_system *s, const double *rs, const int64_t *targets, int64_t nt, double *out,
+                                  int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+    for (int64_t t = 0; t < nt; ++t) {
+        const int64_t i = targets[t], n = s->n;
+        const double *ri = rs + 3 * i;
+        long double tot[3] = {0, 0, 0};
+        if (s->has_lj && (!s->water || i % 3 == 0)) {
+            long double f[3] = {0, 0, 0};
+            const int stride = s->water ? 3 : 1;
+            for (int64_t j = 0; j < n; j += stride) {
+                if (j == i) continue;
+                double rij[3], r, r2;
+                orc_distance_impl(ri, rs + 3 * j, s->bc_kind, s->bc, rij, &r, &r2);
+                if (r2 < s->lj_R2) {
+                    const long double x = rij[0], y = rij[1], z = rij[2];
+                    const long double d2 = x * x + y * y + z * z;
+                    const long double q = (long double)s->lj_sigma2 / d2;
+                    const long double s6 = q * q * q;
+                    const long double fac = (2 * s6 * s6 - s6) / d2;
+                    f[0] += fac * x; f[1] += fac * y; f[2] += fac * z;
+                }
+            }
+            const long double c = 24 * (long double)s->lj_eps / s->ms[i];
+            for (int k = 0; k < 3; ++k) tot[k] += c * f[k];
+        }
+        if (s->has_coulomb) {
+            long double f[3] = {0, 0, 0};
+            const int64_t ex_lo = s->water ? 3 * (i / 3) : i;
+            const int64_t ex_hi = s->water ? ex_lo + 3 : i + 1;
+            for (int64_t j = 0; j < n; ++j) {
+                if (j >= ex_lo && j < ex_hi) continue;
+                double rij[3], r, r2;
+                orc_distance_impl(ri, rs + 3 * j, s->bc_kind, s->bc, rij, &r, &r2);
+                if (r2 < s->el_R2) {
+                    const long double x = rij[0], y = rij[1], z = rij[2];
+                    const long double d2 = x * x + y * y + z * z;
+                    const long double fac = (long double)s->qs[j] / (sqrtl(d2) * d2);
+                    f[0] += fac * x; f[1] += fac * y; f[2] += fac * z;
+                }
+            }
+            const long double c = (long double)s->el_k * s->qs[i] / s->ms[i];
+            for (int k = 0; k < 3; ++k) tot[k] += c * f[k];
+        }
+        if (s->has_dipole) {
+            long double f[3] = {0, 0, 0};
+            const double *mi = s->mm + 3 * i;
+            for (int64_t j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const double *mj = s->mm + 3 * j, *rj = rs + 3 * j;
+                const long double x[3] = {(long double)ri[0] - rj[0], (long double)ri[1] - rj[1], (long double)ri[2] - rj[2]};
+                const long double d2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+                const long double nr = sqrtl(d2);
+                const long double e[3] = {x[0] / nr, x[1] / nr, x[2] / nr};
+                const long double mir = mi[0] * e[0] + mi[1] * e[1] + mi[2] * e[2];
+                const long double mjr = mj[0] * e[0] + mj[1] * e[1] + mj[2] * e[2];
+                const long double mimj = (long double)mi[0] * mj[0] + (long double)mi[1] * mj[1] + (long double)mi[2] * mj[2];
+                for (int k = 0; k < 3; ++k) f[k] += (mi[k] * mjr + mj[k] * mir + e[k] * mimj - 5 * e[k] * mir * mjr) / (d2 * d2);
+            }
+            const long double c = 3 * (long double)s->mu_4pi / s->ms[i];
+            for (int k = 0; k < 3; ++k) tot[k] += c * f[k];
+        }
+        if (s->has_gravity) {
+            long double f[3] = {0, 0, 0};
+            for (int64_t j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const double *rj = rs + 3 * j;
+                const long double x = (long double)ri[0] - rj[0], y = (long double)ri[1] - rj[1], z = (long double)ri[2] - rj[2];
+                const long double nr = sqrtl(x * x + y * y + z * z);
+                const long double fac = (-(long double)s->G * s->ms[j]) / (nr * nr * nr);
+                f[0] += fac * x; f[1] += fac * y; f[2] += fac * z;
+            }
+            for (int k = 0; k < 3; ++k) tot[k] += f[k];
+        }
+        for (int k = 0; k < 3; ++k) out[3 * t + k] = (double)tot[k];
+    }
+    (void)nthreads;
+}
+
 /* In-cutoff neighbour predicate of the reference: for target i, the ordered list of j
  * (ascending) with j != i (stride as LJ index set) and r2 < R2, r2 from
  * get_interparticle_distance in un-fused fp64.  Returns the count; writes at most cap. */

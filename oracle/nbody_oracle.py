@@ -63,6 +63,8 @@ def lib():
         L.orc_rhs.restype = None
         L.orc_gravity_targets_ld.argtypes = [dp, dp, C.c_int64, C.c_double, ip64, C.c_int64, dp, C.c_int]
         L.orc_gravity_targets_ld.restype = None
+        L.orc_accel_targets_ld.argtypes = [C.POINTER(OrcSystem), dp, ip64, C.c_int64, dp, C.c_int]
+        L.orc_accel_targets_ld.restype = None
         L.orc_neighbors_i.argtypes = [dp, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_int, dp, ip32, C.c_int64]
         L.orc_neighbors_i.restype = C.c_int64
         L.orc_distance.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp]
@@ -175,6 +177,16 @@ class System:
         out = np.zeros((3, t.shape[0]), order="F")
         lib().orc_accel_targets(C.byref(self.c), _dp(u), t.ctypes.data_as(C.POINTER(C.c_int64)),
                                 t.shape[0], _dp(out), int(nthreads))
+        return out
+
+    def accel_targets_ld(self, u, targets, nthreads=1):
+        """Extended-precision referee (long double) of the pair potentials for the listed targets: same pair set as the
+        reference predicate, force arithmetic and sums in long double.  Bonded terms and thermostats are not included."""
+        u = _f(u)
+        t = np.ascontiguousarray(targets, dtype=np.int64)
+        out = np.zeros((3, t.shape[0]), order="F")
+        lib().orc_accel_targets_ld(C.byref(self.c), _dp(u), t.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   t.shape[0], _dp(out), int(nthreads))
         return out
 
     def accel_molecules(self, u, mols, nthreads=1):

@@ -33,6 +33,15 @@ def _argon(cells, seed, hot=3.0, thermostat=False):
     return spec, u, v
 
 
+def _group(spec, devices, **opts):
+    """nbx_create_multi context; device-side waits give up after 3 s here (a protocol bug must not eat GPU minutes)."""
+    grp = make_context(spec, device=devices)
+    grp.set_option("spin_timeout_ms", 3000)
+    for k, val in opts.items():
+        grp.set_option(k, val)
+    return grp
+
+
 def _relmax(a, b):
     den = np.maximum(np.linalg.norm(b, axis=0), 1e-300)
     return float((np.linalg.norm(a - b, axis=0) / den).max())
@@ -58,7 +67,7 @@ def test_slab_group_reproduces_the_single_context_trajectory(world, thermostat):
     spec, u, v = _argon(12, 5, thermostat=thermostat)   # 6,912 atoms, 8 layers with the skin: 2 per slab at world 4
     dt, nsteps = 2e-3, 90
     (u1, v1, a1), rebuilds1, T1 = _single_run(spec, u, v, dt, nsteps)
-    grp = make_context(spec, device=[0] * world)
+    grp = _group(spec, [0] * world)
     grp.upload(u, v)
     assert grp.info("group_mode") == 3 and grp.info("group_size") == world and grp.info("slab_verlet") == 1
     grp.step_vv(dt, 50)
@@ -85,9 +94,7 @@ def test_slab_group_without_graph_and_with_cells_every_step():
     dt, nsteps = 2e-3, 40
     (u1, v1, a1), _, _ = _single_run(spec, u, v, dt, nsteps)
     for opts in (dict(graph=0), dict(verlet_skin_permille=0), dict(graph_if_nodes=0)):
-        grp = make_context(spec, device=[0, 0])
-        for k, val in opts.items():
-            grp.set_option(k, val)
+        grp = _group(spec, [0, 0], **opts)
         grp.upload(u, v)
         grp.step_vv(dt, nsteps)
         ug, vg, ag = grp.download(want_dv=True)
@@ -108,6 +115,7 @@ def test_group_members_joined_by_hand_and_driven_from_threads():
     ctxs = []
     for _ in range(world):
         c = make_context(spec)
+        c.set_option("spin_timeout_ms", 3000)
         c.upload(u, v)
         ctxs.append(c)
     join_group_local(ctxs)
@@ -146,7 +154,7 @@ def test_pair_sharded_gravity_group(oracle, world, n):
     spec = dict(ms=ms, gravity=dict(G=1.0))
     one = make_context(spec)
     a1 = one.accel(u).copy()
-    grp = make_context(spec, device=[0] * world)
+    grp = _group(spec, [0] * world)
     ag = grp.accel(u)
     assert grp.info("group_mode") == (1 if n >= 8192 else 1)
     assert _relmax(ag, a1) < 1e-12
@@ -176,7 +184,7 @@ def test_target_block_group_water(oracle):
                 thermostat=dict(kind="berendsen", T=300.0, tau=0.05, kB=w["kB"], N=3 * w["nmol"], Nc=2 * w["nmol"]))
     u, v = F(w["u"]), F(w["v"])
     one = make_context(spec)
-    grp = make_context(spec, device=[0, 0, 0])
+    grp = _group(spec, [0, 0, 0])
     vv = F(v.copy())
     a1 = one.accel(u, vv).copy()
     ag = grp.accel(u, F(v.copy()))
@@ -209,7 +217,7 @@ def test_group_langevin_euler_maruyama(kind):
     u, v = F(w["u"]), F(w["v"])
     dt, nsteps = 1e-9, 6
     (u1, v1, a1), _, _ = _single_run(spec, u, v, dt, nsteps, em=True, seed=77)
-    grp = make_context(spec, device=[0, 0])
+    grp = _group(spec, [0, 0])
     grp.upload(u, v)
     assert grp.info("group_mode") == (1 if kind == "coulomb" else 2)
     grp.step_em(dt, nsteps, 77)
@@ -224,7 +232,7 @@ def test_group_andersen_matches_single_context():
     dt, nsteps = 2e-3, 25
     one = make_context(spec); one.set_seed(5); one.upload(u, v); one.step_vv(dt, nsteps)
     u1, v1, _ = one.download()
-    grp = make_context(spec, device=[0, 0]); grp.set_option("group_mode", 2); grp.set_seed(5); grp.upload(u, v)
+    grp = _group(spec, [0, 0], group_mode=2); grp.set_seed(5); grp.upload(u, v)
     assert grp.info("group_mode") == 2
     grp.step_vv(dt, nsteps)
     ug, vg, _ = grp.download()

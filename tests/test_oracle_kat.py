@@ -347,3 +347,32 @@ def test_rdf_counts_every_pair_inside_half_the_box_twice():
     assert h.sum() == 4 and h[math.ceil(3.337 / dr) - 1] == 4  # pairs (0,1) and (1,2) share a bin; (0,2) at 0.004 < dr is dropped
     rs, gr = orc.rdf_normalise(h, 1, 3, L)
     assert rs[0] == dr / 2 and gr[0] == 0.0
+
+
+def test_extended_precision_referee_agrees_with_the_restatement(oracle):
+    """orc_accel_targets_ld (long double force arithmetic on the reference's pair set; the tests' referee where net
+    accelerations cancel) and the fp64 restatement agree to rounding on a well-conditioned mixed system, potential by
+    potential, under all three boundary kinds."""
+    rng = np.random.default_rng(5)
+    n = 200
+    u = np.asfortranarray(rng.random((3, n)) * 1.3 + 4.0 * rng.integers(-2, 3, (3, n)))
+    ms, qs = rng.random(n) + 0.5, rng.standard_normal(n)
+    mm = np.asfortranarray(rng.standard_normal((3, n)))
+    t = np.arange(n)
+    cases = [dict(bc=("cubic", 1.3), lj=dict(eps=0.7, sigma=0.05, R=0.3)),
+             dict(bc=("periodic", [0.0, 1.3, 0.0, 1.3, 0.0, 1.3]), lj=dict(eps=0.7, sigma=0.05, R=0.9)),
+             dict(bc=("cubic", 1.3), qs=qs, coulomb=dict(k=2.5, R=0.4)),
+             dict(qs=qs, coulomb=dict(k=2.5, R=np.inf)),
+             dict(mm=mm, dipole=dict(mu_4pi=1e-3)),
+             dict(gravity=dict(G=0.3))]
+    for kw in cases:
+        s = oracle.System(ms, **kw)
+        a, b = s.accel_targets(u, t, 2), s.accel_targets_ld(u, t, 2)
+        err = np.linalg.norm(a - b, axis=0) / np.linalg.norm(b, axis=0)
+        assert err.max() < 1e-12, (kw.keys(), err.max())
+    # water: Lennard-Jones acts on the oxygens only, Coulomb skips the own molecule
+    s = oracle.System(np.tile([16.0, 1.0, 1.0], 20), qs=np.tile([-0.8, 0.4, 0.4], 20), water=True, bc=("cubic", 1.3),
+                      lj=dict(eps=0.7, sigma=0.05, R=0.3), coulomb=dict(k=2.5, R=0.5))
+    uw = np.asfortranarray(rng.random((3, 60)) * 1.3)
+    a, b = s.accel_targets(uw, np.arange(60), 1), s.accel_targets_ld(uw, np.arange(60), 1)
+    assert (np.linalg.norm(a - b, axis=0) <= 1e-12 * np.linalg.norm(b, axis=0)).all()
