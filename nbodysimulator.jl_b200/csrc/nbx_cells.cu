@@ -21,6 +21,7 @@
 // exact fp64 predicate decides, and the force is evaluated only there.
 #include "nbx_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -742,8 +743,10 @@ static void launch_verlet_force(nbx_ctx *c, const CellPairArgs &a, const VerletA
 {
     // lanes per target: enough threads to fill the machine (148 SMs x 2048) when the system is small
     const int64_t want = (int64_t)c->sm_count * 2048;
+    // (a slab launches for a capacity bound: the targets are about its share of the box)
+    const int64_t ntgt = c->slab.on ? std::max<int64_t>(1, c->slab.n_total / c->slab.nranks) : (int64_t)a.n;
     int P = 1;
-    while (P < 8 && (int64_t)a.n * P < want) P <<= 1;
+    while (P < 8 && ntgt * P < want) P <<= 1;
     if (c->opt_verlet_lanes > 0) P = c->opt_verlet_lanes;
     const unsigned blocks = (unsigned)(((int64_t)a.n * P + 127) / 128);
 #define NBX_VF(PP) verlet_force_kernel<POT, PP><<<blocks, 128, 0, c->stream>>>(a, v, scale, c->mass, mstride, c->charge, lo, hi, \
@@ -805,8 +808,28 @@ __global__ void cond_set_kernel(cudaGraphConditionalHandle h, const int *__restr
     cudaGraphSetConditional(h, flag[0] != 0 ? 1u : 0u);
 }
 
+// While a graph with IF nodes is being captured: a conditional handle for a kernel of the caller's to set
+// (cudaGraphSetConditional) before cond_scope_begin(..., pre) adds the node.  *ok = false otherwise.
+int cond_handle_create(nbx_ctx *c, cudaGraphConditionalHandle *h, bool *ok)
+{
+    *ok = false;
+    if (!c->cond_capture || c->cond_fail || !c->aux_stream) return NBX_OK;
+    cudaStreamCaptureStatus st;
+    unsigned long long id;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t nd = 0;
+    if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &g, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive || !g)
+        return NBX_OK;
+    if (cudaGraphConditionalHandleCreate(h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return NBX_OK; }
+    *ok = true;
+    return NBX_OK;
+}
+
 // From here to cond_scope_end the launches on c->stream land in the IF node's body graph.  No-op outside a capture.
-int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
+// pre: a handle from cond_handle_create that a kernel of the caller's has set already (else a one-thread kernel sets it
+// from flag[0] here).
+int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc, const cudaGraphConditionalHandle *pre)
 {
     sc->active = false;
     if (!c->cond_capture || c->cond_fail || !c->aux_stream) return NBX_OK;
@@ -818,8 +841,11 @@ int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc)
     if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &g, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive || !g)
         return NBX_OK;
     cudaGraphConditionalHandle h;
-    if (cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return NBX_OK; }
-    cond_set_kernel<<<1, 1, 0, c->stream>>>(h, flag);
+    if (pre) h = *pre;
+    else {
+        if (cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) { c->cond_fail = true; cudaGetLastError(); return NBX_OK; }
+        cond_set_kernel<<<1, 1, 0, c->stream>>>(h, flag);
+    }
     if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &g, &deps, &nd) != cudaSuccess) { c->cond_fail = true; return fail(c, NBX_ERR_CUDA, "graph IF node: capture info"); }
     cudaGraphNodeParams p = {};
     p.type = cudaGraphNodeTypeConditional;
@@ -985,9 +1011,12 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
             c->slab.rebuild_now = false;
         }
         if (c->slab.phase == 1) { NBX_CUDA(c, cudaGetLastError()); return NBX_OK; }
-        timer_begin(c, NBX_T_CELL_BUILD);
-        verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, c->dyn);
-        timer_end(c, NBX_T_CELL_BUILD);
+        if (!c->slab.records_fresh) { // (slab_enqueue: the position update and the halo receive already wrote the records)
+            timer_begin(c, NBX_T_CELL_BUILD);
+            verlet_refresh_kernel<<<blocks256, 256, 0, c->stream>>>(px, ld, w, cl->sorted_idx, ni, cl->sp4, cl->v_flags, c->dyn);
+            timer_end(c, NBX_T_CELL_BUILD);
+        }
+        c->slab.records_fresh = false;
         a = make_args(c, cl, R2);
         const int acc_flag = accumulate ? 1 : 0;
         timer_begin(c, NBX_T_PAIR_CELLS);
@@ -1007,7 +1036,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         timer_end(c, NBX_T_CELL_BUILD);
     }
     CondScope scope;
-    NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope)); // (graph capture: the chain below becomes the body of an IF node)
+    NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope, nullptr)); // (graph capture: the chain below becomes the body of an IF node)
     {
         const int rc = cells_build(c, cl, px, w, gid, n, ld, key_div, cl->v_flags);
         if (rc != NBX_OK) { cond_scope_end(c, &scope); return rc; }

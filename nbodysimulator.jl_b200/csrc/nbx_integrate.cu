@@ -151,7 +151,9 @@ int ensure_red(nbx_ctx *c)
 {
     if (c->d_red) return NBX_OK;
     c->red_cap = kRedBlocksMax * 4;
-    return dev_alloc(c, &c->d_red, (size_t)c->red_cap);
+    NBX_TRY(dev_alloc(c, &c->d_red, (size_t)c->red_cap));
+    NBX_CUDA(c, cudaMemsetAsync(c->d_red, 0, sizeof(double) * (size_t)c->red_cap, c->stream)); // (the tail holds a block ticket)
+    return NBX_OK;
 }
 
 int launch_sum_mv2(nbx_ctx *c, const double *vel, int64_t lo, int64_t hi)
@@ -243,9 +245,11 @@ __global__ void vv_pos_kernel(double *__restrict__ pos, const double *__restrict
 template <bool BEREND>
 __global__ void vv_vel_kernel(double *__restrict__ vel, const double *__restrict__ a_old, double *__restrict__ a_new,
                               const double *__restrict__ mass, int64_t ld, int64_t lo, int64_t hi, double hdt,
-                              double *__restrict__ partial, const double *__restrict__ scal, double kB, double ndf,
-                              double T0, double gamma, const int *__restrict__ dyn)
+                              double *__restrict__ partial, const double *scal, double kB, double ndf,
+                              double T0, double gamma, const int *__restrict__ dyn, int *__restrict__ ticket,
+                              double *out, double *out2) // (scal, out, out2 all point into the scalar block)
 {
+    __shared__ int last_block;
     if (dyn) hi = min(hi, lo + (int64_t)dyn[0]);
     double sc = 0.0;
     if (BEREND) {
@@ -271,7 +275,23 @@ __global__ void vv_vel_kernel(double *__restrict__ vel, const double *__restrict
         s = fma(mass[i], v2, s);
     }
     const double b = block_sum(s);
-    if (threadIdx.x == 0) partial[blockIdx.x] = b;
+    // the last block to finish adds the partials exactly as final_sum_kernel does (one launch less per step)
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = b;
+        __threadfence();
+        last_block = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_block) return;
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kRedThreads) t += __ldcg(partial + i);
+    const double total = block_sum(t);
+    if (threadIdx.x == 0) {
+        out[0] = total;
+        if (out2) out2[0] = total;
+        *ticket = 0;
+    }
 }
 
 int launch_vv_pos(nbx_ctx *c, double dt)
@@ -298,16 +318,17 @@ int launch_vv_vel(nbx_ctx *c, double dt, bool with_thermostat)
         if (c->thermo == NBX_THERMO_BERENDSEN) fused = true;
         else NBX_TRY(launch_thermostat_rhs(c, c->acc, c->vel));
     }
+    // (T_slot != 0: the distributed loops keep the all-reduced sum in its own slot; the local one goes to both)
+    int *ticket = reinterpret_cast<int *>(c->d_red + c->red_cap - 1);
+    double *out2 = c->T_slot ? c->d_scal + c->T_slot : nullptr;
     timer_begin(c, NBX_T_INTEGRATE);
     if (fused)
         vv_vel_kernel<true><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
                                                               0.5 * dt, c->d_red, c->d_scal + c->T_slot, c->kB, ndf, c->T0,
-                                                              0.5 / c->tparam, c->dyn);
+                                                              0.5 / c->tparam, c->dyn, ticket, c->d_scal, out2);
     else
         vv_vel_kernel<false><<<nb, kRedThreads, 0, c->stream>>>(c->vel, c->acc_old, c->acc, c->mass, c->npad, lo, hi,
-                                                               0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0, c->dyn);
-    // (T_slot != 0: the slab driver keeps the all-reduced sum in its own slot, see nbx_slab_step_begin)
-    final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal, c->T_slot ? c->d_scal + c->T_slot : nullptr);
+                                                               0.5 * dt, c->d_red, c->d_scal, 0.0, 1.0, 0.0, 0.0, c->dyn, ticket, c->d_scal, out2);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;

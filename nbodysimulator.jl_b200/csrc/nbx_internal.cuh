@@ -91,6 +91,8 @@ struct SlabState {
     int phase = 0;             // cells_pairs: 0 rebuild (if rebuild_now) + refresh + forces, 1 rebuild chain only, 2 refresh + forces only
     const int *cond = nullptr; // device flag while slab_run enqueues: the rebuild chain runs iff cond[0] != 0, the halo refresh iff == 0
     bool started = false;      // nbx_slab_start distributed the particles and built the first lists
+    const CellList *refresh_cl = nullptr; // while slab_one_step enqueues the halo receive: write the ghosts' records too
+    bool records_fresh = false; // the cell-order records hold the current positions (written by slab_pos_kernel / the halo receive)
     bool scal0_global = true;  // d_scal[0] holds the sum over ALL ranks (after an upload / at the end of a run), not the local one
 };
 
@@ -325,7 +327,7 @@ void preload_cells();
 void preload_integrate();
 // nbx_multi.cu
 CommDev comm_dev(const nbx_ctx *c);
-int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out);
+int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out, const cudaGraphConditionalHandle *cond = nullptr);
 int ensure_red(nbx_ctx *c);
 void maybe_pin(nbx_ctx *c, const void *p, size_t bytes);
 int comm_alloc(nbx_ctx *c);
@@ -354,7 +356,8 @@ int leader_energy(nbx_ctx *c, double *ekin, double *epot, double *temperature);
 void graph_drop(nbx_ctx *c);
 // nbx_cells.cu: the launches between begin and end become the body of a graph IF node on flag[0] while capturing
 struct CondScope { bool active = false; cudaStream_t saved = nullptr; };
-int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc);
+int cond_handle_create(nbx_ctx *c, cudaGraphConditionalHandle *h, bool *ok);
+int cond_scope_begin(nbx_ctx *c, const int *flag, CondScope *sc, const cudaGraphConditionalHandle *pre);
 int cond_scope_end(nbx_ctx *c, CondScope *sc);
 // nbx_bonded.cu
 int launch_spcfw_bonded(nbx_ctx *c, double *acc_out);

@@ -52,8 +52,10 @@ __device__ __forceinline__ bool spin_ge_d(const volatile double *flag, double wa
 //   in0 (nullable; taken from rank 0 only while seq[SEQ_GLOBAL0] is set -- the value is then already the global one: the sum
 //   m v^2 of an upload or of the end of a run; the flag is consumed here, so every step is the same launch sequence),
 //   in12 (nullable: two values); out0, out12 (nullable); flag_out[0] = (sum of in12[0..1] != 0): the collective rebuild decision
-__global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, const double *in12, double *out0, double *out12,
-                                       int *flag_out)
+// The two flag inputs are zeroed once read (the next step's check raises them again: no memset per step), and with a
+// conditional handle the kernel also decides the graph's IF node (cudaGraphSetConditional): one launch less per step.
+__global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, double *in12, double *out0, double *out12,
+                                       int *flag_out, cudaGraphConditionalHandle cond, int has_cond)
 {
     const int in0_rank0_only = cd.seq[SEQ_GLOBAL0];
     __shared__ double v[kMaxRanks][3];
@@ -82,7 +84,10 @@ __global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, const doub
         if (bad) { cd.seq[SEQ_TIMEOUT] = 1; s1 = 1.0; }
         if (out0) out0[0] = s0;
         if (out12) { out12[0] = s1; out12[1] = s2; }
-        if (flag_out) flag_out[0] = (s1 != 0.0 || s2 != 0.0) ? 1 : 0;
+        const int any = (s1 != 0.0 || s2 != 0.0) ? 1 : 0;
+        if (flag_out) flag_out[0] = any;
+        if (has_cond) cudaGraphSetConditional(cond, (unsigned)any);
+        if (in12) { in12[0] = 0.0; in12[1] = 0.0; }
         cd.seq[SEQ_SCAL] = s;
         cd.seq[SEQ_GLOBAL0] = 0;
     }
@@ -249,10 +254,11 @@ int comm_arm_global0(nbx_ctx *c)
     return NBX_OK;
 }
 
-int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out)
+int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out, const cudaGraphConditionalHandle *cond)
 {
     NBX_TRY(comm_arm_global0(c)); // (a replayed graph never comes through here: the step loops arm the flag before they enqueue)
-    comm_allreduce3_kernel<<<1, 32, 0, c->stream>>>(comm_dev(c), in0, c->d_scal + 13, out0, c->d_scal + 13, flag_out);
+    comm_allreduce3_kernel<<<1, 32, 0, c->stream>>>(comm_dev(c), in0, c->d_scal + 13, out0, nullptr, flag_out,
+                                                    cond ? *cond : cudaGraphConditionalHandle{}, cond ? 1 : 0);
     NBX_CUDA(c, cudaGetLastError());
     return NBX_OK;
 }

@@ -302,8 +302,10 @@ __global__ void __launch_bounds__(kSlabBlock) slab_halo_send_kernel(SlabArrays s
 }
 
 // the ghost slots were laid down by the rebuild's unpack: halos from the left, then from the right, after the own
+// (slot_of != null: the ghost's cell-order record is refreshed here too, so no separate refresh pass is needed)
 __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restrict__ dn, double *rx, int64_t msg_doubles,
-                                      int direct, int capM, int capH, const int *__restrict__ skip, unsigned long long timeout_ns)
+                                      int direct, int capM, int capH, const int *__restrict__ skip, unsigned long long timeout_ns,
+                                      const int *__restrict__ slot_of, double4 *__restrict__ sp4)
 {
     if (skip && skip[0]) return;
     const int msg = dn[DN_MSG];
@@ -325,6 +327,30 @@ __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restric
     const double *rec = (side == 0 ? recvL : recvR) + kHdr + (size_t)capM * kMigW + (size_t)k * kHaloW;
     const int d = n_own + (side == 0 ? 0 : haloL) + k;
     dst.pos[d] = rec[1]; dst.pos[ld + d] = rec[2]; dst.pos[2 * ld + d] = rec[3];
+    if (slot_of) sp4[slot_of[d]] = make_double4(rec[1], rec[2], rec[3], dst.charge ? dst.charge[d] : 0.0);
+}
+
+// Position update of the own particles fused with what a regular step needs next: the displacement check against the
+// build-time positions (-> flags[1] = 1.0 when a particle moved more than skin/2, or a list overflowed) and the refresh of
+// the particle's cell-order record.  Same arithmetic as vv_pos_kernel / slab_verlet_check_kernel / verlet_refresh_kernel.
+__global__ void slab_pos_kernel(double *__restrict__ pos, const double *__restrict__ vel, const double *__restrict__ acc,
+                                const double *__restrict__ w, int64_t ld, const int *__restrict__ dn, double dt, double hdt2,
+                                const double *__restrict__ ref, int64_t rld, double lim2, const int *__restrict__ slot_of,
+                                double4 *__restrict__ sp4, const int *__restrict__ vflags, double *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool moved = i == 0 && vflags[1];
+    if (i < dn[DN_OWN]) {
+        const double x = fma(hdt2, acc[i], fma(dt, vel[i], pos[i]));
+        const double y = fma(hdt2, acc[ld + i], fma(dt, vel[ld + i], pos[ld + i]));
+        const double z = fma(hdt2, acc[2 * ld + i], fma(dt, vel[2 * ld + i], pos[2 * ld + i]));
+        pos[i] = x; pos[ld + i] = y; pos[2 * ld + i] = z;
+        const double dx = x - ref[i], dy = y - ref[rld + i], dz = z - ref[2 * rld + i];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        moved = moved || !(d2 <= lim2); // also catches NaN
+        sp4[slot_of[i]] = make_double4(x, y, z, w ? w[i] : 0.0);
+    }
+    if (moved) flags[1] = 1.0;
 }
 
 // displacement of the own particles from the positions the lists were built from: out[0] |= beyond the soft limit
@@ -619,7 +645,9 @@ int slab_refresh_recv(nbx_ctx *c)
     const SlabArrays dst = arrays(c->pos, c->vel, c->acc, c->mass, c->charge, c->gid);
     slab_halo_recv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(dst, c->npad, s.d_n, s.rx, s.msg_doubles,
                                                                                   s.direct ? 1 : 0, (int)s.capM, (int)s.capH, s.cond,
-                                                                                  (unsigned long long)c->spin_timeout_ms * 1000000ull);
+                                                                                  (unsigned long long)c->spin_timeout_ms * 1000000ull,
+                                                                                  s.refresh_cl ? s.refresh_cl->slot_of : nullptr,
+                                                                                  s.refresh_cl ? s.refresh_cl->sp4 : nullptr);
     NBX_CUDA(c, cudaGetLastError());
     s.packed = false;
     return NBX_OK;
@@ -735,14 +763,30 @@ static int slab_one_step(nbx_ctx *c, double dt)
     SlabState &s = c->slab;
     CellList *cl = c->has_lj ? &c->cl_lj : &c->cl_el;
     const bool needT = c->thermo == NBX_THERMO_BERENDSEN;
-    NBX_TRY(launch_vv_pos(c, dt));
-    NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
     if (s.verlet) {
-        NBX_TRY(slab_verlet_check(c, 1.0, nullptr, c->d_scal + 13));
-        NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, cl->v_flags));
+        // regular step = 6 launches: position update + check + own records | all-reduce + IF decision | halo send |
+        // halo receive + ghost records | listed pairs | velocity update + sum m v^2
+        const bool lists = cl->v_valid && cl->v_ref && cl->slot_of && !s.rebuild_now;
+        if (lists) {
+            const double lim = 0.5 * cl->v_skin * (1.0 - 1e-9);
+            const int n = (int)s.cap_loc;
+            timer_begin(c, NBX_T_INTEGRATE);
+            slab_pos_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pos, c->vel, c->acc, c->has_lj ? nullptr : c->charge, c->npad, s.d_n, dt,
+                                                                   0.5 * dt * dt, cl->v_ref, cl->cap_n, lim * lim, cl->slot_of, cl->sp4,
+                                                                   cl->v_flags, c->d_scal + 13);
+            timer_end(c, NBX_T_INTEGRATE);
+            NBX_CUDA(c, cudaGetLastError());
+        } else {
+            NBX_TRY(launch_vv_pos(c, dt));
+            NBX_TRY(slab_verlet_check(c, 1.0, nullptr, c->d_scal + 13));
+        }
+        cudaGraphConditionalHandle h{};
+        bool have_h = false;
+        NBX_TRY(cond_handle_create(c, &h, &have_h));
+        NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, cl->v_flags, have_h ? &h : nullptr));
         s.cond = cl->v_flags;
         CondScope scope;
-        NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope));
+        NBX_TRY(cond_scope_begin(c, cl->v_flags, &scope, have_h ? &h : nullptr));
         int rc = slab_pack(c);                         // migration round
         if (rc == NBX_OK) rc = slab_unpack(c, nullptr);
         s.record_halo = true;                          // halo round incl. the arrivals, remembered
@@ -754,12 +798,16 @@ static int slab_one_step(nbx_ctx *c, double dt)
         s.phase = 0;
         const int rc2 = cond_scope_end(c, &scope);
         if (rc != NBX_OK || rc2 != NBX_OK) { s.cond = nullptr; return rc != NBX_OK ? rc : rc2; }
+        s.refresh_cl = lists ? cl : nullptr;
         rc = slab_refresh_send(c);                     // (skipped on the device when the rebuild ran)
         if (rc == NBX_OK) rc = slab_refresh_recv(c);
+        s.refresh_cl = nullptr;
         s.cond = nullptr;
         NBX_TRY(rc);
+        s.records_fresh = lists;                       // (a rebuild writes the records from the same positions)
         s.phase = 2;
     } else {
+        NBX_TRY(launch_vv_pos(c, dt));
         if (needT) NBX_TRY(comm_allreduce3(c, c->d_scal, c->d_scal + 12, nullptr));
         NBX_TRY(slab_pack(c));
         NBX_TRY(slab_unpack(c, nullptr));
@@ -767,6 +815,7 @@ static int slab_one_step(nbx_ctx *c, double dt)
     std::swap(c->acc, c->acc_old);
     const int rc = compute_pairs(c);
     s.phase = 0;
+    s.records_fresh = false;
     NBX_TRY(rc);
     return launch_vv_vel(c, dt, true);
 }
@@ -786,6 +835,7 @@ int slab_enqueue(nbx_ctx *c, double dt, int64_t nsteps)
     if (c->thermo == NBX_THERMO_ANDERSEN || c->thermo == NBX_THERMO_LANGEVIN || c->thermo == NBX_THERMO_NOSEHOOVER)
         return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_vv: slabs run NVE or with the Berendsen thermostat");
     NBX_TRY(comm_arm_global0(c));
+    NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream)); // the all-reduce re-zeroes the flags it has read
     NBX_TRY(steps_graphed(c, 13, dt, nsteps, true, s.verlet ? 2 : 6, [&]() { return slab_one_step(c, dt); }));
     // leave the scalar block as a single context does: [0] = the sum over all ranks
     NBX_CUDA(c, cudaMemsetAsync(c->d_scal + 13, 0, 2 * sizeof(double), c->stream));
@@ -810,6 +860,7 @@ int slab_finish(nbx_ctx *c)
 void preload_slab()
 {
     cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, slab_pos_kernel);
     cudaFuncGetAttributes(&a, slab_count_kernel);
     cudaFuncGetAttributes(&a, slab_scan_kernel);
     cudaFuncGetAttributes(&a, slab_pack_kernel);
