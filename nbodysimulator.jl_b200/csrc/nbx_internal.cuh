@@ -66,7 +66,7 @@ struct SlabState {
     bool on = false, packed = false, first = false; // first: the next pack selects the slab from the full upload
     bool direct = false;                            // neighbours' receive areas are mapped: the pack kernel stores into them
     double *rx = nullptr;                           // receive area: flags + 4 message buffers (2 sides x 2 parities)
-    int64_t rx_doubles = 0;
+    int64_t rx_doubles = 0, ll_off = 0;             // ll_off: start of the LL area (halo refresh of slab_enqueue) inside rx
     double *peer[2] = {nullptr, nullptr};           // receive areas of the left / right neighbour (direct mode)
     std::vector<void *> ipc_opened;
     int rank = 0, nranks = 1;
@@ -101,8 +101,8 @@ struct SlabState {
 // system-scope stores and spin on their own window: scalar all-reduces, "positions of step k have landed" and "partial
 // accelerations of step k are complete" flags.  No collective library and no host in the loop.
 constexpr int kMaxRanks = 16;
-constexpr int kWinScal = 64;                        // [2 parities][kMaxRanks][4] doubles: seq, v0, v1, v2
-constexpr int kWinPos = kWinScal + 2 * kMaxRanks * 4;  // [kMaxRanks] int64: positions of sequence number s have landed
+constexpr int kWinScal = 64;                        // [2 parities][kMaxRanks][8] LL words: three doubles as 6 x {32-bit half, tag}
+constexpr int kWinPos = kWinScal + 2 * kMaxRanks * 8;  // [kMaxRanks] int64: positions of sequence number s have landed
 constexpr int kWinAcc = kWinPos + kMaxRanks;           // [kMaxRanks] int64: partial accelerations s are staged
 constexpr int kWinDoubles = kWinAcc + kMaxRanks + 32;
 enum { SEQ_SCAL = 0, SEQ_POS = 1, SEQ_ACC = 2, SEQ_TICKET = 3, SEQ_TIMEOUT = 4, SEQ_TICKET2 = 5, SEQ_GLOBAL0 = 6, SEQ_N = 8 };
@@ -489,6 +489,34 @@ __device__ __forceinline__ double rcp_fast(double x)
     const double e = fma(-x, y0, 1.0);
     const double p = fma(e, e, e);
     return fma(y0, p, y0);
+}
+
+// "LL" words (the low-latency protocol of collective libraries): a 64-bit store is atomic, so {32-bit payload, 32-bit tag}
+// validates itself -- the receiver spins on the tag, and neither side needs a fence, a flag or a completion count.
+__device__ __forceinline__ void ll_store(unsigned long long *dst, double v, unsigned tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    *reinterpret_cast<volatile unsigned long long *>(dst) = t | (b & 0xffffffffull);
+    *reinterpret_cast<volatile unsigned long long *>(dst + 1) = t | (b >> 32);
+}
+// false on a time-out
+__device__ __forceinline__ bool ll_load(const unsigned long long *src, unsigned tag, unsigned long long timeout_ns, double *out)
+{
+    const volatile unsigned long long *p = reinterpret_cast<const volatile unsigned long long *>(src);
+    unsigned long long lo = p[0], hi = p[1];
+    if ((unsigned)(lo >> 32) != tag || (unsigned)(hi >> 32) != tag) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            lo = p[0]; hi = p[1];
+            if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) return false;
+        }
+    }
+    *out = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return true;
 }
 
 // one 32-byte cell-order record with a single 256-bit load (LDG.E.ENL2.256): half the L1 sector traffic of

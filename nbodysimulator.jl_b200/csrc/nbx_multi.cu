@@ -68,14 +68,14 @@ __global__ void comm_allreduce3_kernel(CommDev cd, const double *in0, double *in
         double a = in0 ? in0[0] : 0.0;
         if (in0_rank0_only && cd.rank != 0) a = 0.0;
         const double b = in12 ? in12[0] : 0.0, e = in12 ? in12[1] : 0.0;
-        volatile double *slot = cd.win[t] + kWinScal + ((s & 1) * kMaxRanks + cd.rank) * 4;
-        slot[1] = a; slot[2] = b; slot[3] = e;
-        __threadfence_system();
-        slot[0] = (double)s;
-        const volatile double *mine = cd.win[cd.rank] + kWinScal + ((s & 1) * kMaxRanks + t) * 4;
-        if (!spin_ge_d(mine, (double)s, cd.timeout_ns)) bad = 1;
-        __threadfence_system();
-        v[t][0] = mine[1]; v[t][1] = mine[2]; v[t][2] = mine[3];
+        // LL words: no fence, no flag -- every 64-bit word carries its own tag (the sequence number)
+        unsigned long long *slot = reinterpret_cast<unsigned long long *>(cd.win[t] + kWinScal) + ((s & 1) * kMaxRanks + cd.rank) * 8;
+        ll_store(slot, a, (unsigned)s); ll_store(slot + 2, b, (unsigned)s); ll_store(slot + 4, e, (unsigned)s);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(cd.win[cd.rank] + kWinScal) + ((s & 1) * kMaxRanks + t) * 8;
+        if (!ll_load(mine, (unsigned)s, cd.timeout_ns, &v[t][0]) || !ll_load(mine + 2, (unsigned)s, cd.timeout_ns, &v[t][1]) ||
+            !ll_load(mine + 4, (unsigned)s, cd.timeout_ns, &v[t][2])) {
+            bad = 1; v[t][0] = v[t][1] = v[t][2] = 0.0;
+        }
     }
     __syncthreads();
     if (t == 0) {

@@ -33,6 +33,7 @@
 // leftmost layer and is a ghost of the left neighbour only, which kept it).
 #include "nbx_internal.cuh"
 
+#include <algorithm>
 #include <cstring>
 
 namespace nbx {
@@ -47,7 +48,9 @@ enum { CAT_STAY = 0, CAT_MIGL = 1, CAT_MIGR = 2, CAT_HALOL = 3, CAT_HALOR = 4, C
 enum { CNT_ARRL = 5, CNT_ARRR = 6, CNT_N = 8 };
 // persistent counters d_n
 enum { DN_OWN = 0, DN_GHOST = 1, DN_LOST = 2, DN_CAP = 3, DN_MSG = 4, DN_TICKET = 5, DN_TIMEOUT = 6, DN_HALOL = 8, DN_HALOR = 9,
+       DN_RHALOL = 10, DN_RHALOR = 11, // halo records RECEIVED from the left / right at the last rebuild
        DN_N = 12 };
+constexpr int kLLWords = 6; // x, y, z as LL words
 constexpr int kRxHdr = 16; // doubles in front of the receive area: [0] 'message m from the left is complete', [1] same from the right
 
 
@@ -330,6 +333,50 @@ __global__ void slab_halo_recv_kernel(SlabArrays dst, int64_t ld, int *__restric
     if (slot_of) sp4[slot_of[d]] = make_double4(rec[1], rec[2], rec[3], dst.charge ? dst.charge[d] : 0.0);
 }
 
+// Halo refresh of slab_enqueue between rebuilds, LL protocol: the current positions of the recorded boundary-layer particles
+// go straight into the neighbours' LL areas as self-validating 64-bit words tagged with the step's exchange number (the
+// all-reduce that precedes it in every rank's stream is the barrier that makes one buffer enough).  No fence, no flag, no
+// completion count; the receiver's threads each wait for their own six words and write position + cell-order record.
+__global__ void __launch_bounds__(256) slab_ll_send_kernel(const double *__restrict__ pos, int64_t ld, const int *__restrict__ idxL,
+                                                           const int *__restrict__ idxR, const int *__restrict__ dn,
+                                                           unsigned long long *outL, unsigned long long *outR, int capH,
+                                                           const int *__restrict__ seq, const int *__restrict__ skip)
+{
+    if (skip && skip[0]) return;
+    const unsigned tag = (unsigned)seq[0];
+    const int nL = dn[DN_HALOL], nR = dn[DN_HALOR];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * capH; t += gridDim.x * blockDim.x) {
+        const int side = t / capH, k = t - side * capH;
+        if (k >= (side == 0 ? nL : nR)) continue;
+        const int i = (side == 0 ? idxL : idxR)[k];
+        unsigned long long *w = (side == 0 ? outL : outR) + (size_t)k * kLLWords;
+        ll_store(w, pos[i], tag); ll_store(w + 2, pos[ld + i], tag); ll_store(w + 4, pos[2 * ld + i], tag);
+    }
+}
+
+__global__ void __launch_bounds__(256) slab_ll_recv_kernel(double *__restrict__ pos, const double *__restrict__ charge, int64_t ld,
+                                                           int *__restrict__ dn, const unsigned long long *__restrict__ ll, int capH,
+                                                           const int *__restrict__ seq, const int *__restrict__ skip,
+                                                           unsigned long long timeout_ns, const int *__restrict__ slot_of,
+                                                           double4 *__restrict__ sp4)
+{
+    if (skip && skip[0]) return;
+    const unsigned tag = (unsigned)seq[0];
+    const int haloL = dn[DN_RHALOL], haloR = dn[DN_RHALOR], n_own = dn[DN_OWN];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = t / capH, k = t - side * capH;
+    if (side >= 2 || k >= (side == 0 ? haloL : haloR)) return;
+    const unsigned long long *w = ll + ((size_t)side * capH + k) * kLLWords;
+    double x, y, z;
+    if (!ll_load(w, tag, timeout_ns, &x) || !ll_load(w + 2, tag, timeout_ns, &y) || !ll_load(w + 4, tag, timeout_ns, &z)) {
+        dn[DN_TIMEOUT] = 1;
+        return;
+    }
+    const int d = n_own + (side == 0 ? 0 : haloL) + k;
+    pos[d] = x; pos[ld + d] = y; pos[2 * ld + d] = z;
+    sp4[slot_of[d]] = make_double4(x, y, z, charge ? charge[d] : 0.0);
+}
+
 // Position update of the own particles fused with what a regular step needs next: the displacement check against the
 // build-time positions (-> flags[1] = 1.0 when a particle moved more than skin/2, or a list overflowed) and the refresh of
 // the particle's cell-order record.  Same arithmetic as vv_pos_kernel / slab_verlet_check_kernel / verlet_refresh_kernel.
@@ -396,6 +443,7 @@ __global__ void slab_unpack_kernel(SlabArrays dst, int64_t ld, int64_t cap_cols,
     const bool fits = (int64_t)n_own + n_ghost <= cap_cols;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counts[CNT_ARRL] = arrL; counts[CNT_ARRR] = arrR;
+        dn[DN_RHALOL] = haloL; dn[DN_RHALOR] = haloR;
         dn[DN_OWN] = fits ? n_own : 0; dn[DN_GHOST] = fits ? n_ghost : 0;
         if (!fits) dn[DN_CAP] = 1;
     }
@@ -544,7 +592,8 @@ int slab_init(nbx_ctx *c, int rank, int nranks)
         NBX_CUDA(c, cudaMemsetAsync(s.msg[k], 0, sizeof(double) * (size_t)s.msg_doubles, c->stream));
     }
     // receive area: flags + {from-left, from-right} x {parity 0, 1}; host-driven exchanges use parity 0
-    s.rx_doubles = kRxHdr + 4 * s.msg_doubles;
+    s.ll_off = kRxHdr + 4 * s.msg_doubles;                      // LL area: [from-left, from-right][capH][6 words]
+    s.rx_doubles = s.ll_off + 2 * s.capH * kLLWords;
     NBX_TRY(dev_alloc(c, &s.rx, (size_t)s.rx_doubles));
     NBX_CUDA(c, cudaMemsetAsync(s.rx, 0, sizeof(double) * (size_t)s.rx_doubles, c->stream));
     s.msg[2] = s.rx + kRxHdr;
@@ -798,10 +847,26 @@ static int slab_one_step(nbx_ctx *c, double dt)
         s.phase = 0;
         const int rc2 = cond_scope_end(c, &scope);
         if (rc != NBX_OK || rc2 != NBX_OK) { s.cond = nullptr; return rc != NBX_OK ? rc : rc2; }
-        s.refresh_cl = lists ? cl : nullptr;
-        rc = slab_refresh_send(c);                     // (skipped on the device when the rebuild ran)
-        if (rc == NBX_OK) rc = slab_refresh_recv(c);
-        s.refresh_cl = nullptr;
+        if (lists) { // LL halo refresh (skipped on the device when the rebuild ran); one slab has no neighbours at all
+            if (s.nranks > 1) {
+                const int *seq = c->comm.d_seq + SEQ_SCAL;
+                unsigned long long *toL = reinterpret_cast<unsigned long long *>(s.peer[0] + s.ll_off) + (size_t)s.capH * kLLWords; // left's from-right
+                unsigned long long *toR = reinterpret_cast<unsigned long long *>(s.peer[1] + s.ll_off);                           // right's from-left
+                const int64_t threads = 2 * s.capH;
+                const unsigned sgrid = (unsigned)std::min<int64_t>((threads + 255) / 256, (int64_t)c->sm_count * 2);
+                timer_begin(c, NBX_T_INTEGRATE);
+                slab_ll_send_kernel<<<sgrid, 256, 0, c->stream>>>(c->pos, c->npad, s.halo_idx[0], s.halo_idx[1], s.d_n, toL, toR, (int)s.capH,
+                                                                 seq, s.cond);
+                slab_ll_recv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(
+                    c->pos, c->charge, c->npad, s.d_n, reinterpret_cast<const unsigned long long *>(s.rx + s.ll_off), (int)s.capH, seq, s.cond,
+                    (unsigned long long)c->spin_timeout_ms * 1000000ull, cl->slot_of, cl->sp4);
+                timer_end(c, NBX_T_INTEGRATE);
+                NBX_CUDA(c, cudaGetLastError());
+            }
+        } else {
+            rc = slab_refresh_send(c);
+            if (rc == NBX_OK) rc = slab_refresh_recv(c);
+        }
         s.cond = nullptr;
         NBX_TRY(rc);
         s.records_fresh = lists;                       // (a rebuild writes the records from the same positions)
@@ -861,6 +926,8 @@ void preload_slab()
 {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, slab_pos_kernel);
+    cudaFuncGetAttributes(&a, slab_ll_send_kernel);
+    cudaFuncGetAttributes(&a, slab_ll_recv_kernel);
     cudaFuncGetAttributes(&a, slab_count_kernel);
     cudaFuncGetAttributes(&a, slab_scan_kernel);
     cudaFuncGetAttributes(&a, slab_pack_kernel);
