@@ -630,11 +630,13 @@ def run_b200(args):
     kernel_ms = k_ms / max(k_cnt, 1)
     instr_pp = 9 if pairs_mode else 16  # FP64-pipe instructions per ORDERED pair
     share = 1.0 / world
-    if pairs_mode and world > 1:   # rank 0's ring offsets k = 0, world, 2 world, ... <= K of the NT-tile half ring (k = K of an even ring is half an offset)
-        NT = -(-n // 1024)
+    if pairs_mode and world > 1:   # rank 0's ring offsets k = 0, world, 2 world, ... of the NT-tile half ring; the half offset k = K of an
+        NT = -(-n // 1024)         # even ring is dealt out over all ranks by tile (csrc/nbx_sympairs.cu)
         K = NT // 2
-        units = lambda ks: sum(0.5 if (NT % 2 == 0 and k == K and K > 0) else 1.0 for k in ks)  # noqa: E731
-        share = units(range(0, K + 1, world)) / units(range(0, K + 1))
+        if NT % 2 == 0 and K > 0:
+            share = (len(range(0, K, world)) + 0.5 / world) / (K + 0.5)
+        else:
+            share = len(range(0, K + 1, world)) / (K + 1.0)
     pairs_per_launch = pairs_per_step * share
     achieved_tf = FLOP_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e12
     traffic = captured_traffic("void sym_kernel") if world == 1 else None

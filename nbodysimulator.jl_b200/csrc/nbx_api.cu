@@ -153,7 +153,15 @@ int compute_pairs(nbx_ctx *c)
             const bool accum = acc_flag();
             NBX_TRY(cells_pairs(c, &c->cl_el, c->el_R, pot, c->pos, c->charge, c->gid, c->n, c->slab.on ? c->slab.n_total : c->n,
                                 c->npad, c->water ? 3 : 1, lo, hi, 1, c->acc, c->npad, accum, &used));
-            if (!used) NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, accum));
+            if (!used) {
+                // no cell list for this cutoff (R >= L/3): all pairs with the exact periodic predicate -- once per UNORDERED pair
+                // when the context evaluates every target, the box is cubic and R < L/2 (no accepted pair on the wrap tie)
+                const bool whole = lo == 0 && hi == c->n && c->pair_nranks == 1 && !c->slab.on;
+                if (whole && c->opt_sym && c->n >= c->sym_min_n && c->bc_kind == NBX_BC_CUBIC && c->el_R < 0.5 * c->bc[0])
+                    NBX_TRY(launch_sympairs_coulomb_pbc(c, pot == 2, c->acc, accum));
+                else
+                    NBX_TRY(launch_allpairs_pbc(c, pot, c->pos, c->n, c->npad, lo, hi, 1, c->acc, c->npad, accum));
+            }
         }
     }
     if (c->has_dip) NBX_TRY(launch_allpairs_dipole(c, c->acc, acc_flag()));

@@ -284,6 +284,7 @@ int launch_allpairs_dipole(nbx_ctx *c, double *acc_out, bool accumulate);
 // nbx_sympairs.cu
 int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int scale_kind, double scale,
                     double *acc_out, bool accumulate);
+int launch_sympairs_coulomb_pbc(nbx_ctx *c, bool excl3, double *acc_out, bool accumulate);
 int launch_allpairs_pbc(nbx_ctx *c, int pot, const double *px, int64_t n, int64_t ld, int64_t lo, int64_t hi,
                         int mstride, double *acc_out, int64_t ld_out, bool accumulate);
 // nbx_cells.cu

@@ -21,23 +21,34 @@
 // segment.  sym_reduce_kernel adds all slots of a body in ascending slot order -> bit-reproducible.
 #include "nbx_internal.cuh"
 
+#include <cstring>
+
 namespace nbx {
 
 struct SymParams {
     const double *x, *y, *z, *w;
     int n, npad;
     int NT, K;             // tiles; largest ring offset
-    int kr0, kstride, M;   // this rank's offsets k(m) = kr0 + m * kstride, m = 0..M-1
+    int kr0, kstride, M;   // this rank's offsets k(m) = kr0 + m * kstride for m < M0; m = M0 (if M > M0): the half offset K
+    int M0;                // of an even ring, which EVERY rank takes a share of (tiles A = rank mod kstride): balanced shares
     int S, seg_len;        // segments of the local offset list
     double *part;          // [(S + M)][3][npad]: A-side slots per segment, then B-side slots per local offset
+    // periodic cutoff variant (PBC = 1): cubic box edge, half edge, squared cutoff, high word of the half edge
+    double L, radius, R2;
+    int hi_radius;
 };
 
-template <int T, int U, bool UNIFORM, bool DIAG, int UNR>
+// PBC = 1: Coulomb with a cutoff under CubicPeriodicBoundaryConditions (src/basic_potentials.jl:288-297 with the distance of
+// src/boundary_conditions.jl:138-165): rij = ri - rj in the reference's orientation (i = the stationary body), the compare-
+// and-subtract wrap, un-fused r2, strict r2 < R2.  For R < L/2 no accepted pair has a component on the +-L/2 tie, so the
+// partner's own evaluation, wrap(rj - ri), is exactly -wrap(ri - rj): one evaluation serves both bodies with the reference's
+// pair set.  EXCL3: pairs inside one molecule (i/3 == j/3) are skipped (src/nbody_to_ode.jl:331-351).
+template <int T, int U, bool UNIFORM, bool DIAG, int UNR, int PBC = 0, bool EXCL3 = false>
 __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&ay)[T], const double (&az)[T],
                                           const double (&aw)[T], double (&fx)[T], double (&fy)[T], double (&fz)[T],
                                           double (&bx)[U], double (&by)[U], double (&bz)[U], double (&bw)[U],
                                           double (&gx)[U], double (&gy)[U], double (&gz)[U], int lane, int ibase,
-                                          int jbase)
+                                          int jbase, const SymParams *pp = nullptr)
 {
     const int src = (lane + 1) & 31;
 #pragma unroll(UNR)
@@ -46,8 +57,32 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
         for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const double dx = bx[u] - ax[t], dy = by[u] - ay[t], dz = bz[u] - az[t];
-                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double dx, dy, dz, r2;
+                bool ok = true;
+                if (PBC) {
+                    double x = __dsub_rn(ax[t], bx[u]), y = __dsub_rn(ay[t], by[u]), z = __dsub_rn(az[t], bz[u]);
+                    const int hx = __double2hiint(x) & 0x7fffffff, hy = __double2hiint(y) & 0x7fffffff,
+                              hz = __double2hiint(z) & 0x7fffffff;
+                    const int hm = max(hx, max(hy, hz));
+                    if (hm >= pp->hi_radius) {
+                        if (hm >= 0x5d000000) ok = false; // a padding body (parked at 1e150): weight 0, never in the cutoff
+                        else {
+                            x = wrap_cubic(x, pp->radius, pp->L); y = wrap_cubic(y, pp->radius, pp->L); z = wrap_cubic(z, pp->radius, pp->L);
+                        }
+                    }
+                    r2 = r2_unfused(x, y, z);
+                    ok = ok && (__double_as_longlong(r2) < __double_as_longlong(pp->R2));
+                    if (EXCL3) {
+                        const int j = jbase + u * 32 + ((lane + s) & 31);
+                        const int i = ibase + t * 32 + lane;
+                        ok = ok && (i / 3 != j / 3);
+                    }
+                    dx = -x; dy = -y; dz = -z;
+                    r2 = ok ? r2 : 1.0;
+                } else {
+                    dx = bx[u] - ax[t]; dy = by[u] - ay[t]; dz = bz[u] - az[t];
+                    r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                }
                 if (DIAG) {
                     // body index of source u at this step vs target t (same tile)
                     const int j = jbase + u * 32 + ((lane + s) & 31);
@@ -60,7 +95,8 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
                 const double y3 = a * y0;
                 const double p = fma(1.875, e, 1.5);
                 const double q = p * e;
-                const double g = fma(y3, q, y3); // r^-3 to ~3 ulp
+                double g = fma(y3, q, y3); // r^-3 to ~3 ulp
+                if (PBC) g = ok ? g : 0.0;
                 if (UNIFORM) {
                     fx[t] = fma(g, dx, fx[t]); fy[t] = fma(g, dy, fy[t]); fz[t] = fma(g, dz, fz[t]);
                     if (!DIAG) { gx[u] = fma(-g, dx, gx[u]); gy[u] = fma(-g, dy, gy[u]); gz[u] = fma(-g, dz, gz[u]); }
@@ -91,13 +127,15 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
     // after 32 passes every body (and its accumulator) is back in the lane that loaded it
 }
 
-// offset k of tile A is skipped when it would visit a tile pair twice (even NT, k = NT/2, upper half)
-__host__ __device__ __forceinline__ bool sym_live(int k, int A, int NT, int K)
+// offset k of tile A is skipped when it would visit a tile pair twice (even NT, k = NT/2, upper half); the lower half of
+// that offset is dealt out over the ranks by tile (a whole offset more on one rank would cost it 1 / (2 offsets per rank))
+__host__ __device__ __forceinline__ bool sym_live(int k, int A, int NT, int K, int rank, int nranks)
 {
-    return !((NT & 1) == 0 && k == K && K > 0 && A >= K);
+    if ((NT & 1) == 0 && k == K && K > 0) return A < K && (A % nranks) == rank;
+    return true;
 }
 
-template <int T, int U, bool UNIFORM, int MINB, int UNR>
+template <int T, int U, bool UNIFORM, int MINB, int UNR, int PBC = 0, bool EXCL3 = false>
 __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
 {
     constexpr int TS = 128 * T;       // bodies per tile
@@ -119,7 +157,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     uint32_t parity = 0;
 
     const int nitems = p.NT * p.S;
-    auto kof = [&](int m) { return p.kr0 + m * p.kstride; };
+    auto kof = [&](int m) { return m < p.M0 ? p.kr0 + m * p.kstride : p.K; };
     // B tile of (tile A, local offset index m) -> stage st
     auto issue = [&](int A, int m, int st) {
         const int B0 = ((A + kof(m)) % p.NT) * TS;
@@ -130,7 +168,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
         bulk_g2s(dst + 2 * TS, p.z + B0, TS * sizeof(double), &full[st]);
         bulk_g2s(dst + 3 * TS, p.w + B0, TS * sizeof(double), &full[st]);
     };
-    auto next_live = [&](int A, int m, int mend) { while (m < mend && !sym_live(kof(m), A, p.NT, p.K)) ++m; return m; };
+    auto next_live = [&](int A, int m, int mend) { while (m < mend && !sym_live(kof(m), A, p.NT, p.K, p.kr0, p.kstride)) ++m; return m; };
     int st = 0;              // ring stage of the next tile: runs on across items
     bool have_first = false; // the previous item already issued this item's first tile (a short segment must not
                              // expose the copy latency once per item: multi-GPU shares have two offsets per segment)
@@ -184,11 +222,16 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
                     gx[u] = gy[u] = gz[u] = 0.0;
                 }
                 if (k == 0) {
-                    ring_pass<T, U, UNIFORM, true, 1>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
-                                                      B0 + set * SET);
+                    ring_pass<T, U, UNIFORM, true, 1, PBC, EXCL3>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane, ibase,
+                                                                  B0 + set * SET, &p);
                 } else {
-                    ring_pass<T, U, UNIFORM, false, UNR>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane,
-                                                         ibase, B0 + set * SET);
+                    // (molecules only straddle ADJACENT tiles: the exclusion test is compiled into the k = 1 pass alone)
+                    if (EXCL3 && k == 1)
+                        ring_pass<T, U, UNIFORM, false, 1, PBC, true>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane,
+                                                                      ibase, B0 + set * SET, &p);
+                    else
+                        ring_pass<T, U, UNIFORM, false, UNR, PBC, false>(ax, ay, az, aw, fx, fy, fz, bx, by, bz, bw, gx, gy, gz, lane,
+                                                                         ibase, B0 + set * SET, &p);
                     // B-side sums of the four warps, added in warp order, go to the slot of this ring offset
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -238,10 +281,10 @@ __global__ void sym_reduce_kernel(const SymParams p, int TS, int kind, double sc
         s0 += b[i]; s1 += b[np + i]; s2 += b[2 * np + i];
     }
     for (int m = 0; m < p.M; ++m) {
-        const int k = p.kr0 + m * p.kstride;
+        const int k = m < p.M0 ? p.kr0 + m * p.kstride : p.K;
         if (k == 0) continue;                                       // the diagonal block has no B side
         const int A = (tile - k % p.NT + p.NT) % p.NT;               // the tile that visited us at this offset
-        if (!sym_live(k, A, p.NT, p.K)) continue;
+        if (!sym_live(k, A, p.NT, p.K, p.kr0, p.kstride)) continue;
         const double *b = p.part + (size_t)(p.S + m) * 3 * np;
         s0 += b[i]; s1 += b[np + i]; s2 += b[2 * np + i];
     }
@@ -251,9 +294,9 @@ __global__ void sym_reduce_kernel(const SymParams p, int TS, int kind, double sc
     else { ax[i] = f * s0; ay[i] = f * s1; az[i] = f * s2; }
 }
 
-template <int T, int U, bool UNIFORM, int MINB, int UNR>
+template <int T, int U, bool UNIFORM, int MINB, int UNR, int PBC = 0, bool EXCL3 = false>
 static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, double scale, double *acc_out,
-                   bool accumulate)
+                   bool accumulate, double R2 = 0.0)
 {
     constexpr int TS = 128 * T, SET = 32 * U;
     SymParams p{};
@@ -263,7 +306,16 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
     p.K = p.NT / 2;
     p.kr0 = c->pair_rank;
     p.kstride = c->pair_nranks;
-    p.M = p.kr0 <= p.K ? (p.K - p.kr0) / p.kstride + 1 : 0;
+    if (PBC) {
+        p.L = c->bc[0]; p.radius = 0.5 * c->bc[0]; p.R2 = R2;
+        int64_t bits;
+        memcpy(&bits, &p.radius, sizeof bits);
+        p.hi_radius = (int)(bits >> 32);
+    }
+    const bool half = (p.NT % 2 == 0) && p.K > 0;      // even ring: offset K is half an offset, shared by all ranks
+    const int kfull = half ? p.K - 1 : p.K;            // largest whole offset
+    p.M0 = p.kr0 <= kfull ? (kfull - p.kr0) / p.kstride + 1 : 0;
+    p.M = p.M0 + (half ? 1 : 0);
     const int grid_full = c->sm_count * MINB;
     // enough items for a balanced static round-robin (>= ~24 per CTA), at least 2 offsets per segment
     int S = (24 * grid_full + p.NT - 1) / p.NT;
@@ -280,7 +332,7 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
         c->part_bytes = bytes;
     }
     p.part = c->part;
-    auto kern = sym_kernel<T, U, UNIFORM, MINB, UNR>;
+    auto kern = sym_kernel<T, U, UNIFORM, MINB, UNR, PBC, EXCL3>;
     const size_t smem = (size_t)(2 * 4 * TS + 4 * 3 * SET) * sizeof(double);
     const void *key = reinterpret_cast<const void *>(kern);
     bool done = false;
@@ -341,6 +393,15 @@ int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int 
         if (uniform) return run_sym<8, 2, true, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
         return run_sym<8, 2, false, 2, 4>(c, w, wval, scale_kind, scale, acc_out, accumulate);
     }
+}
+
+// Coulomb with a cutoff in a cubic periodic box as all UNORDERED pairs (the boxes a cell list cannot serve: R >= L/3):
+// half the evaluations of the ordered kernel with the exact periodic predicate.  excl3: own-molecule exclusion (water).
+// The caller has checked R < L/2 and that the context evaluates all targets.
+int launch_sympairs_coulomb_pbc(nbx_ctx *c, bool excl3, double *acc_out, bool accumulate)
+{
+    if (excl3) return run_sym<8, 2, false, 2, 2, 1, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2);
+    return run_sym<8, 2, false, 2, 2, 1, false>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2);
 }
 
 } // namespace nbx

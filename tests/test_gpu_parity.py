@@ -749,3 +749,44 @@ def test_langevin_drift_is_the_oracles_without_noise(oracle, kind):
     assert rel_err_per_body(vg, y).max() < 1e-11
     _check(ag, s.rhs(x, y, NT))   # a(x_end) is left resident
     ctx.close()
+
+
+@pytest.mark.parametrize("water", [False, True])
+def test_coulomb_cutoff_beyond_the_cell_list_uses_each_pair_once(oracle, water):
+    """Coulomb with a cutoff of 0.49 L in a cubic periodic box (no cell list possible: R >= L/3): the Newton's-third-law
+    kernel with the reference's periodic predicate (rij = ri - rj wrapped into [-L/2, L/2), un-fused r2, strict <) must
+    reproduce the ordered all-pairs kernel and the oracle; lattice sites put many pairs exactly on the +-L/2 wrap tie
+    (all of them outside the cutoff), drifted coordinates exercise the wrap loops, water the own-molecule exclusion
+    across tile boundaries (1,024 is not a multiple of 3)."""
+    rng = np.random.Generator(np.random.Philox(91))
+    m, L = 22, 11.0
+    g = (np.arange(m) + 0.5) * (L / m)
+    sites = np.stack(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1)          # 10,648 sites
+    if water:
+        nm = 3000
+        o = sites[:, rng.choice(sites.shape[1], nm, replace=False)] + 0.02 * rng.standard_normal((3, nm))
+        u = np.empty((3, 3 * nm))
+        u[:, 0::3] = o
+        u[:, 1::3] = o + np.array([[0.1], [0.0], [0.0]])
+        u[:, 2::3] = o + np.array([[-0.03], [0.0], [0.09]])
+        qs = np.tile([-0.82, 0.41, 0.41], nm)
+        ms = np.tile([15.999, 1.008, 1.008], nm)
+    else:
+        u = sites.copy()
+        u[:, ::2] += 0.03 * rng.standard_normal(u[:, ::2].shape)                  # half the sites stay exactly on the lattice
+        qs = np.where(np.arange(u.shape[1]) % 2 == 0, 1.0, -1.0) * (0.5 + rng.random(u.shape[1]))
+        ms = rng.random(u.shape[1]) + 1.0
+    u = F(u + L * rng.integers(-2, 3, size=u.shape))                              # the reference never wraps positions
+    spec = dict(ms=ms, qs=qs, water=water, bc=("cubic", L), coulomb=dict(k=1.7, R=0.49 * L))
+    s = make_oracle(oracle, spec)
+    targets = np.arange(0, u.shape[1], 23)
+    ref = s.accel_targets(u, targets, NT)
+    res = []
+    for sym in (1, 0):
+        ctx = make_context(spec)
+        ctx.set_option("symmetric_pairs", sym)
+        res.append(ctx.accel(u).copy())
+        assert ctx.info("cells_el") == 0
+        ctx.close()
+    _check_refereed(res[0][:, targets], ref, s, u, targets)
+    _check(res[0], res[1], tol=1e-13)
