@@ -149,6 +149,13 @@ NBX_API int nbx_upload(nbx_ctx *ctx, const double *u, const double *v);
 NBX_API int nbx_step_vv(nbx_ctx *ctx, double dt, int64_t nsteps);
 NBX_API int nbx_step_em(nbx_ctx *ctx, double dt, int64_t nsteps, uint64_t seed);
 NBX_API int nbx_download(nbx_ctx *ctx, double *u, double *v, double *dv);
+/* Frames for the result accessors (run_simulation(...; saveat), src/nbody_simulation_result.jl:468-487; SimulationResult
+ * :5-8, :49-104): nsteps velocity-Verlet steps on the device, the state copied out after every save_every steps and after
+ * the last one: frame k = the 3 x ncols arrays at u_frames + 3 ncols k (t = t0 + min((k + 1) save_every, nsteps) dt);
+ * either array may be NULL.  max_frames: capacity in frames (ceil(nsteps / save_every) are written; NBX_ERR_CAPACITY
+ * otherwise); *nframes receives the count.  Works on single contexts, group members and nbx_create_multi handles. */
+NBX_API int nbx_run_vv(nbx_ctx *ctx, double dt, int64_t nsteps, int64_t save_every, double *u_frames, double *v_frames,
+                       int64_t max_frames, int64_t *nframes);
 NBX_API int nbx_set_seed(nbx_ctx *ctx, uint64_t seed);
 
 /* Split form of one velocity-Verlet step for multi-GPU drivers that exchange positions

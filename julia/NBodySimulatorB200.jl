@@ -4,11 +4,17 @@
 # sequence of C-ABI calls is exercised from Python ctypes (nbodysimulator.jl_b200/_lib.py, tests/).
 # Every ccall below matches one prototype of include/nbody_b200.h.
 #
-# Two adapters over the one C ABI (SURVEY.md section 8b):
+# Three adapters over the one C ABI (SURVEY.md section 8b):
 #   (1) RHS drop-in   : B200Problem(sim) -> a normal SecondOrderODEProblem whose soode_system! is
 #                       `ccall(:nbx_accel, ...)`; any DiffEq integrator / callback / accessor works.
 #   (2) fused drop-in : run_simulation(sim, B200VelocityVerlet(); dt, saveat) runs the whole loop on
-#                       the device and wraps the saved frames in a SimulationResult.
+#                       the device (nbx_run_vv) and wraps the saved frames in a SimulationResult.
+#   (3) plugin closure: GPUPotential(parameters) <: PotentialParameters whose get_accelerating_function
+#                       returns the reference's own per-particle `acceleration!(dv, u, v, t, i)`
+#                       (src/nbody_to_ode.jl:156-242): one device evaluation per sweep, served column by column.
+# `device` is one CUDA ordinal or a collection of them (`device = 0:7`): several GPUs go through
+# nbx_create_multi -- the same calls on one handle, fanned out inside the library (pair sharding, x-slabs or
+# target blocks, exchanges over NVLink peer memory); nothing else changes on the Julia side.
 module NBodySimulatorB200
 
 using NBodySimulator
@@ -29,9 +35,14 @@ mutable struct B200Context
     h::Ptr{Cvoid}
     n::Int
     ncols::Int
-    function B200Context(device::Integer = 0)
+    function B200Context(device = 0)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:nbx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, device)
+        rc = if device isa Integer
+            ccall((:nbx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), ref, device)
+        else   # several GPUs of this process behind one handle
+            devs = Cint[d for d in device]
+            ccall((:nbx_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), ref, length(devs), devs)
+        end
         rc == 0 || throw(NbxError(rc, unsafe_string(ccall((:nbx_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
         ctx = new(ref[], 0, 0)
         finalizer(c -> ccall((:nbx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
@@ -112,7 +123,7 @@ end
 Same object `SciMLBase.SecondOrderODEProblem(simulation)` returns (src/nbody_to_ode.jl:460-491), with
 `soode_system!` evaluated on the GPU.  `u`, `v`, `dv` are the solver's own `Matrix{Float64}` (3 x ncols).
 """
-function B200Problem(s::NBodySimulation; device::Integer = 0)
+function B200Problem(s::NBodySimulation; device = 0)
     ctx = configure!(B200Context(device), s)
     (u0, v0, n) = gather_bodies_initial_coordinates(s)
     function soode_system!(dv, v, u, p, t)
@@ -131,26 +142,64 @@ function NBodySimulator.run_simulation(s::NBodySimulation, ::B200VelocityVerlet;
     (u0, v0, n) = gather_bodies_initial_coordinates(s)
     check(ctx, ccall((:nbx_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx.h, u0, v0))
     nsteps = round(Int, (s.tspan[2] - s.tspan[1]) / dt)
-    ts = [s.tspan[1]]
-    frames = [ArrayPartition(copy(v0), copy(u0))]
-    done = 0
-    while done < nsteps
-        k = min(saveat, nsteps - done)
-        check(ctx, ccall((:nbx_step_vv, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), ctx.h, dt, k))
-        done += k
-        u = similar(u0); v = similar(v0)
-        check(ctx, ccall((:nbx_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                         ctx.h, u, v, C_NULL))
-        push!(ts, s.tspan[1] + done * dt)
-        push!(frames, ArrayPartition(v, u))
-    end
+    nfr = cld(nsteps, saveat)
+    us = Array{Float64}(undef, 3, ctx.ncols, nfr)      # frame k = us[:, :, k]: consecutive 3 x ncols column-major arrays
+    vs = Array{Float64}(undef, 3, ctx.ncols, nfr)
+    got = Ref{Int64}(0)
+    check(ctx, ccall((:nbx_run_vv, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
+                     ctx.h, dt, nsteps, saveat, us, vs, nfr, got))
+    ts = [s.tspan[1]; [s.tspan[1] + min(k * saveat, nsteps) * dt for k in 1:got[]]]
+    frames = [ArrayPartition(copy(v0), copy(u0)); [ArrayPartition(vs[:, :, k], us[:, :, k]) for k in 1:got[]]]
     # a DiffEq-shaped solution so that get_position / temperature / energies / rdf / msd work unchanged
     prob = B200Problem(s; device = device)
     sol = SciMLBase.build_solution(prob, B200VelocityVerlet(), ts, frames; retcode = SciMLBase.ReturnCode.Success)
     return NBodySimulator.SimulationResult(sol, s)
 end
 
-# ---- (3) frame analysis on the device: rdf / msd (src/nbody_simulation_result.jl:664-783) ------------------------
+# ---- (3) the plugin interface itself: a PotentialParameters subtype served by the device ----------------------------
+"""
+    GPUPotential(parameters)
+
+Wraps one of the reference's parameter structs (LennardJonesParameters, ElectrostaticParameters, MagnetostaticParameters,
+GravitationalParameters).  `get_accelerating_function` then returns the reference's per-particle closure
+`acceleration!(dv, u, v, t, i)` (src/nbody_to_ode.jl:156-242, src/basic_potentials.jl:10-19): the first index of a sweep
+evaluates ALL accelerations of that potential on the device (one nbx_accel call on a context holding only this potential),
+later indices add the cached column -- so a `PotentialNBodySystem(bodies, Dict(:custom => GPUPotential(p)))` runs through the
+unmodified `soode_system!` loop (:474-488) of the reference.
+"""
+struct GPUPotential{P <: NBodySimulator.PotentialParameters} <: NBodySimulator.PotentialParameters
+    parameters::P
+    device::Any
+end
+GPUPotential(p) = GPUPotential(p, 0)
+
+function NBodySimulator.get_accelerating_function(g::GPUPotential, simulation::NBodySimulation)
+    p = g.parameters
+    name = p isa NBodySimulator.LennardJonesParameters ? :lennard_jones :
+           p isa NBodySimulator.ElectrostaticParameters ? :electrostatic :
+           p isa NBodySimulator.MagnetostaticParameters ? :magnetostatic :
+           p isa NBodySimulator.GravitationalParameters ? :gravitational : error("no B200 kernel for $(typeof(p))")
+    only = NBodySimulation(PotentialNBodySystem(simulation.system.bodies, Dict(name => p)), simulation.tspan,
+                           simulation.boundary_conditions, NullThermostat(), simulation.kb)
+    ctx = configure!(B200Context(g.device), only)
+    n = ctx.n
+    cache = zeros(3, n)
+    last_i = Ref(typemax(Int)); last_t = Ref(NaN); last_u = Ref{Ptr{Float64}}(C_NULL); last_sum = Ref(NaN)
+    return function (dv, u, v, t, i)
+        # a sweep visits i in ascending order (:475): a non-increasing index, another array, time or content starts a new one
+        if i <= last_i[] || t != last_t[] || pointer(u) != last_u[] || sum(view(u, :, 1:n)) != last_sum[]
+            uu = size(u, 2) == n ? u : u[:, 1:n]       # (Nose-Hoover states carry an extra column, :6-8)
+            check(ctx, ccall((:nbx_accel, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                             ctx.h, uu, C_NULL, t, cache))
+            last_t[] = t; last_u[] = pointer(u); last_sum[] = sum(view(u, :, 1:n))
+        end
+        last_i[] = i
+        dv .+= view(cache, :, i)
+        return nothing
+    end
+end
+
+# ---- (4) frame analysis on the device: rdf / msd (src/nbody_simulation_result.jl:664-783) ------------------------
 # Same return values as NBodySimulator.rdf / msd; the O(frames x N^2) pair loop runs in rdf_kernel (integer histogram,
 # identical counts), the normalisation is the reference's (:695-707).
 function rdf_b200(sr::NBodySimulator.SimulationResult; device::Integer = 0)
@@ -189,6 +238,6 @@ function msd_b200(sr::NBodySimulator.SimulationResult; device::Integer = 0)
     return (ts, dr2)
 end
 
-export B200Context, B200Problem, B200VelocityVerlet, rdf_b200, msd_b200
+export B200Context, B200Problem, B200VelocityVerlet, GPUPotential, rdf_b200, msd_b200
 
 end # module

@@ -52,6 +52,7 @@ SIGNATURES = {
     "nbx_step_vv": (C.c_int, [_vp, C.c_double, _i64]),
     "nbx_step_em": (C.c_int, [_vp, C.c_double, _i64, C.c_uint64]),
     "nbx_download": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "nbx_run_vv": (C.c_int, [_vp, C.c_double, _i64, _i64, _dp, _dp, _i64, C.POINTER(_i64)]),
     "nbx_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "nbx_vv_begin": (C.c_int, [_vp, C.c_double]),
     "nbx_vv_finish": (C.c_int, [_vp, C.c_double]),
@@ -242,6 +243,17 @@ class Context:
 
     def step_vv(self, dt, nsteps=1):
         self._ck(self.lib.nbx_step_vv(self.h, float(dt), int(nsteps)))
+
+    def run_vv(self, dt, nsteps, save_every=1, want_v=True):
+        """nsteps velocity-Verlet steps with the state saved every ``save_every`` steps: (u_frames, v_frames), each
+        (frames, 3, ncols) with the frames' arrays in Julia's column-major layout."""
+        frames = -(-int(nsteps) // int(save_every))
+        u = np.zeros((frames, self.ncols, 3))   # frame-major; each frame is 3 x ncols column-major = (ncols, 3) C-order
+        v = np.zeros((frames, self.ncols, 3)) if want_v else None
+        got = _i64()
+        self._ck(self.lib.nbx_run_vv(self.h, float(dt), int(nsteps), int(save_every), _p(u), _p(v), frames, C.byref(got)))
+        u = u[: got.value].transpose(0, 2, 1)
+        return u, (v[: got.value].transpose(0, 2, 1) if want_v else None)
 
     def step_em(self, dt, nsteps=1, seed=0):
         self._ck(self.lib.nbx_step_em(self.h, float(dt), int(nsteps), int(seed)))

@@ -9,6 +9,7 @@
 
 #include "nbx_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <utility>
 
@@ -948,6 +949,34 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     }
     for (; s < nsteps; ++s) NBX_TRY(one_step());
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return NBX_OK;
+}
+
+// run_simulation with saveat (src/nbody_simulation_result.jl:468-487): nsteps velocity-Verlet steps on the device, the state
+// copied out every save_every steps (and after the last one) as consecutive 3 x ncols frames -- what the Julia shim wraps
+// into the SciMLBase solution behind SimulationResult (:5-8, :49-104).
+int nbx_run_vv(nbx_ctx *c, double dt, int64_t nsteps, int64_t save_every, double *u_frames, double *v_frames, int64_t max_frames,
+               int64_t *nframes)
+{
+    if (!c) return NBX_ERR_INVALID;
+    if (nframes) *nframes = 0;
+    if (nsteps < 0 || save_every < 1) return fail(c, NBX_ERR_INVALID, "nbx_run_vv: nsteps >= 0 and save_every >= 1");
+    const int64_t ncols = c->is_group ? c->ncols : c->ncols;
+    const int64_t need = (nsteps + save_every - 1) / save_every;
+    if ((u_frames || v_frames) && max_frames < need)
+        return fail(c, NBX_ERR_CAPACITY, "nbx_run_vv: %lld frames needed, capacity %lld", (long long)need, (long long)max_frames);
+    int64_t done = 0, k = 0;
+    while (done < nsteps) {
+        const int64_t chunk = std::min<int64_t>(save_every, nsteps - done);
+        NBX_TRY(nbx_step_vv(c, dt, chunk));
+        done += chunk;
+        if (u_frames || v_frames) {
+            const size_t off = (size_t)k * 3 * (size_t)ncols;
+            NBX_TRY(nbx_download(c, u_frames ? u_frames + off : nullptr, v_frames ? v_frames + off : nullptr, nullptr));
+        }
+        ++k;
+    }
+    if (nframes) *nframes = k;
     return NBX_OK;
 }
 

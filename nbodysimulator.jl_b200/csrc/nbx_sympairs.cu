@@ -36,6 +36,8 @@ struct SymParams {
     // periodic cutoff variant (PBC = 1): cubic box edge, half edge, squared cutoff, high word of the half edge
     double L, radius, R2;
     int hi_radius;
+    const int *gate;       // the kernel runs iff gate == nullptr or gate[0] == gate_want (fast / general periodic variant)
+    int gate_want;
 };
 
 // PBC = 1: Coulomb with a cutoff under CubicPeriodicBoundaryConditions (src/basic_potentials.jl:288-297 with the distance of
@@ -59,16 +61,41 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
             for (int t = 0; t < T; ++t) {
                 double dx, dy, dz, r2;
                 bool ok = true;
-                if (PBC) {
+                if (PBC == 2) {
+                    // every coordinate lies within [-L/4, 5L/4) (checked on the device before the launch): |ri - rj| < 3L/2,
+                    // so ONE round of the reference's wrap loop settles every component; a component exactly on the tie
+                    // (-L/2 stays, +L/2 wraps) follows the loop's own conditions.  No branch, no integer work.
                     double x = __dsub_rn(ax[t], bx[u]), y = __dsub_rn(ay[t], by[u]), z = __dsub_rn(az[t], bz[u]);
-                    const int hx = __double2hiint(x) & 0x7fffffff, hy = __double2hiint(y) & 0x7fffffff,
-                              hz = __double2hiint(z) & 0x7fffffff;
+                    if (x >= pp->radius) x = __dsub_rn(x, pp->L); else if (x < -pp->radius) x = __dadd_rn(x, pp->L);
+                    if (y >= pp->radius) y = __dsub_rn(y, pp->L); else if (y < -pp->radius) y = __dadd_rn(y, pp->L);
+                    if (z >= pp->radius) z = __dsub_rn(z, pp->L); else if (z < -pp->radius) z = __dadd_rn(z, pp->L);
+                    r2 = r2_unfused(x, y, z);
+                    ok = r2 < pp->R2;
+                    if (EXCL3) {
+                        const int j = jbase + u * 32 + ((lane + s) & 31);
+                        const int i = ibase + t * 32 + lane;
+                        ok = ok && (i / 3 != j / 3);
+                    }
+                    dx = -x; dy = -y; dz = -z;
+                    r2 = ok ? r2 : 1.0;
+                } else if (PBC) {
+                    const double x0 = __dsub_rn(ax[t], bx[u]), y0 = __dsub_rn(ay[t], by[u]), z0 = __dsub_rn(az[t], bz[u]);
+                    // In an all-pairs sweep most pairs need the wrap (any component beyond L/2), so its first round is
+                    // branch-free: |c| > L/2 is decided on the high words, c -+ L is the loop's own rounded subtraction.
+                    // High words equal to the half edge's, or a result still beyond it (coordinates that drifted by more
+                    // than a box), take the reference's loops (rare).
+                    const int wx = __double2hiint(x0), wy = __double2hiint(y0), wz = __double2hiint(z0);
+                    const int hx = wx & 0x7fffffff, hy = wy & 0x7fffffff, hz = wz & 0x7fffffff;
                     const int hm = max(hx, max(hy, hz));
-                    if (hm >= pp->hi_radius) {
-                        if (hm >= 0x5d000000) ok = false; // a padding body (parked at 1e150): weight 0, never in the cutoff
-                        else {
-                            x = wrap_cubic(x, pp->radius, pp->L); y = wrap_cubic(y, pp->radius, pp->L); z = wrap_cubic(z, pp->radius, pp->L);
-                        }
+                    ok = hm < 0x5d000000; // a padding body (parked at 1e150): weight 0, never in the cutoff
+                    const int Lh = __double2hiint(pp->L), Ll = __double2loint(pp->L);
+                    const double xw = __dsub_rn(x0, __hiloint2double(Lh | (wx & 0x80000000), Ll));
+                    const double yw = __dsub_rn(y0, __hiloint2double(Lh | (wy & 0x80000000), Ll));
+                    const double zw = __dsub_rn(z0, __hiloint2double(Lh | (wz & 0x80000000), Ll));
+                    double x = hx > pp->hi_radius ? xw : x0, y = hy > pp->hi_radius ? yw : y0, z = hz > pp->hi_radius ? zw : z0;
+                    const int nx = __double2hiint(x) & 0x7fffffff, ny = __double2hiint(y) & 0x7fffffff, nz = __double2hiint(z) & 0x7fffffff;
+                    if (ok && max(nx, max(ny, nz)) >= pp->hi_radius) {
+                        x = wrap_cubic(x0, pp->radius, pp->L); y = wrap_cubic(y0, pp->radius, pp->L); z = wrap_cubic(z0, pp->radius, pp->L);
                     }
                     r2 = r2_unfused(x, y, z);
                     ok = ok && (__double_as_longlong(r2) < __double_as_longlong(pp->R2));
@@ -148,6 +175,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     __shared__ __align__(8) uint64_t full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (PBC && p.gate && p.gate[0] != p.gate_want) return;
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -296,7 +324,7 @@ __global__ void sym_reduce_kernel(const SymParams p, int TS, int kind, double sc
 
 template <int T, int U, bool UNIFORM, int MINB, int UNR, int PBC = 0, bool EXCL3 = false>
 static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, double scale, double *acc_out,
-                   bool accumulate, double R2 = 0.0)
+                   bool accumulate, double R2 = 0.0, const int *gate = nullptr, int gate_want = 0, bool reduce = true)
 {
     constexpr int TS = 128 * T, SET = 32 * U;
     SymParams p{};
@@ -311,6 +339,7 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
         int64_t bits;
         memcpy(&bits, &p.radius, sizeof bits);
         p.hi_radius = (int)(bits >> 32);
+        p.gate = gate; p.gate_want = gate_want;
     }
     const bool half = (p.NT % 2 == 0) && p.K > 0;      // even ring: offset K is half an offset, shared by all ranks
     const int kfull = half ? p.K - 1 : p.K;            // largest whole offset
@@ -351,7 +380,7 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
     c->last_nchunk = p.S;
     double f = scale;
     if (UNIFORM) f *= wval;
-    sym_reduce_kernel<<<(p.n + 255) / 256, 256, 0, c->stream>>>(p, TS, scale_kind, f, c->mass, c->charge, acc_out,
+    if (reduce) sym_reduce_kernel<<<(p.n + 255) / 256, 256, 0, c->stream>>>(p, TS, scale_kind, f, c->mass, c->charge, acc_out,
                                                                acc_out + c->npad, acc_out + 2 * c->npad,
                                                                accumulate ? 1 : 0);
     NBX_CUDA(c, cudaGetLastError());
@@ -395,13 +424,33 @@ int launch_sympairs(nbx_ctx *c, const double *w, bool uniform, double wval, int 
     }
 }
 
+// flag[0] = 1 when some coordinate lies outside [-L/4, 5L/4) (then |ri - rj| can reach 3L/2 and one wrap round is not enough)
+__global__ void pbc_window_kernel(const double *__restrict__ pos, int64_t ld, int n, double lo, double hi, int *__restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pos[i], y = pos[ld + i], z = pos[2 * ld + i];
+    if (!(x >= lo && x < hi && y >= lo && y < hi && z >= lo && z < hi)) flag[0] = 1;
+}
+
 // Coulomb with a cutoff in a cubic periodic box as all UNORDERED pairs (the boxes a cell list cannot serve: R >= L/3):
 // half the evaluations of the ordered kernel with the exact periodic predicate.  excl3: own-molecule exclusion (water).
-// The caller has checked R < L/2 and that the context evaluates all targets.
+// The caller has checked R < L/2 and that the context evaluates all targets.  Two launches, one of which returns at
+// once: the branch-free variant while every coordinate is within a quarter box of the cell, else the general one.
 int launch_sympairs_coulomb_pbc(nbx_ctx *c, bool excl3, double *acc_out, bool accumulate)
 {
-    if (excl3) return run_sym<8, 2, false, 2, 2, 1, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2);
-    return run_sym<8, 2, false, 2, 2, 1, false>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2);
+    NBX_TRY(ensure_red(c));
+    int *flag = reinterpret_cast<int *>(c->d_red + c->red_cap - 4); // [0] drifted, [1] scratch (the tail of the reduction scratch)
+    const double L = c->bc[0];
+    NBX_CUDA(c, cudaMemsetAsync(flag, 0, 2 * sizeof(int), c->stream));
+    pbc_window_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, (int)c->n, -0.25 * L, 1.25 * L, flag);
+    NBX_CUDA(c, cudaGetLastError());
+    if (excl3) {
+        NBX_TRY((run_sym<8, 2, false, 2, 2, 2, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 0, false)));
+        return run_sym<8, 2, false, 2, 2, 1, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 1, true);
+    }
+    NBX_TRY((run_sym<8, 2, false, 2, 2, 2, false>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 0, false)));
+    return run_sym<8, 2, false, 2, 2, 1, false>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 1, true);
 }
 
 } // namespace nbx

@@ -238,3 +238,25 @@ def test_group_andersen_matches_single_context():
     ug, vg, _ = grp.download()
     assert _relmax(ug, u1) < 1e-11 and _relmax(vg, v1) < 1e-8
     one.close(); grp.close()
+
+
+@pytest.mark.parametrize("devices", [0, [0, 0]])
+def test_run_vv_streams_frames_through_the_abi(devices):
+    """nbx_run_vv (the saveat path of run_simulation): the frames equal what step + download give, on one context and on a
+    slab group."""
+    spec, u, v = _argon(8, 13, hot=2.0)
+    dt = 2e-3
+    a = make_context(spec, device=devices)
+    a.upload(u, v)
+    uf, vf = a.run_vv(dt, 25, save_every=10)
+    assert uf.shape == (3, 3, u.shape[1]) and vf.shape == uf.shape
+    b = make_context(spec)
+    b.upload(u, v)
+    for k, n in enumerate((10, 10, 5)):
+        b.step_vv(dt, n)
+        ub, vb, _ = b.download()
+        assert np.array_equal(uf[k], ub) and np.array_equal(vf[k], vb)
+    with pytest.raises(_lib.NbxError):
+        a.lib.nbx_run_vv  # noqa: B018  (symbol exists)
+        a._ck(a.lib.nbx_run_vv(a.h, dt, 30, 10, uf.ctypes.data_as(_lib._dp), None, 2, None))   # capacity: 3 frames needed
+    a.close(); b.close()
