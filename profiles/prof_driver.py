@@ -49,7 +49,7 @@ def main():
         if "PROF_VERLET" in os.environ:
             ctx.set_option("verlet_skin_permille", int(os.environ["PROF_VERLET"]))
     elif what == "water":
-        w = wl.water_omm(arg or 32, Rel=float(os.environ.get("PROF_REL", "0.9162")))
+        w = wl.water_omm(arg or 32, Rel=(float(os.environ.get("PROF_REL", "0.9162")) or None))
         u, v, dt = w["u"], w["v"], w["dt"]
         ctx.system(w["ms"], qs=w["qs"], water=True)
         ctx.boundary(_lib.BC_CUBIC, [w["L"]])
