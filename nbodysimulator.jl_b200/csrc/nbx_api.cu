@@ -1189,6 +1189,8 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(c, NBX_ERR_INVALID, "verlet_lanes: 0, 1, 2, 4 or 8");
         c->opt_verlet_lanes = (int)value;
     }
+    else if (!strcmp(key, "verlet_branchfree")) c->opt_verlet_branchfree = (int)value;
+    else if (!strcmp(key, "verlet_banked")) c->opt_verlet_banked = (int)value;
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
     else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;

@@ -289,6 +289,7 @@ struct CellPairArgs {
     double L, radius, R2, sigma2;
     float R2f;     // prefilter threshold on the fp32 squared distance in cell units (margin included)
     int hi_radius; // high word of `radius`: |x| with a smaller high word needs no wrapping
+    int hi_far2;   // high word of fl(radius^2): an unwrapped r2 with a smaller high word has no component to wrap
 };
 
 template <int POT, int EXCL, int MODE>
@@ -584,6 +585,8 @@ struct VerletArgs {
     int64_t stride;
     const int *dyn; // slab mode: [0] own, [1] ghosts on the device (launch sizes are bounds); else null
     int consume;    // the force kernel clears flags[0] (no refresh kernel ran: the position update refreshed the records)
+    int banked;     // the lists are laid out in blocks of four by record position inside a 128-byte line (see verlet_build_slot)
+    int branchfree; // force kernel: batches of four evaluated without branches (interleaved dependency chains)
 };
 
 // one lane per slot: the fp32 scan of cell_pairs2_kernel, survivors appended to the slot's list
@@ -597,6 +600,16 @@ __global__ void __launch_bounds__(128) verlet_build_kernel(const CellPairArgs a,
         verlet_build_slot(a, v, k);
 }
 
+// Banked layout (VerletArgs::banked).  A gathered record is one 32-byte sector; the L1 data stage serves a 256-bit warp
+// load four lanes at a time and needs one pass per DISTINCT sector of the same position inside a 128-byte line (measured,
+// profiles/micro/l1_gather.cu: 32 random records cost 20-21 cycles per warp gather, 9.5-12 when the four lanes of every
+// group read the four different positions).  The position of a record is its slot number mod 4, so the list of a slot is
+// written in blocks of four entries, entry p of a block being a record of position p, and the force kernel makes the four
+// lanes of a group read four different p of their blocks at any time.  A slot's partners are not spread evenly over the
+// four positions: entries of an over-full position that do not fit below the list's final block count go to places
+// left open by the other positions (in scan order -- nothing depends on anything but the slot numbers), the last
+// places still open hold the slot's own number as a sentinel (r2 = 0 exactly: the force kernel's predicate is
+// 0 < r2 < R2).  Two scans: the first counts the survivors per position.
 __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const VerletArgs &v, int k)
 {
     const float4 me = a.sl4[k];
@@ -605,35 +618,66 @@ __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const V
     const int nc = a.nc;
     const int cx = cid % nc, cy = (cid / nc) % nc, cz = cid / (nc * nc);
     const float fnc = (float)nc;
-    int cnt = 0;
-    bool over = false;
-    auto scan = [&](int b, int e, float tx, float ty, float tz) {
-        for (int m = b; m < e; ++m) {
-            const float4 cj = __ldg(&a.sl4[m]);
-            const float dx = tx - cj.x, dy = ty - cj.y, dz = tz - cj.z;
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (r2 < a.R2f && __float_as_int(cj.w) != key) {
-                if (cnt < v.cap) v.list[(size_t)cnt * v.stride + k] = m;
-                else over = true;
-                ++cnt;
+    auto sweep = [&](auto &&hit) {
+        auto scan = [&](int b, int e, float tx, float ty, float tz) {
+            for (int m = b; m < e; ++m) {
+                const float4 cj = __ldg(&a.sl4[m]);
+                const float dx = tx - cj.x, dy = ty - cj.y, dz = tz - cj.z;
+                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (r2 < a.R2f && __float_as_int(cj.w) != key) hit(m);
             }
+        };
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            const int dz = r / 3 - 1, dy = r - (r / 3) * 3 - 1;
+            int z = cz + dz, y = cy + dy;
+            float tz = me.z, ty = me.y;
+            if (z < 0) { z += nc; tz += fnc; } else if (z >= nc) { z -= nc; tz -= fnc; }
+            if (y < 0) { y += nc; ty += fnc; } else if (y >= nc) { y -= nc; ty -= fnc; }
+            const int row = (z * nc + y) * nc;
+            const int xa = cx > 0 ? cx - 1 : 0, xb = cx < nc - 1 ? cx + 1 : nc - 1;
+            scan(a.start[row + xa], a.start[row + xb + 1], me.x, ty, tz);
+            if (cx == 0) scan(a.start[row + nc - 1], a.start[row + nc], me.x + fnc, ty, tz);
+            else if (cx == nc - 1) scan(a.start[row], a.start[row + 1], me.x - fnc, ty, tz);
         }
     };
-#pragma unroll 1
-    for (int r = 0; r < 9; ++r) {
-        const int dz = r / 3 - 1, dy = r - (r / 3) * 3 - 1;
-        int z = cz + dz, y = cy + dy;
-        float tz = me.z, ty = me.y;
-        if (z < 0) { z += nc; tz += fnc; } else if (z >= nc) { z -= nc; tz -= fnc; }
-        if (y < 0) { y += nc; ty += fnc; } else if (y >= nc) { y -= nc; ty -= fnc; }
-        const int row = (z * nc + y) * nc;
-        const int xa = cx > 0 ? cx - 1 : 0, xb = cx < nc - 1 ? cx + 1 : nc - 1;
-        scan(a.start[row + xa], a.start[row + xb + 1], me.x, ty, tz);
-        if (cx == 0) scan(a.start[row + nc - 1], a.start[row + nc], me.x + fnc, ty, tz);
-        else if (cx == nc - 1) scan(a.start[row], a.start[row + 1], me.x - fnc, ty, tz);
+    if (!v.banked) {
+        int cnt = 0;
+        sweep([&](int m) {
+            if (cnt < v.cap) v.list[(size_t)cnt * v.stride + k] = m;
+            ++cnt;
+        });
+        v.nlist[k] = cnt < v.cap ? cnt : v.cap;
+        if (cnt > v.cap) v.flags[1] = 1;
+        return;
     }
-    v.nlist[k] = cnt < v.cap ? cnt : v.cap;
-    if (over) v.flags[1] = 1;
+    // the four per-position counters live in one register pair (16 bits each: the capacity is checked by the caller)
+    unsigned long long have = 0ull;
+    int cnt = 0;
+    sweep([&](int m) { have += 1ull << ((m & 3) * 16); ++cnt; });
+    if (cnt > v.cap) { // (cap is a multiple of four)
+        v.nlist[k] = 0;
+        v.flags[1] = 1;
+        return;
+    }
+    const int blocks = (cnt + 3) >> 2;
+    auto count_of = [&](int p) { return (int)((have >> (p * 16)) & 0xffffull); };
+    // open places, position by position: blocks [count_of(q), blocks) of position q
+    int hq = 0, hh = count_of(0);
+    auto settle = [&]() { while (hq < 4 && hh >= blocks) { ++hq; hh = hq < 4 ? count_of(hq) : 0; } };
+    settle();
+    unsigned long long used = 0ull;
+    sweep([&](int m) {
+        const int p = m & 3;
+        const int t = (int)((used >> (p * 16)) & 0xffffull);
+        used += 1ull << (p * 16);
+        int blk, pos;
+        if (t < blocks) { blk = t; pos = p; }
+        else { blk = hh; pos = hq; ++hh; settle(); }
+        v.list[(size_t)(4 * blk + ((pos - k) & 3)) * v.stride + k] = m;
+    });
+    while (hq < 4) { v.list[(size_t)(4 * hh + ((hq - k) & 3)) * v.stride + k] = k; ++hh; settle(); } // sentinel: the slot itself
+    v.nlist[k] = 4 * blocks;
 }
 
 // after a rebuild: remember the positions the list was built from
@@ -664,15 +708,14 @@ __global__ void verlet_refresh_kernel(const double *__restrict__ px, int64_t ld,
 // P lanes share one target (P = 1, 2, 4, 8): lane s of the group takes the entries s, s + P, ... and the partial sums
 // meet in a butterfly (fixed order).  Small systems with long lists (32,768 water oxygens x 136 entries, 98,304
 // charges x 424) otherwise leave most of the machine idle and walk every list serially.
+// the targets of one tile of 128 threads (tile * 128 / P ...)
 template <int POT, int P>
-__global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a, const VerletArgs v, double scale,
-                                                           const double *__restrict__ mass, int mstride,
-                                                           const double *__restrict__ charge, int lo, int hi,
-                                                           double *__restrict__ acc, int64_t ld, int accumulate)
+__device__ __forceinline__ void verlet_force_tile(const CellPairArgs &a, const VerletArgs &v, double scale,
+                                                  const double *__restrict__ mass, int mstride,
+                                                  const double *__restrict__ charge, int lo, int hi,
+                                                  double *__restrict__ acc, int64_t ld, int accumulate, int tile)
 {
-    if (v.consume && blockIdx.x == 0 && threadIdx.x == 0) v.flags[0] = 0; // the rebuild request was consumed by the chain before
-    if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
-    const int t = blockIdx.x * 128 + threadIdx.x;
+    const int t = tile * 128 + threadIdx.x;
     const int k = t / P, sub = t % P;
     const int n_loc = dyn_loc(v.dyn, a.n);
     if (v.dyn) hi = min(hi, v.dyn[0]); // slab mode: the own particles are the targets, the ghosts only sources
@@ -684,54 +727,92 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
     const double4 pi = a.sp4[kk];
     const int cnt = live ? v.nlist[kk] : 0;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    auto pair = [&](const double4 pj) {
-        double rx = __dsub_rn(pi.x, pj.x), ry = __dsub_rn(pi.y, pj.y), rz = __dsub_rn(pi.z, pj.z);
-        const int hx = __double2hiint(rx) & 0x7fffffff, hy = __double2hiint(ry) & 0x7fffffff,
-                  hz = __double2hiint(rz) & 0x7fffffff;
-        if (max(hx, max(hy, hz)) >= a.hi_radius) {
+    // The wrap loops of the reference change a component only when |component| >= L/2, and then the UNWRAPPED r2 is at
+    // least fl((L/2)^2) > R2 (rounding is monotone).  So: r2 of the raw differences first; inside the cutoff means no
+    // component needed wrapping and r2 is the reference's; outside, only an r2 whose high word reaches that of
+    // fl((L/2)^2) can belong to a pair that straddles a periodic face (rare) and is wrapped and tested again.
+    // Inside = 0 < r2 < R2 on the bit patterns (one unsigned compare of r2 - 1 ulp; r2 = 0 is the sentinel entry of a
+    // banked list, the slot itself).
+    const unsigned long long R2m1 = (unsigned long long)__double_as_longlong(a.R2) - 1ull;
+    auto inside = [&](double r2) { return (unsigned long long)__double_as_longlong(r2) - 1ull < R2m1; };
+    auto rewrap = [&](double &rx, double &ry, double &rz, double &r2) { // rare
+        if (__double2hiint(r2) >= a.hi_far2) {
             rx = wrap_cubic(rx, a.radius, a.L);
             ry = wrap_cubic(ry, a.radius, a.L);
             rz = wrap_cubic(rz, a.radius, a.L);
+            r2 = r2_unfused(rx, ry, rz);
         }
-        const double r2 = r2_unfused(rx, ry, rz);
-        if (__double_as_longlong(r2) < __double_as_longlong(a.R2)) {
-            double f;
-            if (POT == 0) {
-                const double inv = rcp_fast(r2);
-                const double qq = a.sigma2 * inv;
-                const double s6 = qq * qq * qq;
-                f = (s6 * inv) * fma(2.0, s6, -1.0);
-            } else {
-                f = w_rinv3(r2, pj.w);
-            }
-            f0 = fma(f, rx, f0);
-            f1 = fma(f, ry, f1);
-            f2 = fma(f, rz, f2);
+    };
+    auto strength = [&](double r2, double w) {
+        if (POT == 0) { // (2 s12 - s6) / r2 = 2 (s6 / r2) (s6 - 1/2): the exact factor 2 is applied with the scale
+            const double inv = rcp_fast(r2);
+            const double qq = a.sigma2 * inv;
+            const double s6 = qq * qq * qq;
+            return (s6 * inv) * (s6 - 0.5);
         }
+        return w_rinv3(r2, w);
+    };
+    auto pair = [&](const double4 pj) {
+        double rx = __dsub_rn(pi.x, pj.x), ry = __dsub_rn(pi.y, pj.y), rz = __dsub_rn(pi.z, pj.z);
+        double r2 = r2_unfused(rx, ry, rz);
+        if (!inside(r2)) {
+            if (__double2hiint(r2) < a.hi_far2) return;
+            rewrap(rx, ry, rz, r2);
+            if (!inside(r2)) return;
+        }
+        const double f = strength(r2, pj.w);
+        f0 = fma(f, rx, f0);
+        f1 = fma(f, ry, f1);
+        f2 = fma(f, rz, f2);
+    };
+    // a batch of four without branches: the four dependency chains (r2 -> reciprocal -> strength) interleave, which is
+    // what the kernel lacks with 7 warps per scheduler; entries outside the cutoff (a quarter of the list) add an exact 0.
+    // Same operations in the same order as four calls of pair(): bit-identical sums.
+    auto pair4 = [&](const double4 q0, const double4 q1, const double4 q2, const double4 q3) {
+        double x0 = __dsub_rn(pi.x, q0.x), y0 = __dsub_rn(pi.y, q0.y), z0 = __dsub_rn(pi.z, q0.z);
+        double x1 = __dsub_rn(pi.x, q1.x), y1 = __dsub_rn(pi.y, q1.y), z1 = __dsub_rn(pi.z, q1.z);
+        double x2 = __dsub_rn(pi.x, q2.x), y2 = __dsub_rn(pi.y, q2.y), z2 = __dsub_rn(pi.z, q2.z);
+        double x3 = __dsub_rn(pi.x, q3.x), y3 = __dsub_rn(pi.y, q3.y), z3 = __dsub_rn(pi.z, q3.z);
+        double s0 = r2_unfused(x0, y0, z0), s1 = r2_unfused(x1, y1, z1), s2 = r2_unfused(x2, y2, z2), s3 = r2_unfused(x3, y3, z3);
+        if (max(max(__double2hiint(s0), __double2hiint(s1)), max(__double2hiint(s2), __double2hiint(s3))) >= a.hi_far2) {
+            rewrap(x0, y0, z0, s0); rewrap(x1, y1, z1, s1); rewrap(x2, y2, z2, s2); rewrap(x3, y3, z3, s3);
+        }
+        double g0 = strength(s0, q0.w), g1 = strength(s1, q1.w), g2 = strength(s2, q2.w), g3 = strength(s3, q3.w);
+        g0 = inside(s0) ? g0 : 0.0; g1 = inside(s1) ? g1 : 0.0; g2 = inside(s2) ? g2 : 0.0; g3 = inside(s3) ? g3 : 0.0;
+        f0 = fma(g0, x0, f0); f1 = fma(g0, y0, f1); f2 = fma(g0, z0, f2);
+        f0 = fma(g1, x1, f0); f1 = fma(g1, y1, f1); f2 = fma(g1, z1, f2);
+        f0 = fma(g2, x2, f0); f1 = fma(g2, y2, f1); f2 = fma(g2, z2, f2);
+        f0 = fma(g3, x3, f0); f1 = fma(g3, y3, f1); f2 = fma(g3, z3, f2);
     };
     const int *lp = v.list + kk;
     int e = sub;
+    // banked lists (verlet_build_slot): the four lanes of a group must read four different record positions at any time.
+    // Row r of a block of slot k holds position (r + k) mod 4.  P = 1 (four targets per group, rows walked in step) and
+    // P >= 4 (one target per group, lane sub reads row sub) satisfy that as they are; P = 2 (two targets per group: rows
+    // {0, 1} then {2, 3}) needs the odd slot one row ahead.
+    const int ahead = (v.banked && P == 2) ? (kk & 1) : 0;
+    auto at = [&](int q) -> size_t { return (size_t)(P == 2 ? ((q & ~3) | ((q + ahead) & 3)) : q) * v.stride; };
     // four gathers in flight per lane; the list entries of the NEXT batch are fetched before the current one is evaluated,
-    // so that a batch costs one memory round trip (the gathers), not two in a row (entries, then gathers).  (Measured and
-    // dropped, r02: also issuing the next batch's GATHERS ahead + a branch-free force, 86 registers -- 0.309 vs 0.263 ms per
-    // step at 1,048,576 atoms, 0.059 vs 0.055 at 131,072: the occupancy it costs outweighs the latency it hides.)
+    // so that a batch costs one memory round trip (the gathers), not two in a row (entries, then gathers).  Measured and
+    // dropped in r02 (1,048,576 atoms, ms per step against 0.244 for this loop): the next batch's gathers issued ahead
+    // into a second set of landing registers (86 registers) 0.309; eight gathers per batch (96 registers, 5 blocks per
+    // SM) 0.283; the next batch's records prefetched into L1 (CCTL.PF1, no registers) 0.293; list rows prefetched into
+    // L2 two to eight batches ahead: no change; 10 or 12 blocks per SM (48 / 40 registers, spills) 0.333 / 0.339;
+    // persistent CTAs that keep an SM on one contiguous range of tiles (record misses of L1 -58 %) 0.283 -- per-SM
+    // time did not move, the static ranges only added imbalance.
     bool have = e + 3 * P < cnt;
     int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-    if (have) {
-        m0 = lp[(size_t)e * v.stride]; m1 = lp[(size_t)(e + P) * v.stride]; m2 = lp[(size_t)(e + 2 * P) * v.stride];
-        m3 = lp[(size_t)(e + 3 * P) * v.stride];
-    }
+    auto entry = [&](int q) { return ld_stream(lp + at(q)); };
+    if (have) { m0 = entry(e); m1 = entry(e + P); m2 = entry(e + 2 * P); m3 = entry(e + 3 * P); }
     while (have) {
         const double4 p0 = load_rec(a.sp4 + m0), p1 = load_rec(a.sp4 + m1), p2 = load_rec(a.sp4 + m2), p3 = load_rec(a.sp4 + m3);
         e += 4 * P;
         have = e + 3 * P < cnt;
-        if (have) {
-            m0 = lp[(size_t)e * v.stride]; m1 = lp[(size_t)(e + P) * v.stride]; m2 = lp[(size_t)(e + 2 * P) * v.stride];
-            m3 = lp[(size_t)(e + 3 * P) * v.stride];
-        }
-        pair(p0); pair(p1); pair(p2); pair(p3);
+        if (have) { m0 = entry(e); m1 = entry(e + P); m2 = entry(e + 2 * P); m3 = entry(e + 3 * P); }
+        if (v.branchfree) pair4(p0, p1, p2, p3);
+        else { pair(p0); pair(p1); pair(p2); pair(p3); }
     }
-    for (; e < cnt; e += P) pair(load_rec(a.sp4 + lp[(size_t)e * v.stride]));
+    for (; e < cnt; e += P) pair(load_rec(a.sp4 + entry(e)));
     if (P > 1) {
 #pragma unroll
         for (int o = 1; o < P; o <<= 1) {
@@ -741,13 +822,24 @@ __global__ void __launch_bounds__(128) verlet_force_kernel(const CellPairArgs a,
         }
         if (!live || sub != 0) return;
     }
-    double coeff = scale / mass[(size_t)i * mstride];
+    double coeff = (POT == 0 ? 2.0 * scale : scale) / mass[(size_t)i * mstride];
     if (POT == 1) coeff *= charge[i];
     if (accumulate) {
         acc[i] += coeff * f0; acc[ld + i] += coeff * f1; acc[2 * ld + i] += coeff * f2;
     } else {
         acc[i] = coeff * f0; acc[ld + i] = coeff * f1; acc[2 * ld + i] = coeff * f2;
     }
+}
+
+template <int POT, int P>
+__global__ void __launch_bounds__(128, 8) verlet_force_kernel(const CellPairArgs a, const VerletArgs v, double scale,
+                                                              const double *__restrict__ mass, int mstride,
+                                                              const double *__restrict__ charge, int lo, int hi,
+                                                              double *__restrict__ acc, int64_t ld, int accumulate)
+{
+    if (v.consume && blockIdx.x == 0 && threadIdx.x == 0) v.flags[0] = 0; // the rebuild request was consumed by the chain before
+    if (v.flags[1]) return; // overflow: the scan-per-step kernel takes over
+    verlet_force_tile<POT, P>(a, v, scale, mass, mstride, charge, lo, hi, acc, ld, accumulate, blockIdx.x);
 }
 
 template <int POT>
@@ -908,6 +1000,9 @@ static CellPairArgs make_args(const nbx_ctx *c, const CellList *cl, double R2)
     int64_t bits;
     memcpy(&bits, &a.radius, sizeof bits);
     a.hi_radius = (int)(bits >> 32);
+    const double far2 = a.radius * a.radius;
+    memcpy(&bits, &far2, sizeof bits);
+    a.hi_far2 = (int)(bits >> 32);
     return a;
 }
 
@@ -985,8 +1080,12 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     const double expect = (double)nplan / (L * L * L) * 4.18879020478639 * (R + skin) * (R + skin) * (R + skin);
     int cap = (int)(1.5 * expect) + 24;
     if (cap > ni - 1) cap = ni > 1 ? ni - 1 : 1;
+    cap = (cap + 3) & ~3; // whole blocks of four (banked layout)
+    // (the position of a record is its LOCAL slot number mod 4: a slab would order its lists differently from the single
+    // context and lose the bit-for-bit equality of the two, for a few per cent of a kernel that is a third of its step)
+    const int banked = (c->opt_verlet_banked && !c->slab.on && cap < 4 * 65535) ? 1 : 0; // (16-bit counters in the build)
     const bool same = cl->v_valid && cl->v_n == n && (slabv || cl->v_px == px) && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
-                      cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap;
+                      cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap && cl->v_banked == banked;
     if (!same) {
         if (cl->v_cap_alloc < (int64_t)cap * cl->cap_n) {
             NBX_TRY(dev_alloc(c, &cl->v_list, (size_t)cap * (size_t)cl->cap_n));
@@ -1002,7 +1101,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         NBX_CUDA(c, cudaMemsetAsync(cl->v_flags, 1, sizeof(int), c->stream)); // [0] != 0: build now
         NBX_CUDA(c, cudaMemsetAsync(cl->v_ref, 0, sizeof(double) * 3 * (size_t)cl->cap_n, c->stream));
         cl->v_valid = true; cl->v_n = n; cl->v_px = px; cl->v_R = R; cl->v_skin = skin; cl->v_L = L;
-        cl->v_key_div = key_div; cl->v_nc = cl->grid.nc[0]; cl->v_cap = cap;
+        cl->v_key_div = key_div; cl->v_nc = cl->grid.nc[0]; cl->v_cap = cap; cl->v_banked = banked;
         if (slabv) c->slab.rebuild_now = true;
     }
     const int blocks256 = (ni + 255) / 256;
@@ -1012,6 +1111,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
         CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin));
         VerletArgs v{};
         v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = c->dyn;
+        v.banked = banked; v.branchfree = c->opt_verlet_branchfree;
         // phase 1 / 2 (slab_enqueue): the rebuild chain and the evaluation are enqueued separately, and whether the chain
         // RUNS is decided on the device (slab.cond == v_flags: every kernel of it returns at once unless flags[0] is set)
         if (c->slab.phase != 2 && c->slab.rebuild_now) {
@@ -1057,6 +1157,7 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     CellPairArgs a = make_args(c, cl, (R + skin) * (R + skin)); // scan threshold of the list build
     VerletArgs v{};
     v.list = cl->v_list; v.nlist = cl->v_nlist; v.flags = cl->v_flags; v.cap = cap; v.stride = cl->cap_n; v.dyn = nullptr;
+    v.banked = banked; v.branchfree = c->opt_verlet_branchfree;
     v.consume = pre ? 1 : 0;
     timer_begin(c, NBX_T_CELL_BUILD);
     verlet_build_kernel<<<map_grid(c, ni, 128), 128, 0, c->stream>>>(a, v);

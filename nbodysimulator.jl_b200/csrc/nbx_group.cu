@@ -38,6 +38,9 @@ int leader_create(nbx_ctx **out, int ndev, const int *devs)
             return rc;
         }
         m->leader = lead;
+        // a slab never orders its lists by record position (local slot numbers); the members evaluate a(0) before they
+        // become slabs, and that evaluation must add in the same order as the steps that follow
+        m->opt_verlet_banked = 0;
         lead->members.push_back(m);
     }
     // peer access between every pair of distinct devices (the kernels store into each other's memory)

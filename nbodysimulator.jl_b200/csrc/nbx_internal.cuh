@@ -58,7 +58,7 @@ struct CellList {
     int64_t v_n = 0;
     const double *v_px = nullptr;
     double v_R = 0, v_skin = 0, v_L = 0;
-    int v_key_div = 0, v_nc = 0, v_cap = 0;
+    int v_key_div = 0, v_nc = 0, v_cap = 0, v_banked = 0;
 };
 
 // slab decomposition state (nbx_slab.cu)
@@ -222,6 +222,8 @@ struct nbx_ctx {
     bool cond_capture = false, cond_fail = false;
     cudaStream_t aux_stream = nullptr;
     int opt_fuse_update = 1;       // nbx_step_vv: position update + displacement check + record refresh in one kernel
+    int opt_verlet_banked = 1;     // Verlet lists in blocks of four by record position in a 128-byte line (conflict-free L1 gathers)
+    int opt_verlet_branchfree = 1; // Verlet force kernel: batches of four list entries evaluated without branches
     int opt_verlet_lanes = 0;      // lanes per target of the Verlet force kernel (0: chosen from the system size; 1, 2, 4, 8)
     int opt_sym = 1;            // Newton's-third-law all-pairs kernel for unsharded 1/r^2 systems
     int64_t sym_min_n = 8192;
@@ -526,6 +528,15 @@ __device__ __forceinline__ double4 load_rec(const double4 *p)
 {
     double4 r;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+// a word of a stream that is read once (Verlet list entries): no L1 allocation, so that it does not displace the gathered
+// records
+__device__ __forceinline__ int ld_stream(const int *p)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 

@@ -59,6 +59,9 @@ def main():
         ctx.add_spcfw(s["rOH"], s["aHOH"], s["kb"], s["ka"])
     else:
         raise SystemExit(__doc__)
+    for kv in filter(None, os.environ.get("PROF_OPTS", "").split(",")):  # e.g. PROF_OPTS=verlet_banked=0,verlet_lanes=4
+        k, val = kv.split("=")
+        ctx.set_option(k, int(val))
     ctx.upload(u, v)
     ctx.step_vv(dt, steps)
     ctx.synchronize()

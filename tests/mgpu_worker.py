@@ -37,6 +37,7 @@ def slab_main(cells):
             ctx.boundary(_lib.BC_CUBIC, [w["L"]])
             ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
             ctx.set_option("verlet_skin_permille", skin)
+            ctx.set_option("verlet_banked", 0)
             if thermo:
                 ctx.thermostat(_lib.THERMO_BERENDSEN, 90.0, 20 * dt, w["kB"], n, 0)
             return ctx
@@ -123,12 +124,14 @@ def group_main():
     ok = True
     for name, spec, u, v, dt, steps, em, tol in _group_cases():
         one = make_context(spec, device=local)
+        one.set_option("verlet_banked", 0)   # the list order of the slabs (see tests/test_gpu_group.py::_single_run)
         one.upload(u, v)
         (one.step_em(dt, steps, 9) if em else one.step_vv(dt, steps))
         ur, vr, ar = one.download(want_dv=True)
         a_rhs = one.accel(u).copy() if "thermostat" not in spec else None
         one.close()
         ctx = make_context(spec, device=local)
+        ctx.set_option("verlet_banked", 0)   # (a(0) is evaluated before the context becomes a slab)
         ctx.upload(u, v)
         join_group_dist(ctx)
         mode = ctx.info("group_mode")
@@ -176,6 +179,7 @@ def multi_main():
     ok = True
     for name, spec, u, v, dt, steps, em, tol in _group_cases():
         one = make_context(spec, device=0)
+        one.set_option("verlet_banked", 0)
         one.upload(u, v)
         (one.step_em(dt, steps, 9) if em else one.step_vv(dt, steps))
         ur, vr, ar = one.download(want_dv=True)

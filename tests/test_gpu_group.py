@@ -49,6 +49,9 @@ def _relmax(a, b):
 
 def _single_run(spec, u, v, dt, nsteps, em=False, seed=0):
     ctx = make_context(spec)
+    # slabs keep the plain list order (the position-ordered layout depends on the LOCAL slot numbers): the single context
+    # is compared with them in that order, bit for bit
+    ctx.set_option("verlet_banked", 0)
     ctx.upload(u, v)
     (ctx.step_em(dt, nsteps, seed) if em else ctx.step_vv(dt, nsteps))
     out = ctx.download(want_dv=True)
@@ -116,6 +119,7 @@ def test_group_members_joined_by_hand_and_driven_from_threads():
     for _ in range(world):
         c = make_context(spec)
         c.set_option("spin_timeout_ms", 3000)
+        c.set_option("verlet_banked", 0)   # a(0) is evaluated before the context becomes a slab: same list order from the start
         c.upload(u, v)
         ctxs.append(c)
     join_group_local(ctxs)
@@ -251,6 +255,8 @@ def test_run_vv_streams_frames_through_the_abi(devices):
     uf, vf = a.run_vv(dt, 25, save_every=10)
     assert uf.shape == (3, 3, u.shape[1]) and vf.shape == uf.shape
     b = make_context(spec)
+    if devices != 0:
+        b.set_option("verlet_banked", 0)   # the list order of the slabs
     b.upload(u, v)
     for k, n in enumerate((10, 10, 5)):
         b.step_vv(dt, n)

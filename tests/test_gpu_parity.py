@@ -426,6 +426,41 @@ def test_verlet_force_lanes_per_target(oracle, lanes):
     ctx.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8])
+@pytest.mark.parametrize("n_side", [7, 8])
+def test_verlet_banked_lists_keep_the_pair_set(oracle, lanes, n_side):
+    """Lists laid out in blocks of four by record position (conflict-free L1 gathers, padded with the slot itself as a
+    sentinel) and the branch-free batch evaluation: the same partners in another order.  Against the plain layout with
+    the branching evaluation: 1e-13; against the oracle: the contract; after a hot run with rebuilds too.  n_side = 7:
+    1,372 atoms, list lengths and the slot count are no multiples of four."""
+    w, u = _fcc(n_side, 0.05, 37, drift=True)
+    spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+    ref = make_oracle(oracle, spec).rhs(u, w["v"], NT)
+    out = {}
+    for banked, bf in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        ctx = make_context(spec)
+        ctx.set_option("verlet_lanes", lanes)
+        ctx.set_option("verlet_banked", banked)
+        ctx.set_option("verlet_branchfree", bf)
+        a = ctx.accel(u).copy()
+        assert ctx.info("verlet_lj") > 0 and ctx.info("verlet_overflow") == 0
+        _check(a, ref)
+        assert np.array_equal(a, ctx.accel(u))  # deterministic
+        out[(banked, bf)] = a
+        if banked and bf:
+            v = F(3.0 * w["v"])
+            ctx.upload(u, v)
+            ctx.step_vv(2e-3, 60)
+            ug, vg, ag = ctx.download(want_dv=True)
+            assert ctx.info("verlet_rebuilds") >= 3 and ctx.info("verlet_overflow") == 0
+            _check(ag, make_oracle(oracle, spec).rhs(ug, vg.copy(order="F"), NT))
+        ctx.close()
+    assert np.array_equal(out[(0, 0)], out[(0, 1)])  # same operations in the same order
+    assert np.array_equal(out[(1, 0)], out[(1, 1)])
+    scale = np.linalg.norm(out[(0, 0)], axis=0).max()
+    assert np.abs(out[(1, 1)] - out[(0, 0)]).max() <= 1e-13 * scale
+
+
 @pytest.mark.parametrize("thermo", [None, "berendsen"])
 def test_fused_position_update_is_bit_identical(oracle, thermo):
     """nbx_step_vv with one cutoff potential: the position update also checks the displacements and refreshes the
