@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -87,12 +87,14 @@ class ClockSampler:
 
         def pump():
             for line in self.proc.stdout:
-                self.rows.append(line.strip())
+                self.rows.append((time.perf_counter(), line.strip()))
 
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (the timed region); when it is shorter than the sampling
+        period and holds none, of all samples since start() (warm-up + timed steps: the same load), and says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -102,7 +104,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.06)]
+        window = "timed steps"
+        if not rows:
+            rows = [r for _, r in self.rows]
+            window = "warm-up + timed steps (the timed region is shorter than the sampling period)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -116,7 +123,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -537,15 +544,16 @@ def run_b200(args):
         return float(t.item())
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()           # (nvidia-smi needs a few hundred ms to deliver its first sample: started before the warm-up)
     ctx.step_vv(DT_GRAVITY, max(args.warmup, 3))
     barrier()
     ctx.timing_reset()
     ctx.timing_enable(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_begin = time.perf_counter()
     ms_total = timed_steps(ctx, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     ctx.timing_enable(False)
     pairs_per_step = float(n) * float(n - 1)
     value = pairs_per_step * args.steps / (ms_total * 1e-3)

@@ -66,11 +66,14 @@ __device__ __forceinline__ void ring_pass(const double (&ax)[T], const double (&
                     // so ONE round of the reference's wrap loop settles every component; a component exactly on the tie
                     // (-L/2 stays, +L/2 wraps) follows the loop's own conditions.  No branch, no integer work.
                     double x = __dsub_rn(ax[t], bx[u]), y = __dsub_rn(ay[t], by[u]), z = __dsub_rn(az[t], bz[u]);
-                    if (x >= pp->radius) x = __dsub_rn(x, pp->L); else if (x < -pp->radius) x = __dadd_rn(x, pp->L);
-                    if (y >= pp->radius) y = __dsub_rn(y, pp->L); else if (y < -pp->radius) y = __dadd_rn(y, pp->L);
-                    if (z >= pp->radius) z = __dsub_rn(z, pp->L); else if (z < -pp->radius) z = __dadd_rn(z, pp->L);
+                    // (one compare of |c| per component: a component exactly on the tie -L/2, which the loop leaves alone,
+                    // may be folded to +L/2 here -- either way r2 >= L^2/4 > R2 and the pair is outside)
+                    const int Lh = __double2hiint(pp->L), Ll = __double2loint(pp->L);
+                    if (fabs(x) >= pp->radius) x = __dsub_rn(x, __hiloint2double(Lh | (__double2hiint(x) & 0x80000000), Ll));
+                    if (fabs(y) >= pp->radius) y = __dsub_rn(y, __hiloint2double(Lh | (__double2hiint(y) & 0x80000000), Ll));
+                    if (fabs(z) >= pp->radius) z = __dsub_rn(z, __hiloint2double(Lh | (__double2hiint(z) & 0x80000000), Ll));
                     r2 = r2_unfused(x, y, z);
-                    ok = r2 < pp->R2;
+                    ok = __double_as_longlong(r2) < __double_as_longlong(pp->R2); // (r2 >= 0: IEEE order == order of the bit patterns)
                     if (EXCL3) {
                         const int j = jbase + u * 32 + ((lane + s) & 31);
                         const int i = ibase + t * 32 + lane;
@@ -446,6 +449,8 @@ int launch_sympairs_coulomb_pbc(nbx_ctx *c, bool excl3, double *acc_out, bool ac
     pbc_window_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->pos, c->npad, (int)c->n, -0.25 * L, 1.25 * L, flag);
     NBX_CUDA(c, cudaGetLastError());
     if (excl3) {
+        // (other shapes of the branch-free variant, r02, ms per water step at 98,304 atoms against 10.2 for this one:
+        // <4,4,3,2> 11.2, <8,2,2,4> 13.1, <8,1,3,4> 13.7, <8,2,2,1> 10.3, <8,1,2,2> 10.4, <4,2,4,2> 11.7, <4,2,3,4> 10.2)
         NBX_TRY((run_sym<8, 2, false, 2, 2, 2, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 0, false)));
         return run_sym<8, 2, false, 2, 2, 1, true>(c, c->charge, 1.0, 1, -c->el_k, acc_out, accumulate, c->el_R2, flag, 1, true);
     }
