@@ -379,8 +379,9 @@ def other_configs(local, world, steps=5):
     modes = {0: "1 GPU", 1: "pair sharding", 2: "target blocks", 3: "x-slabs"}
     try:
         for tag, rel, what in (("config4_water_cutoff_0.9162nm", 0.9162, "cell lists for O-O Lennard-Jones and Coulomb"),
-                               ("config4_water_cutoff_0.49L", None, "Coulomb cutoff 4.886 nm = half the box: all-pairs kernel "
-                                                                    "with the exact periodic predicate")):
+                               ("config4_water_cutoff_0.49L", None, "Coulomb cutoff 4.886 nm = 0.49 L (no cell list possible): every unordered pair "
+                                                                    "once, the reference's periodic predicate (1 GPU: Newton's-"
+                                                                    "third-law kernel; groups: ordered target blocks)")):
             w = wl.water_omm(32, Rel=rel)
             ctx = _lib.Context(local)
             ctx.system(w["ms"], qs=w["qs"], water=True)

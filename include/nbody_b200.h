@@ -300,6 +300,12 @@ NBX_API int nbx_timing_reset(nbx_ctx *ctx);
  *                       "prefilter" (1: fp32 candidate scan before the exact fp64 predicate),
  *                       "verlet_skin_permille" (100: Verlet lists with skin = 0.1 R; 0: rescan the cells every evaluation),
  *                       "verlet_lanes" (0: lanes per target chosen from the system size; 1, 2, 4, 8),
+ *                       "verlet_banked" (1: a target's list is stored in blocks of four ordered by the partner record's position
+ *                       inside its 128-byte line, so that the gathers of four neighbouring lanes never collide in the L1 data
+ *                       banks; the order depends on the LOCAL slot numbers, so slabs and the members of nbx_create_multi
+ *                       always use 0, and a context that is compared bit for bit with them -- or joins a group by hand after
+ *                       its upload -- sets 0 as well), "verlet_branchfree" (1: batches of four list entries evaluated without
+ *                       branches; same operations, same sums),
  *   groups            : "group_mode" (leader of nbx_create_multi; 0), "pin_host" (0; 1: page-lock the caller's u / v / dv buffers
  *                       the first time nbx_accel sees them -- the caller must keep them alive until nbx_destroy / nbx_system),
  *   nbx_step_vv       : "graph" (1: two-step CUDA graph), "graph_if_nodes" (1: rebuild chain as the body of an IF node),

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(128) verlet_build_kernel(const CellPairArgs a,
 // four positions: entries of an over-full position that do not fit below the list's final block count go to places
 // left open by the other positions (in scan order -- nothing depends on anything but the slot numbers), the last
 // places still open hold the slot's own number as a sentinel (r2 = 0 exactly: the force kernel's predicate is
-// 0 < r2 < R2).  Two scans: the first counts the survivors per position.
+// 0 < r2 < R2).
 __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const VerletArgs &v, int k)
 {
     const float4 me = a.sl4[k];
@@ -651,31 +651,38 @@ __device__ __forceinline__ void verlet_build_slot(const CellPairArgs &a, const V
         if (cnt > v.cap) v.flags[1] = 1;
         return;
     }
-    // the four per-position counters live in one register pair (16 bits each: the capacity is checked by the caller)
+    // one scan: survivor number t of position p goes to row p of block t at once (the rows reach up to twice the
+    // capacity: a position may hold more than a quarter of a list); the four counters live in one register pair
     unsigned long long have = 0ull;
     int cnt = 0;
-    sweep([&](int m) { have += 1ull << ((m & 3) * 16); ++cnt; });
-    if (cnt > v.cap) { // (cap is a multiple of four)
+    bool over = false;
+    const int bmax = v.cap >> 1; // blocks that exist (2 x cap rows)
+    sweep([&](int m) {
+        const int p = m & 3;
+        const int t = (int)((have >> (p * 16)) & 0xffffull);
+        if (t < bmax) v.list[(size_t)(4 * t + ((p - k) & 3)) * v.stride + k] = m;
+        else over = true;
+        have += 1ull << (p * 16);
+        ++cnt;
+    });
+    if (cnt > v.cap || over) { // (cap is a multiple of four)
         v.nlist[k] = 0;
         v.flags[1] = 1;
         return;
     }
+    // the list ends after `blocks` blocks: entries beyond (of over-full positions) move to the places the other
+    // positions left open below, blocks [count_of(q), blocks) of position q; what stays open holds the sentinel
     const int blocks = (cnt + 3) >> 2;
     auto count_of = [&](int p) { return (int)((have >> (p * 16)) & 0xffffull); };
-    // open places, position by position: blocks [count_of(q), blocks) of position q
     int hq = 0, hh = count_of(0);
     auto settle = [&]() { while (hq < 4 && hh >= blocks) { ++hq; hh = hq < 4 ? count_of(hq) : 0; } };
     settle();
-    unsigned long long used = 0ull;
-    sweep([&](int m) {
-        const int p = m & 3;
-        const int t = (int)((used >> (p * 16)) & 0xffffull);
-        used += 1ull << (p * 16);
-        int blk, pos;
-        if (t < blocks) { blk = t; pos = p; }
-        else { blk = hh; pos = hq; ++hh; settle(); }
-        v.list[(size_t)(4 * blk + ((pos - k) & 3)) * v.stride + k] = m;
-    });
+    for (int p = 0; p < 4; ++p)
+        for (int t = blocks; t < count_of(p); ++t) {
+            const int m = v.list[(size_t)(4 * t + ((p - k) & 3)) * v.stride + k];
+            v.list[(size_t)(4 * hh + ((hq - k) & 3)) * v.stride + k] = m;
+            ++hh; settle();
+        }
     while (hq < 4) { v.list[(size_t)(4 * hh + ((hq - k) & 3)) * v.stride + k] = k; ++hh; settle(); } // sentinel: the slot itself
     v.nlist[k] = 4 * blocks;
 }
@@ -1087,9 +1094,10 @@ int cells_pairs(nbx_ctx *c, CellList *cl, double R, int pot, const double *px, c
     const bool same = cl->v_valid && cl->v_n == n && (slabv || cl->v_px == px) && cl->v_R == R && cl->v_skin == skin && cl->v_L == L &&
                       cl->v_key_div == key_div && cl->v_nc == cl->grid.nc[0] && cl->v_cap == cap && cl->v_banked == banked;
     if (!same) {
-        if (cl->v_cap_alloc < (int64_t)cap * cl->cap_n) {
-            NBX_TRY(dev_alloc(c, &cl->v_list, (size_t)cap * (size_t)cl->cap_n));
-            cl->v_cap_alloc = (int64_t)cap * cl->cap_n;
+        const int64_t rows = banked ? 2 * (int64_t)cap : (int64_t)cap; // (banked: the build places entries beyond the final length first)
+        if (cl->v_cap_alloc < rows * cl->cap_n) {
+            NBX_TRY(dev_alloc(c, &cl->v_list, (size_t)rows * (size_t)cl->cap_n));
+            cl->v_cap_alloc = rows * cl->cap_n;
         }
         if (cl->v_ref_n < cl->cap_n) {
             NBX_TRY(dev_alloc(c, &cl->v_ref, (size_t)3 * (size_t)cl->cap_n));

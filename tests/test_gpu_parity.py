@@ -786,13 +786,15 @@ def test_langevin_drift_is_the_oracles_without_noise(oracle, kind):
     ctx.close()
 
 
+@pytest.mark.parametrize("drift", [True, False])
 @pytest.mark.parametrize("water", [False, True])
-def test_coulomb_cutoff_beyond_the_cell_list_uses_each_pair_once(oracle, water):
+def test_coulomb_cutoff_beyond_the_cell_list_uses_each_pair_once(oracle, water, drift):
     """Coulomb with a cutoff of 0.49 L in a cubic periodic box (no cell list possible: R >= L/3): the Newton's-third-law
     kernel with the reference's periodic predicate (rij = ri - rj wrapped into [-L/2, L/2), un-fused r2, strict <) must
     reproduce the ordered all-pairs kernel and the oracle; lattice sites put many pairs exactly on the +-L/2 wrap tie
-    (all of them outside the cutoff), drifted coordinates exercise the wrap loops, water the own-molecule exclusion
-    across tile boundaries (1,024 is not a multiple of 3)."""
+    (all of them outside the cutoff), drifted coordinates exercise the wrap loops (the general variant of the kernel; with
+    every coordinate inside the box the branch-free one-round variant runs), water the own-molecule exclusion across tile
+    boundaries (1,024 is not a multiple of 3)."""
     rng = np.random.Generator(np.random.Philox(91))
     m, L = 22, 11.0
     g = (np.arange(m) + 0.5) * (L / m)
@@ -811,7 +813,9 @@ def test_coulomb_cutoff_beyond_the_cell_list_uses_each_pair_once(oracle, water):
         u[:, ::2] += 0.03 * rng.standard_normal(u[:, ::2].shape)                  # half the sites stay exactly on the lattice
         qs = np.where(np.arange(u.shape[1]) % 2 == 0, 1.0, -1.0) * (0.5 + rng.random(u.shape[1]))
         ms = rng.random(u.shape[1]) + 1.0
-    u = F(u + L * rng.integers(-2, 3, size=u.shape))                              # the reference never wraps positions
+    if drift:
+        u = u + L * rng.integers(-2, 3, size=u.shape)                             # the reference never wraps positions
+    u = F(u)
     spec = dict(ms=ms, qs=qs, water=water, bc=("cubic", L), coulomb=dict(k=1.7, R=0.49 * L))
     s = make_oracle(oracle, spec)
     targets = np.arange(0, u.shape[1], 23)
