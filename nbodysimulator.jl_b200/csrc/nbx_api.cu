@@ -103,10 +103,9 @@ int compute_pairs(nbx_ctx *c)
 {
     const bool pair_mode = c->pair_nranks > 1;
     if (pair_mode) {
-        const bool central_only = !c->has_lj && !c->has_dip && !c->has_spcfw && !c->water &&
-                                  (!c->has_coul || (c->bc_kind == NBX_BC_INFINITE && isinf(c->el_R2)));
-        if (!central_only)
-            return fail(c, NBX_ERR_UNSUPPORTED, "pair sharding covers unbounded gravity / Coulomb only; use nbx_shard");
+        if (!pair_capable(c))
+            return fail(c, NBX_ERR_UNSUPPORTED, "pair sharding covers unbounded gravity / Coulomb, and Coulomb with a cutoff of "
+                        "L/3 <= R < L/2 in a cubic box; use nbx_shard");
         NBX_TRY(zero_rows(c, c->acc, 0, c->n));
     }
     const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
@@ -157,7 +156,8 @@ int compute_pairs(nbx_ctx *c)
             if (!used) {
                 // no cell list for this cutoff (R >= L/3): all pairs with the exact periodic predicate -- once per UNORDERED pair
                 // when the context evaluates every target, the box is cubic and R < L/2 (no accepted pair on the wrap tie)
-                const bool whole = lo == 0 && hi == c->n && c->pair_nranks == 1 && !c->slab.on;
+                // (pair sharding: this rank's ring offsets, for all bodies -- the other terms above covered the own block only)
+                const bool whole = (pair_mode || (lo == 0 && hi == c->n)) && !c->slab.on;
                 if (whole && c->opt_sym && c->n >= c->sym_min_n && c->bc_kind == NBX_BC_CUBIC && c->el_R < 0.5 * c->bc[0])
                     NBX_TRY(launch_sympairs_coulomb_pbc(c, pot == 2, c->acc, accum));
                 else

@@ -132,10 +132,7 @@ int leader_accel(nbx_ctx *c, const double *u, double *v, double *dv)
         int mode = c->opt_group_mode;
         if (mode == 0 || mode == 3) mode = -1; // pairs where possible, else targets
         if (mode == -1) {
-            const nbx_ctx *x = c->members[0];
-            const bool central = !x->has_lj && !x->has_dip && !x->has_spcfw && !x->water && (x->has_grav || x->has_coul) &&
-                                 (!x->has_coul || (x->bc_kind == NBX_BC_INFINITE && std::isinf(x->el_R2)));
-            mode = central ? 1 : 2;
+            mode = pair_capable(c->members[0]) ? 1 : 2;
         }
         NBX_TRY(leader_join(c, mode));
     }

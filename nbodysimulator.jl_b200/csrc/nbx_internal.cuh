@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <utility>
+#include <cmath>
 #include <vector>
 
 #include "../../include/nbody_b200.h"
@@ -278,6 +279,25 @@ int dev_alloc(nbx_ctx *c, T **p, size_t count)
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc");
     return NBX_OK;
 }
+
+// Pair sharding (every rank evaluates its ring offsets of the Newton's-third-law kernel for ALL bodies, the partial rows
+// are summed at the owners) covers: unbounded gravity / Coulomb alone; and Coulomb with a cutoff that no cell list can
+// serve (L/3 <= R < L/2 in a cubic box: the periodic variant of the kernel) together with terms that each rank
+// evaluates for its own block only (Lennard-Jones over cell lists, the SPC/Fw bonds and angle) -- water with the
+// reference's default electrostatic cutoff of 0.49 L.
+inline bool pair_central_only(const nbx_ctx *c)
+{
+    return !c->has_lj && !c->has_dip && !c->has_spcfw && !c->water && (c->has_grav || c->has_coul) &&
+           (!c->has_coul || (c->bc_kind == NBX_BC_INFINITE && std::isinf(c->el_R2)));
+}
+inline bool pair_periodic_coulomb(const nbx_ctx *c)
+{
+    if (!c->has_coul || c->has_grav || c->has_dip || c->bc_kind != NBX_BC_CUBIC || !c->opt_sym || c->n < c->sym_min_n) return false;
+    const double L = c->bc[0], R = c->el_R;
+    if (!(L > 0.0) || !std::isfinite(R) || !(R > 0.0) || !(R < 0.5 * L)) return false;
+    return !c->opt_cell_list || std::floor(L / (R * (1.0 + 1e-6))) < 3.0; // (cells_plan: fewer than 3 cells per edge)
+}
+inline bool pair_capable(const nbx_ctx *c) { return pair_central_only(c) || pair_periodic_coulomb(c); }
 
 // ---- kernels implemented across the .cu files (host launchers) ----------------------------
 // nbx_allpairs.cu

@@ -263,12 +263,6 @@ int comm_allreduce3(nbx_ctx *c, const double *in0, double *out0, int *flag_out, 
     return NBX_OK;
 }
 
-static bool central_only(const nbx_ctx *c)
-{
-    return !c->has_lj && !c->has_dip && !c->has_spcfw && !c->water && (c->has_grav || c->has_coul) &&
-           (!c->has_coul || (c->bc_kind == NBX_BC_INFINITE && std::isinf(c->el_R2)));
-}
-
 static bool slab_capable(const nbx_ctx *c)
 {
     const bool coul_cut = c->has_coul && std::isfinite(c->el_R);
@@ -289,11 +283,12 @@ int group_init(nbx_ctx *c, int rank, int nranks, int mode)
         return fail(c, NBX_ERR_INVALID, "nbx_group_init: the context is already sharded");
     if (c->thermo == NBX_THERMO_NOSEHOOVER) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_group_init: the Nose-Hoover thermostat is not distributed");
     if (mode == 0) {
-        if (central_only(c)) mode = 1;
+        if (pair_capable(c)) mode = 1;
         else if (slab_capable(c)) mode = 3;
         else mode = 2;
     }
-    if (mode == 1 && !central_only(c)) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_group_init: pair sharding covers unbounded gravity / Coulomb only");
+    if (mode == 1 && !pair_capable(c))
+        return fail(c, NBX_ERR_UNSUPPORTED, "nbx_group_init: pair sharding covers unbounded gravity / Coulomb, and Coulomb with L/3 <= R < L/2 in a cubic box");
     graph_drop(c);
     NBX_TRY(comm_alloc(c));
     Comm &m = c->comm;

@@ -97,6 +97,9 @@ def _group_cases():
     ww = wl.water_omm(8, Rel=0.9)
     water = dict(ms=ww["ms"], qs=ww["qs"], water=True, bc=("cubic", ww["L"]), lj=ww["lj"], coulomb=ww["coulomb"], spcfw=ww["spcfw"])
     cases.append(("targets water", water, np.asfortranarray(ww["u"]), np.asfortranarray(ww["v"]), ww["dt"], 20, False, 1e-9))
+    wp = wl.water_omm(14)   # default electrostatic cutoff 0.49 L, 8,232 atoms: the unordered Coulomb pairs are sharded
+    waterp = dict(ms=wp["ms"], qs=wp["qs"], water=True, bc=("cubic", wp["L"]), lj=wp["lj"], coulomb=wp["coulomb"], spcfw=wp["spcfw"])
+    cases.append(("pairs water", waterp, np.asfortranarray(wp["u"]), np.asfortranarray(wp["v"]), wp["dt"], 10, False, 1e-9))
     wc = wl.charged_lattice(12288)
     em = dict(ms=wc["ms"], qs=wc["qs"], coulomb=dict(k=wc["coulomb"]["k"], R=np.inf),
               thermostat=dict(kind="langevin", T=90.0, gamma=10.0, kB=1.38e-23))

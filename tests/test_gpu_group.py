@@ -207,6 +207,39 @@ def test_target_block_group_water(oracle):
     one.close(); grp.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_pair_sharded_water_group_with_the_default_cutoff(oracle, world):
+    """SPC/Fw water with the reference's default electrostatic cutoff of 0.49 L (no cell list can serve it): the group
+    shards the UNORDERED Coulomb pairs (periodic Newton's-third-law kernel, every rank its ring offsets, partial rows summed
+    at the owners), while the O-O Lennard-Jones term and the bonds / angle are evaluated by the owner of a block alone."""
+    w = wl.water_omm(14)            # 2,744 molecules = 8,232 atoms: above symmetric_min_n
+    spec = dict(ms=w["ms"], qs=w["qs"], water=True, bc=("cubic", w["L"]), lj=w["lj"], coulomb=w["coulomb"], spcfw=w["spcfw"],
+                thermostat=dict(kind="berendsen", T=300.0, tau=0.05, kB=w["kB"], N=3 * w["nmol"], Nc=2 * w["nmol"]))
+    assert w["coulomb"]["R"] > w["L"] / 3
+    rng = np.random.Generator(np.random.Philox(21))
+    u, v = F(w["u"] + 0.004 * rng.standard_normal(w["u"].shape)), F(w["v"])
+    one = make_context(spec)
+    grp = _group(spec, [0] * world)
+    a1 = one.accel(u, F(v.copy())).copy()
+    ag = grp.accel(u, F(v.copy()))
+    assert grp.info("group_mode") == 1
+    assert _relmax(ag, a1) < 1e-12
+    mols = np.sort(np.random.Generator(np.random.Philox(3)).choice(w["nmol"], 40, replace=False))
+    targets = (3 * mols[:, None] + np.arange(3)[None, :]).ravel()
+    nothermo = {k: val for k, val in spec.items() if k != "thermostat"}
+    ref = make_oracle(oracle, nothermo).accel_molecules(u, mols, NT)
+    g0 = _group(nothermo, [0] * world)
+    assert _relmax(g0.accel(u)[:, targets], ref) < 1e-11
+    g0.close()
+    dt, nsteps = w["dt"], 20
+    one.upload(u, v); one.step_vv(dt, nsteps)
+    grp.upload(u, v); grp.step_vv(dt, nsteps)
+    u1, v1, _ = one.download()
+    ug, vg, _ = grp.download()
+    assert _relmax(ug, u1) < 1e-11 and _relmax(vg, v1) < 1e-8
+    one.close(); grp.close()
+
+
 @pytest.mark.parametrize("kind", ["coulomb", "dipole"])
 def test_group_langevin_euler_maruyama(kind):
     """Config 5 over a group: the noise is keyed by (seed, step, global column), so the group walks the
