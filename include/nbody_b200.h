@@ -143,8 +143,8 @@ NBX_API int nbx_accel(nbx_ctx *ctx, const double *u, double *v, double t, double
  *   x+ = x + dt v + dt^2/2 a;  a+ = f(v, x+);  v+ = v + dt/2 (a + a+)
  * (OrdinaryDiffEqSymplecticRK VelocityVerlet, upstream); Berendsen / Nose-Hoover enter
  * through f, Andersen resamples velocities after each step.  step_em is Euler-Maruyama on
- * the Langevin SDE (src/nbody_to_ode.jl:575-595).  download copies state back (any pointer
- * may be NULL). */
+ * the Langevin SDE (src/nbody_to_ode.jl:575-595; for water the SDEProblem of WaterSPCFw, :600-680, with its
+ * own drift and noise amplitudes as written there).  download copies state back (any pointer may be NULL). */
 NBX_API int nbx_upload(nbx_ctx *ctx, const double *u, const double *v);
 NBX_API int nbx_step_vv(nbx_ctx *ctx, double dt, int64_t nsteps);
 NBX_API int nbx_step_em(nbx_ctx *ctx, double dt, int64_t nsteps, uint64_t seed);

@@ -995,7 +995,6 @@ int nbx_step_em(nbx_ctx *c, double dt, int64_t nsteps, uint64_t seed)
     NBX_TRY(need_resident(c, "nbx_step_em"));
     NBX_TRY(no_slab(c, "nbx_step_em"));
     if (c->thermo != NBX_THERMO_LANGEVIN) return fail(c, NBX_ERR_INVALID, "nbx_step_em: needs the Langevin thermostat");
-    if (c->water) return fail(c, NBX_ERR_UNSUPPORTED, "nbx_step_em: the water SDE variant (src/nbody_to_ode.jl:600-680) is not built");
     if (seed) c->seed = seed;
     if (c->comm.on) {
         NBX_TRY(multi_enqueue_em(c, dt, nsteps));

@@ -379,25 +379,35 @@ __device__ __forceinline__ void normals3(uint64_t seed, uint64_t step, uint32_t 
 // Euler-Maruyama on the Langevin SDE (src/nbody_to_ode.jl:575-595):
 //   x+ = x + dt v ;  v+ = v + dt (a - gamma v) + sigma sqrt(dt) xi
 // sigma is the reference's scalar sqrt(2 gamma kb T / m_1) for every atom (:592).
+// Water (the SDEProblem of WaterSPCFw, :600-680), as written there: the oxygen column gets -(gamma v) / mO on top of the
+// -gamma v that every column gets at the end (the same term subtracted from the hydrogen columns inside the oxygen loop is
+// zeroed again by the hydrogen loop, :627-636), and the noise amplitudes are sqrt(2 gamma kb T) / mO and / mH (:668-669:
+// divided by the mass, not by its root).
 __global__ void em_kernel(double *__restrict__ pos, double *__restrict__ vel, const double *__restrict__ acc,
                           const double *__restrict__ mass, int64_t ld, int64_t lo, int64_t hi, double dt, double gamma,
-                          double sig_sqdt, uint64_t seed, uint64_t step, double *__restrict__ partial)
+                          double sig_sqdt, int water, uint64_t seed, uint64_t step, double *__restrict__ partial)
 {
     double s = 0.0;
     for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
         double g[3], u;
         normals3(seed, step, 1u, (uint64_t)i, g, u);
+        const double m = mass[i];
+        const bool oxygen = water && (i % 3 == 0);
+        const double amp = water ? sig_sqdt / m : sig_sqdt; // (water: sig_sqdt = sqrt(2 gamma kb T) sqrt(dt))
         double v2 = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const int64_t k = d * ld + i;
             const double v = vel[k];
             pos[k] = fma(dt, v, pos[k]);
-            const double vn = v + dt * (acc[k] - gamma * v) + sig_sqdt * g[d];
+            double drift = acc[k];
+            if (oxygen) drift -= gamma * v / m;
+            drift -= gamma * v;
+            const double vn = v + dt * drift + amp * g[d];
             vel[k] = vn;
             v2 = fma(vn, vn, v2);
         }
-        s = fma(mass[i], v2, s);
+        s = fma(m, v2, s);
     }
     const double b = block_sum(s);
     if (threadIdx.x == 0) partial[blockIdx.x] = b;
@@ -408,10 +418,10 @@ int launch_em_step(nbx_ctx *c, double dt)
     NBX_TRY(ensure_red(c));
     const int64_t lo = c->tgt_lo, hi = c->tgt_hi;
     const int nb = red_blocks(c, hi - lo);
-    const double sigma = sqrt(2.0 * c->tparam * c->kB * c->T0 / c->h_m1);
+    const double sigma = c->water ? sqrt(2.0 * c->tparam * c->kB * c->T0) : sqrt(2.0 * c->tparam * c->kB * c->T0 / c->h_m1);
     timer_begin(c, NBX_T_INTEGRATE);
     em_kernel<<<nb, kRedThreads, 0, c->stream>>>(c->pos, c->vel, c->acc, c->mass, c->npad, lo, hi, dt, c->tparam,
-                                                sigma * sqrt(dt), c->seed, c->rng_step, c->d_red);
+                                                sigma * sqrt(dt), c->water ? 1 : 0, c->seed, c->rng_step, c->d_red);
     final_sum_kernel<<<1, kRedThreads, 0, c->stream>>>(c->d_red, nb, c->d_scal);
     timer_end(c, NBX_T_INTEGRATE);
     NBX_CUDA(c, cudaGetLastError());

@@ -323,3 +323,25 @@ def euler_maruyama(sys: System, u0, v0, dt, nsteps, gamma, sigma, rng, nthreads=
         v = np.asfortranarray(v + dt * (a - gamma * v) + sigma * dW)
         u = np.asfortranarray(u_new)
     return u, v
+
+
+def euler_maruyama_water(sys: System, u0, v0, dt, nsteps, gamma, kT, mO, mH, rng, nthreads=1):
+    """EM on the SDE of WaterSPCFw, src/nbody_to_ode.jl:600-680, as written there: drift = a - gamma v for every column
+    (:664), the oxygen columns additionally - (gamma v) / mO (:627-629; the terms subtracted from the hydrogen columns at
+    :630-633 are zeroed again by the hydrogen loop :636-641); noise sqrt(2 gamma kb T) / mO and / mH (:668-676)."""
+    u = np.array(u0, dtype=np.float64, order="F")
+    v = np.array(v0, dtype=np.float64, order="F")
+    sq = np.sqrt(dt)
+    root = np.sqrt(2.0 * gamma * kT)
+    sig = np.tile([root / mO, root / mH, root / mH], u.shape[1] // 3)
+    for _ in range(nsteps):
+        a = sys.rhs(u, v, nthreads)
+        drift = a.copy()
+        drift[:, 0::3] -= gamma * v[:, 0::3] / mO
+        drift -= gamma * v
+        dW = sq * rng.standard_normal(v.shape)
+        u_new = u + dt * v
+        v = np.asfortranarray(v + dt * drift + sig[None, :] * dW)
+        u = np.asfortranarray(u_new)
+    return u, v
+

@@ -786,6 +786,43 @@ def test_langevin_drift_is_the_oracles_without_noise(oracle, kind):
     ctx.close()
 
 
+def test_water_langevin_sde_variant(oracle):
+    """The SDEProblem of WaterSPCFw (src/nbody_to_ode.jl:600-680) as written there: every column drifts with a - gamma v,
+    the oxygen columns additionally with -(gamma v) / mO, and the noise amplitudes are sqrt(2 gamma kb T) / mO and / mH.
+    T0 = 0: the Euler-Maruyama steps equal the oracle's; T0 > 0: one step from the same state, the increments beyond the
+    drift have those two standard deviations (9,000 and 18,000 samples)."""
+    from oracle import nbody_oracle as orc
+
+    w, u, spec = _water(10, 8, Rel=0.9)     # 1,000 molecules
+    v = F(w["v"])
+    mO, mH = float(w["ms"][0]), float(w["ms"][1])
+    gamma, dt, nsteps = 5.0, 0.5 * w["dt"], 4
+    s = make_oracle(oracle, spec)
+    x, y = orc.euler_maruyama_water(s, u, v, dt, nsteps, gamma, 0.0, mO, mH, np.random.default_rng(0), NT)
+    ctx = make_context(dict(spec, thermostat=dict(kind="langevin", T=0.0, gamma=gamma, kB=w["kB"])))
+    ctx.upload(u, v)
+    ctx.step_em(dt, nsteps, 5)
+    ug, vg, ag = ctx.download(want_dv=True)
+    assert rel_err_per_body(ug, x).max() < 1e-13
+    assert rel_err_per_body(vg, y).max() < 1e-10
+    _check(ag, s.rhs(x, y, NT), tol=1e-11)   # a(x_end) is left resident (positions differ by 1e-13: stiff bonds amplify)
+    ctx.close()
+    T0 = 300.0
+    ctx = make_context(dict(spec, thermostat=dict(kind="langevin", T=T0, gamma=gamma, kB=w["kB"])))
+    ctx.upload(u, v)
+    ctx.step_em(dt, 1, 7)
+    _, v1, _ = ctx.download()
+    a0 = s.rhs(u, v, NT)
+    drift = a0 - gamma * v
+    drift[:, 0::3] -= gamma * v[:, 0::3] / mO
+    kick = (v1 - v - dt * drift) / np.sqrt(dt)
+    root = np.sqrt(2.0 * gamma * w["kB"] * T0)
+    assert abs(kick[:, 0::3].std() / (root / mO) - 1.0) < 0.04
+    assert abs(np.concatenate([kick[:, 1::3], kick[:, 2::3]], axis=1).std() / (root / mH) - 1.0) < 0.03
+    assert abs(kick.mean()) < 4.0 * (root / mH) * np.sqrt(2.0 / 3.0 / kick.size)   # (the hydrogens carry the variance)
+    ctx.close()
+
+
 @pytest.mark.parametrize("drift", [True, False])
 @pytest.mark.parametrize("water", [False, True])
 def test_coulomb_cutoff_beyond_the_cell_list_uses_each_pair_once(oracle, water, drift):
