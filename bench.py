@@ -380,8 +380,8 @@ def other_configs(local, world, steps=5):
     try:
         for tag, rel, what in (("config4_water_cutoff_0.9162nm", 0.9162, "cell lists for O-O Lennard-Jones and Coulomb"),
                                ("config4_water_cutoff_0.49L", None, "Coulomb cutoff 4.886 nm = 0.49 L (no cell list possible): every unordered pair "
-                                                                    "once, the reference's periodic predicate (1 GPU: Newton's-"
-                                                                    "third-law kernel; groups: ordered target blocks)")):
+                                                                    "once, the reference's periodic predicate (Newton's-third-law "
+                                                                    "kernel; groups shard the ring offsets)")):
             w = wl.water_omm(32, Rel=rel)
             ctx = _lib.Context(local)
             ctx.system(w["ms"], qs=w["qs"], water=True)
@@ -426,6 +426,28 @@ def other_configs(local, world, steps=5):
                         "value": float(n) * float(n - 1) / (ms * 1e-3), "unit": "pair-interactions/s", "ms_per_step": ms,
                         "n_bodies": n, "n_gpus": world, "decomposition": modes[mode]}
             ctx.close()
+        if world == 1:
+            # config 1, the reference's own CPU-runnable case (examples/liquid_argon.jl as shipped: 216 atoms, R = L/2, velocity
+            # Verlet, no thermostat): the only configuration whose WHOLE workload the CPU port runs here
+            from oracle import nbody_oracle as orc
+
+            w = wl.liquid_argon_si(216)
+            ctx = _lib.Context(local)
+            ctx.system(w["ms"])
+            ctx.boundary(_lib.BC_CUBIC, [w["L"]])
+            ctx.add_lj(w["lj"]["eps"], w["lj"]["sigma"], w["lj"]["R"])
+            grouped(ctx, w["u"], w["v"])
+            ms = timed(lambda k: ctx.step_vv(w["dt"], k), 3000)
+            ctx.close()
+            sysc = orc.System(w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
+            t0 = time.perf_counter()
+            orc.velocity_verlet(sysc, w["u"], w["v"], w["dt"], 300, 1)
+            cpu_ms = (time.perf_counter() - t0) / 300 * 1e3
+            out["config1_liquid_argon_216"] = {"metric": "LJ argon atom-steps/s (examples/liquid_argon.jl as shipped: 216 atoms, R = L/2, velocity Verlet)",
+                                               "value": 216 / (ms * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms, "n_atoms": 216,
+                                               "n_gpus": 1, "decomposition": "1 GPU (a graph of two steps; the step is launch-bound)",
+                                               "cpu_port_1_thread": {"value": 216 / (cpu_ms * 1e-3), "unit": "atom-steps/s",
+                                                                     "ms_per_step": cpu_ms, "sample": "300 of the example's 30,000 steps"}}
     except Exception as e:  # never lose the headline line
         out["error"] = repr(e)
     torch.cuda.synchronize()

@@ -337,7 +337,7 @@ int nbx_destroy(nbx_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_system(c);
-    cudaFree(c->d_scal); cudaFree(c->d_red); cudaFree(c->part);
+    cudaFree(c->sym_ticket); cudaFree(c->d_scal); cudaFree(c->d_red); cudaFree(c->part);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (auto &t : c->timers)
         for (cudaEvent_t ev : t.ev) cudaEventDestroy(ev);
@@ -1193,6 +1193,7 @@ int nbx_set_option(nbx_ctx *c, const char *key, int64_t value)
     else if (!strcmp(key, "symmetric_pairs")) c->opt_sym = (int)value;
     else if (!strcmp(key, "symmetric_min_n")) c->sym_min_n = value;
     else if (!strcmp(key, "sym_variant")) c->opt_sym_variant = (int)value;
+    else if (!strcmp(key, "sym_seg_len")) c->opt_sym_seg_len = (int)value;
     else if (!strcmp(key, "uniform_weights")) { if (!value) c->mass_uniform = c->charge_uniform = false; }
     else return fail(c, NBX_ERR_INVALID, "nbx_set_option: unknown key '%s'", key);
     return NBX_OK;

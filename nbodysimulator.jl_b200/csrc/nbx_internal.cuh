@@ -205,6 +205,8 @@ struct nbx_ctx {
     size_t part_bytes = 0;
     std::vector<const void *> attr_done; // kernels whose dynamic-smem attribute is set
     int last_grid = 0, last_nchunk = 0;
+    int *sym_ticket = nullptr;     // work-item counter of the symmetric all-pairs kernel (zeroed before every launch)
+    int opt_sym_seg_len = 0;       // ring offsets per work item of that kernel (0: chosen from the share)
 
     // ---- water oxygen sub-system (compact SoA of the O columns) ----------------------------
     double *opos = nullptr, *oacc = nullptr; // [3][opad]

@@ -38,6 +38,7 @@ struct SymParams {
     int hi_radius;
     const int *gate;       // the kernel runs iff gate == nullptr or gate[0] == gate_want (fast / general periodic variant)
     int gate_want;
+    int *ticket;           // work items are handed out by this counter (zeroed on the stream before the launch)
 };
 
 // PBC = 1: Coulomb with a cutoff under CubicPeriodicBoundaryConditions (src/basic_potentials.jl:288-297 with the distance of
@@ -177,12 +178,20 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     double *red = ring + 2 * 4 * TS;                            // [4 warps][3][SET]
     __shared__ __align__(8) uint64_t full[2];
 
+    __shared__ int s_item[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (PBC && p.gate && p.gate[0] != p.gate_want) return;
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         fence_mbar_init();
+        // Work items (tile A, segment of ring offsets) are taken from a counter, two at a time: the one in hand and the next,
+        // whose first B tile is fetched during the last tile of the current one.  Items differ in cost (the half offset of an
+        // even ring, the diagonal block, dead items of a rank's share), and a rank of 8 has only ~14 tiles per CTA: the
+        // static round-robin of r01 cost it 16 tile times.  Every item writes its own slots: the sums do not depend on
+        // which CTA took it.
+        s_item[0] = atomicAdd(p.ticket, 1);
+        s_item[1] = atomicAdd(p.ticket, 1);
     }
     __syncthreads();
     uint32_t parity = 0;
@@ -203,7 +212,9 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
     int st = 0;              // ring stage of the next tile: runs on across items
     bool have_first = false; // the previous item already issued this item's first tile (a short segment must not
                              // expose the copy latency once per item: multi-GPU shares have two offsets per segment)
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    int item = s_item[0], item_next = s_item[1];
+    __syncthreads();
+    while (item < nitems) {
         const int A = item / p.S, seg = item - A * p.S;
         const int m0 = seg * p.seg_len;
         const int m1 = min(m0 + p.seg_len, p.M);
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             if (mn < m1) {
                 if (tid == 0) issue(A, mn, st ^ 1); // stage st^1 was released by the barrier that ended the previous block
             } else {
-                const int item2 = item + gridDim.x; // last tile of this item: fetch the first tile of the next one meanwhile
+                const int item2 = item_next; // last tile of this item: fetch the first tile of the next one meanwhile
                 if (item2 < nitems) {
                     const int A2 = item2 / p.S, seg2 = item2 - A2 * p.S;
                     const int e2 = min((seg2 + 1) * p.seg_len, p.M);
@@ -294,6 +305,11 @@ __global__ void __launch_bounds__(128, MINB) sym_kernel(const SymParams p)
             slot[(size_t)p.npad + i] = fy[t];
             slot[2 * (size_t)p.npad + i] = fz[t];
         }
+        if (tid == 0) s_item[0] = atomicAdd(p.ticket, 1);
+        __syncthreads();
+        item = item_next;
+        item_next = s_item[0];
+        __syncthreads();
     }
 }
 
@@ -349,13 +365,23 @@ static int run_sym(nbx_ctx *c, const double *w, double wval, int scale_kind, dou
     p.M0 = p.kr0 <= kfull ? (kfull - p.kr0) / p.kstride + 1 : 0;
     p.M = p.M0 + (half ? 1 : 0);
     const int grid_full = c->sm_count * MINB;
-    // enough items for a balanced static round-robin (>= ~24 per CTA), at least 2 offsets per segment
-    int S = (24 * grid_full + p.NT - 1) / p.NT;
-    const int max_S = (p.M + 1) / 2;
-    if (S > max_S) S = max_S;
-    if (S < 1) S = 1;
-    p.seg_len = p.M > 0 ? (p.M + S - 1) / S : 1;
+    // Segment length: the CTAs take items from a counter, so a launch lasts about (all tiles) / grid + one item + a fixed
+    // cost per item (A-side loads and slot writes; measured small: 262,144 bodies, whole ring of 129 offsets, ms per launch
+    // for 1 / 2 / 3 / 5 offsets per item: 40.13 / 40.31 / 40.37 / 40.50 -- but every segment is another 6 MB slot for the
+    // reduction to read; one rank of eight, 17 offsets: 5.19 / 5.35 / 5.66; the static round-robin of r01: 42.04 and 5.63)
+    int best_len = 1;
+    double best_cost = 1e300;
+    for (int len = 1; len <= 16 && len <= (p.M > 0 ? p.M : 1); ++len) {
+        const double segs = (double)((p.M + len - 1) / len);
+        const double cost = (double)p.NT * p.M / grid_full + len + 0.05 * (double)p.NT * segs / grid_full;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_len = len; }
+    }
+    if (c->opt_sym_seg_len > 0) best_len = c->opt_sym_seg_len;
+    p.seg_len = best_len;
     p.S = p.M > 0 ? (p.M + p.seg_len - 1) / p.seg_len : 1;
+    if (!c->sym_ticket) NBX_TRY(dev_alloc(c, &c->sym_ticket, (size_t)2));
+    p.ticket = c->sym_ticket;
+    NBX_CUDA(c, cudaMemsetAsync(c->sym_ticket, 0, sizeof(int), c->stream));
     const size_t bytes = (size_t)(p.S + p.M) * 3 * p.npad * sizeof(double);
     if (bytes > c->part_bytes) {
         if (c->part) { cudaFree(c->part); c->part = nullptr; c->part_bytes = 0; }
