@@ -156,6 +156,35 @@ function NBodySimulator.run_simulation(s::NBodySimulation, ::B200VelocityVerlet;
     return NBodySimulator.SimulationResult(sol, s)
 end
 
+# Langevin thermostat: the SDE path of run_simulation (src/nbody_simulation_result.jl:488-492, calculate_simulation_sde) with the
+# Euler-Maruyama steps fused on the device (nbx_step_em: atoms src/nbody_to_ode.jl:567-598, water :600-680).  Frames are laid
+# out as the reference's SDEProblem state, hcat(u, v) (3 x 2 ncols).
+struct B200EM end
+
+function NBodySimulator.run_simulation(s::NBodySimulation, ::B200EM; dt, saveat::Integer = 1, seed::Integer = 1, device = 0)
+    s.thermostat isa LangevinThermostat || error("B200EM needs a LangevinThermostat (the reference's SDEProblem)")
+    ctx = configure!(B200Context(device), s)
+    (u0, v0, n) = gather_bodies_initial_coordinates(s)
+    check(ctx, ccall((:nbx_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx.h, u0, v0))
+    nsteps = round(Int, (s.tspan[2] - s.tspan[1]) / dt)
+    ts = [s.tspan[1]]
+    frames = [hcat(u0, v0)]
+    u = similar(u0); v = similar(v0)
+    done = 0
+    while done < nsteps
+        k = min(saveat, nsteps - done)
+        # the seed fixes the Philox key once; the library's step counter runs on across the calls
+        check(ctx, ccall((:nbx_step_em, LIB), Cint, (Ptr{Cvoid}, Float64, Int64, UInt64), ctx.h, dt, k, done == 0 ? UInt64(seed) : UInt64(0)))
+        check(ctx, ccall((:nbx_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ctx.h, u, v, C_NULL))
+        done += k
+        push!(ts, s.tspan[1] + done * dt)
+        push!(frames, hcat(u, v))
+    end
+    prob = SciMLBase.SDEProblem(s)     # only its type and u0 shape are used by the result accessors
+    sol = SciMLBase.build_solution(prob, B200EM(), ts, frames; retcode = SciMLBase.ReturnCode.Success)
+    return NBodySimulator.SimulationResult(sol, s)
+end
+
 # ---- (3) the plugin interface itself: a PotentialParameters subtype served by the device ----------------------------
 """
     GPUPotential(parameters)
@@ -238,6 +267,6 @@ function msd_b200(sr::NBodySimulator.SimulationResult; device::Integer = 0)
     return (ts, dr2)
 end
 
-export B200Context, B200Problem, B200VelocityVerlet, GPUPotential, rdf_b200, msd_b200
+export B200Context, B200Problem, B200VelocityVerlet, B200EM, GPUPotential, rdf_b200, msd_b200
 
 end # module

@@ -298,6 +298,38 @@ __global__ void allpairs_reduce_kernel(const double *__restrict__ part, int nchu
     }
 }
 
+// Small systems (the reference's own examples: 216 argon atoms, 216 water molecules): the tiled kernel would put all targets
+// into ONE CTA that walks the sources serially (221 us for 216 atoms with R = L/2: one warp per scheduler, every FP64
+// latency exposed).  Here a warp owns a target, its lanes stride over the sources straight from L2 and meet in a butterfly
+// of fixed order; the partial sums land in chunk 0 of the layout the reduce kernel reads.
+template <class P>
+__global__ void __launch_bounds__(128) allpairs_small_kernel(const APParams p, const typename P::Args args)
+{
+    constexpr int NA = P::NA, NACC = P::NACC;
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= p.ntgt) return; // (warp-uniform)
+    const typename P::Tgt tg = P::load(args, p.tgt_lo + w);
+    double acc[NACC];
+#pragma unroll
+    for (int c = 0; c < NACC; ++c) acc[c] = 0.0;
+    for (int j = lane; j < p.n; j += 32) {
+        double s[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) s[a] = p.src[a][j];
+        P::template pair<true>(args, tg, acc, s, j, p.n);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < NACC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < NACC; ++c) p.part[(size_t)c * p.part_ld + w] = acc[c];
+    }
+}
+constexpr int kSmallSystem = 1024; // sources and targets up to which the warp-per-target kernel is used
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -336,6 +368,19 @@ template <class P, int T, int THREADS, int S, int NST, int MINB>
 static int run_allpairs(nbx_ctx *c, APParams *p, const typename P::Args &args)
 {
     int grid = 1;
+    if (p->n <= kSmallSystem && p->ntgt <= kSmallSystem && p->ntgt > 0) {
+        p->ntiles = 1; p->nchunk = 1; p->chunk_len = p->nsrc_pad;
+        p->part_ld = ((p->ntgt + 31) / 32) * 32;
+        NBX_TRY(ensure_part(c, (size_t)P::NACC * p->part_ld * sizeof(double)));
+        p->part = c->part;
+        timer_begin(c, NBX_T_PAIR_ALLPAIRS);
+        allpairs_small_kernel<P><<<(p->ntgt + 3) / 4, 128, 0, c->stream>>>(*p, args);
+        timer_end(c, NBX_T_PAIR_ALLPAIRS);
+        NBX_CUDA(c, cudaGetLastError());
+        c->last_grid = (p->ntgt + 3) / 4;
+        c->last_nchunk = 1;
+        return NBX_OK;
+    }
     plan_items<T, THREADS, S>(c, MINB, p, &grid);
     NBX_TRY(ensure_part(c, (size_t)p->nchunk * P::NACC * p->part_ld * sizeof(double)));
     p->part = c->part;

@@ -2,7 +2,7 @@
 # Run on the GPU box (gpurun -- bash profiles/run_profiles.sh <tag>): launch lists + one full-set capture
 # per dominant kernel.  Outputs land in gpurun_out/; `python profiles/summarize.py <tag>` then writes the tracked
 # summaries under profiles/.
-TAG=${1:-r02b}
+TAG=${1:-r02c}
 OUT=gpurun_out
 mkdir -p $OUT
 # (1) launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
