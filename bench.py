@@ -327,7 +327,7 @@ def lj_secondary(local, world, steps, warmup, cells=LJ_CELLS, weak=False):
         "inputs": "25 MB of positions per 1M atoms (L2-resident), Verlet lists streamed from HBM; L2 not flushed between steps",
         "ms_per_step_pair_kernel": pair_ms / k_t, "ms_per_step_cell_build": build_ms / k_t,
         "ms_per_step_integrate": int_ms / k_t,
-        "neighbour_structure": f"Verlet lists (skin 0.1 R) over the cell list, rebuilt when a particle moved skin/2 (decided on the "
+        "neighbour_structure": f"Verlet lists (skin 0.08 R) over the cell list, rebuilt when a particle moved skin/2 (decided on the "
                                f"device{', collectively' if world > 1 else ''}): {rebuilds} rebuilds in the {steps} timed steps",
         "graph": bool(graph), "parity": parity,
     }

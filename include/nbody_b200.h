@@ -298,7 +298,7 @@ NBX_API int nbx_timing_reset(nbx_ctx *ctx);
 /* Tuning knobs (integers; defaults in parentheses; DESIGN.md section 3 says what each buys).  Unknown key -> NBX_ERR_INVALID.
  *   cutoff potentials : "cell_list" (1: cell lists where the box allows, 0: all-pairs kernel with the exact predicate),
  *                       "prefilter" (1: fp32 candidate scan before the exact fp64 predicate),
- *                       "verlet_skin_permille" (100: Verlet lists with skin = 0.1 R; 0: rescan the cells every evaluation),
+ *                       "verlet_skin_permille" (80: Verlet lists with skin = 0.08 R; 0: rescan the cells every evaluation),
  *                       "verlet_lanes" (0: lanes per target chosen from the system size; 1, 2, 4, 8),
  *                       "verlet_banked" (1: a target's list is stored in blocks of four ordered by the partner record's position
  *                       inside its 128-byte line, so that the gathers of four neighbouring lanes never collide in the L1 data

@@ -216,7 +216,7 @@ struct nbx_ctx {
     nbx::CellList cl_lj, cl_el;
     int opt_cell_list = 1;
     int opt_prefilter = 1;
-    int opt_verlet_permille = 100; // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
+    int opt_verlet_permille = 80;  // Verlet skin in thousandths of the cutoff (0: rescan the cells on every evaluation)
     int opt_graph = 1;
     // CUDA graph of nbx_step_vv: the conditional rebuild chain (nine launches that return at once) becomes the body of
     // an IF node decided by one single-thread kernel (cudaGraphSetConditional); falls back to plain capture if the

@@ -577,7 +577,7 @@ def test_lj_config3_full_size_subsample(oracle):
     spec = dict(ms=w["ms"], bc=("cubic", w["L"]), lj=w["lj"])
     ctx = make_context(spec)
     a = ctx.accel(u)
-    assert ctx.info("cells_lj") == 44 ** 3 and ctx.info("verlet_lj") > 0  # cells of edge >= R + skin, skin = 0.1 R
+    assert ctx.info("cells_lj") == 44 ** 3 and ctx.info("verlet_lj") > 0  # cells of edge >= R + skin, skin = 0.08 R
     targets = np.sort(np.random.Generator(np.random.Philox(9)).choice(n, 768, replace=False))
     s = make_oracle(oracle, spec)
     ref = s.accel_targets(u, targets, NT)
