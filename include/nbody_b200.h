@@ -306,11 +306,13 @@ NBX_API int nbx_timing_reset(nbx_ctx *ctx);
  *                       always use 0, and a context that is compared bit for bit with them -- or joins a group by hand after
  *                       its upload -- sets 0 as well), "verlet_branchfree" (1: batches of four list entries evaluated without
  *                       branches; same operations, same sums),
- *   groups            : "group_mode" (leader of nbx_create_multi; 0), "pin_host" (0; 1: page-lock the caller's u / v / dv buffers
+ *   groups            : "group_mode" (leader of nbx_create_multi; 0), "spin_timeout_ms" (10000: a device-side wait for a peer gives
+ *                       up after this long and raises the error flag nbx_slab_check / nbx_synchronize report), "pin_host" (0; 1: page-lock the caller's u / v / dv buffers
  *                       the first time nbx_accel sees them -- the caller must keep them alive until nbx_destroy / nbx_system),
  *   nbx_step_vv       : "graph" (1: two-step CUDA graph), "graph_if_nodes" (1: rebuild chain as the body of an IF node),
  *                       "fuse_update" (1: position update + displacement check + record refresh in one kernel),
  *   all-pairs         : "symmetric_pairs" (1: Newton's-third-law kernel), "symmetric_min_n" (8192), "sym_variant" (0),
+ *                       "sym_seg_len" (0: ring offsets per work item chosen from the share; 1 .. 16),
  *                       "uniform_weights" (0 forgets that all masses / charges are equal),
  *   slab driver       : "slab_record_halo", "slab_rebuild", "temperature_slot" (see the slab section above).
  * nbx_get_info keys: "n", "npad", "ncols", "water", "sm_count", "thermostat", "cells_lj", "cells_el", "verlet_lj", "verlet_el",
