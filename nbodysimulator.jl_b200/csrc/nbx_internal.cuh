@@ -544,6 +544,33 @@ __device__ __forceinline__ bool ll_load(const unsigned long long *src, unsigned 
     return true;
 }
 
+// the two words of a value `stride` words apart (word-major message layouts: a warp's store is contiguous)
+__device__ __forceinline__ void ll_store_strided(unsigned long long *dst, size_t stride, double v, unsigned tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    *reinterpret_cast<volatile unsigned long long *>(dst) = t | (b & 0xffffffffull);
+    *reinterpret_cast<volatile unsigned long long *>(dst + stride) = t | (b >> 32);
+}
+__device__ __forceinline__ bool ll_load_strided(const unsigned long long *src, size_t stride, unsigned tag, unsigned long long timeout_ns,
+                                                double *out)
+{
+    const volatile unsigned long long *p = reinterpret_cast<const volatile unsigned long long *>(src);
+    unsigned long long lo = p[0], hi = p[stride];
+    if ((unsigned)(lo >> 32) != tag || (unsigned)(hi >> 32) != tag) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            lo = p[0]; hi = p[stride];
+            if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) return false;
+        }
+    }
+    *out = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return true;
+}
+
 // one 32-byte cell-order record with a single 256-bit load (LDG.E.ENL2.256): half the L1 sector traffic of
 // a 128 + 64 bit pair when every lane gathers a different record
 __device__ __forceinline__ double4 load_rec(const double4 *p)

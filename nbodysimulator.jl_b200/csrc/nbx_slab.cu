@@ -349,8 +349,12 @@ __global__ void __launch_bounds__(256) slab_ll_send_kernel(const double *__restr
         const int side = t / capH, k = t - side * capH;
         if (k >= (side == 0 ? nL : nR)) continue;
         const int i = (side == 0 ? idxL : idxR)[k];
-        unsigned long long *w = (side == 0 ? outL : outR) + (size_t)k * kLLWords;
-        ll_store(w, pos[i], tag); ll_store(w + 2, pos[ld + i], tag); ll_store(w + 4, pos[2 * ld + i], tag);
+        // word j of halo particle k at [j][capH] + k: a warp's store is 256 contiguous bytes = eight full sectors on the
+        // link (particle-major words were 32 partial sectors per store)
+        unsigned long long *w = (side == 0 ? outL : outR) + k;
+        ll_store_strided(w, (size_t)capH, pos[i], tag);
+        ll_store_strided(w + 2 * (size_t)capH, (size_t)capH, pos[ld + i], tag);
+        ll_store_strided(w + 4 * (size_t)capH, (size_t)capH, pos[2 * ld + i], tag);
     }
 }
 
@@ -366,9 +370,10 @@ __global__ void __launch_bounds__(256) slab_ll_recv_kernel(double *__restrict__ 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int side = t / capH, k = t - side * capH;
     if (side >= 2 || k >= (side == 0 ? haloL : haloR)) return;
-    const unsigned long long *w = ll + ((size_t)side * capH + k) * kLLWords;
+    const unsigned long long *w = ll + (size_t)side * capH * kLLWords + k;
     double x, y, z;
-    if (!ll_load(w, tag, timeout_ns, &x) || !ll_load(w + 2, tag, timeout_ns, &y) || !ll_load(w + 4, tag, timeout_ns, &z)) {
+    if (!ll_load_strided(w, (size_t)capH, tag, timeout_ns, &x) || !ll_load_strided(w + 2 * (size_t)capH, (size_t)capH, tag, timeout_ns, &y) ||
+        !ll_load_strided(w + 4 * (size_t)capH, (size_t)capH, tag, timeout_ns, &z)) {
         dn[DN_TIMEOUT] = 1;
         return;
     }
