@@ -36,6 +36,93 @@ def test_header_symbols_are_exported_and_bound(lib):
     assert lib.load().nbx_version() >= 100
 
 
+def _split_args(text):
+    out, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "({[":
+            depth += 1
+        if ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _c_kind(decl):
+    """Class of one C parameter / return type of include/nbody_b200.h."""
+    d = decl.strip()
+    if d in ("void", ""):
+        return None
+    if "*" in d:
+        return "cstr" if re.match(r"const\s+char\s*\*", d) else "ptr"
+    base = re.sub(r"\b(const|unsigned)\b", lambda m: "u" if m.group(1) == "unsigned" else "", d)
+    base = re.sub(r"\s+\w+$", "", base.strip()) if " " in base.strip() else base.strip()  # drop the parameter name
+    return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "double": "f64"}[base.strip()]
+
+
+def _header_prototypes():
+    text = open(os.path.join(ROOT, "include", "nbody_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"NBX_API\s+([\w\s\*]*?)\b(nbx_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        protos[name] = (_c_kind(ret), [k for k in (_c_kind(a) for a in _split_args(args)) if k is not None])
+    return protos
+
+
+def _ctypes_kind(t):
+    if t is None:
+        return None
+    if t in (ctypes.c_char_p,):
+        return "cstr"
+    if t is ctypes.c_void_p or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+        return "ptr"
+    return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_uint64: "u64", ctypes.c_double: "f64"}[t]
+
+
+def test_ctypes_signatures_match_the_header(lib):
+    """Every prototype of include/nbody_b200.h against the ctypes binding: same arity, same class (pointer / 32- or 64-bit
+    integer / double / C string) of every parameter and of the return value."""
+    protos = _header_prototypes()
+    assert set(protos) == set(lib.SIGNATURES)
+    for name, (ret, args) in protos.items():
+        cres, cargs = lib.SIGNATURES[name]
+        assert _ctypes_kind(cres) == ret, name
+        assert [_ctypes_kind(a) for a in cargs] == args, (name, args)
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """julia/NBodySimulatorB200.jl cannot be executed here (no Julia): every ccall in it is checked statically against the
+    header -- the symbol exists, the arity is right and every argument has the class the C prototype wants."""
+    protos = _header_prototypes()
+    text = open(os.path.join(ROOT, "julia", "NBodySimulatorB200.jl")).read()
+    jl = {"Cint": "i32", "Int64": "i64", "UInt64": "u64", "Float64": "f64", "Cstring": "cstr"}
+
+    def kind(t):
+        t = t.strip()
+        return "ptr" if t.startswith(("Ptr{", "Ref{")) else jl[t]
+
+    calls = re.findall(r"ccall\(\(:(nbx_\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", text)
+    assert len(calls) >= 25
+    seen = set()
+    for name, ret, args in calls:
+        assert name in protos, f"{name} is not in include/nbody_b200.h"
+        want_ret, want_args = protos[name]
+        assert kind(ret) == want_ret, name
+        got = [kind(a) for a in _split_args(args)]
+        want = ["ptr" if k == "cstr" else k for k in want_args]
+        assert got == want, (name, got, want)
+        seen.add(name)
+    for must in ("nbx_create", "nbx_create_multi", "nbx_system", "nbx_boundary", "nbx_thermostat", "nbx_accel", "nbx_upload",
+                 "nbx_run_vv", "nbx_step_em", "nbx_download", "nbx_rdf_add", "nbx_msd"):
+        assert must in seen
+
+
 def test_library_holds_sm100a_code_only(lib):
     import shutil
     import subprocess
