@@ -206,6 +206,21 @@ def test_water_spcfw_short_run():
     assert temperature(sr, t1) == pytest.approx(np.dot(ms, (vs ** 2).sum(axis=0)) / (kb * ndf), rel=1e-12)
 
 
+def test_water_langevin_thermostating():
+    # test/water_test.jl:135-152 "Water thermostating": 216 SPC/Fw molecules, LangevinThermostat(275, 100), run_simulation(sim, EM(),
+    # dt = 0.5e-3) to t2 = 200 x 0.5e-4 (20 steps); the reference's own (loose) criterion |T2 - T0| / T0 <= 1.  The SDE is the
+    # water variant of src/nbody_to_ode.jl:600-680 (oxygen friction term, noise amplitudes divided by the mass).
+    water, L, kb = _water_system(6)
+    T0, tau = 275.0, 0.5e-3
+    t2 = 200 * 0.5e-4
+    sim = NBodySimulation(water, (0.0, t2), CubicPeriodicBoundaryConditions(L), LangevinThermostat(T0, 100.0), kb)
+    sr = run_simulation(sim, EM(), dt=tau, seed=11)
+    T2 = temperature(sr, t2)
+    assert np.isfinite(T2) and abs(T2 - T0) / T0 <= 1.0
+    x = get_position(sr, t2)
+    assert np.isfinite(x).all()
+
+
 def test_lennard_jones_rdf_and_msd():
     # test/lennard_jones_test.jl:120-150: 125 argon atoms, cubic PBC, R = 0.5 L, 400 VV steps; MSD grows, RDF peaks near sigma
     T, kb = 120.0, 8.3144598e-3
