@@ -871,7 +871,15 @@ int nbx_vv_finish(nbx_ctx *c, double dt)
     return NBX_OK;
 }
 
-int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
+// A captured two-step graph that outlives one call: nbx_run_vv keeps it across its chunks (nothing but nbx_download
+// happens in between, so every buffer and every host-side decision baked into the capture still holds).
+struct StepGraphKeep {
+    cudaGraphExec_t exec = nullptr;
+    double dt = 0.0;
+    double *acc0 = nullptr; // the acc / acc_old roles the capture started from (they swap every step)
+};
+
+static int step_vv_impl(nbx_ctx *c, double dt, int64_t nsteps, StepGraphKeep *keep)
 {
     if (c && c->is_group) return leader_step_vv(c, dt, nsteps);
     NBX_TRY(guard(c));
@@ -906,13 +914,26 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     // Long runs replay a CUDA graph of TWO steps (the acc / acc_old swap has period two): every decision inside a
     // step (Verlet rebuild, overflow fallback) is taken on the device, so the launch sequence is the same for all
     // steps.  Andersen draws from a host-side step counter and the phase timers record events: both stay eager.
-    const bool graphable = c->opt_graph && !c->timing && c->thermo != NBX_THERMO_ANDERSEN && nsteps - s >= 32 &&
-                           c->stream != nullptr && c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
-    if (graphable) {
+    const bool graph_ok = c->opt_graph && !c->timing && c->thermo != NBX_THERMO_ANDERSEN && c->stream != nullptr &&
+                          c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
+    // (a graph that will be kept pays for its capture over all chunks of the run: short chunks are worth it too)
+    const bool graphable = graph_ok && nsteps - s >= (keep ? 6 : 32);
+    if (graph_ok && keep && keep->exec && keep->dt == dt) {
+        // a kept graph: one eager step first if the acc / acc_old roles are the other way round (odd chunk lengths)
+        if (c->acc != keep->acc0) { NBX_TRY(one_step()); ++s; }
+        cudaError_t e = cudaSuccess;
+        if (c->acc == keep->acc0)
+            for (; s + 2 <= nsteps; s += 2) {
+                e = cudaGraphLaunch(keep->exec, c->stream);
+                if (e != cudaSuccess) break;
+            }
+        if (e != cudaSuccess) return cuda_fail(c, e, "CUDA graph of the velocity-Verlet step (kept)");
+    } else if (graphable) {
         for (int w = 0; w < 2; ++w, ++s) NBX_TRY(one_step()); // warm-up: allocations and attribute calls happen outside the capture
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         cudaError_t e = cudaSuccess;
+        double *const acc_at_capture = c->acc;
         if (c->opt_cond_nodes && !c->cond_fail && !c->aux_stream &&
             cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { c->aux_stream = nullptr; cudaGetLastError(); }
         for (int attempt = 0; attempt < 2; ++attempt) { // second attempt: plain capture, should the IF nodes be refused
@@ -943,6 +964,11 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
                 if (e != cudaSuccess) break;
             }
         }
+        if (exec && keep && e == cudaSuccess) {
+            if (keep->exec) cudaGraphExecDestroy(keep->exec);
+            keep->exec = exec; keep->dt = dt; keep->acc0 = acc_at_capture;
+            exec = nullptr;
+        }
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess) return cuda_fail(c, e, "CUDA graph of the velocity-Verlet step");
@@ -951,6 +977,8 @@ int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps)
     NBX_CUDA(c, cudaStreamSynchronize(c->stream));
     return NBX_OK;
 }
+
+int nbx_step_vv(nbx_ctx *c, double dt, int64_t nsteps) { return step_vv_impl(c, dt, nsteps, nullptr); }
 
 // run_simulation with saveat (src/nbody_simulation_result.jl:468-487): nsteps velocity-Verlet steps on the device, the state
 // copied out every save_every steps (and after the last one) as consecutive 3 x ncols frames -- what the Julia shim wraps
@@ -966,16 +994,20 @@ int nbx_run_vv(nbx_ctx *c, double dt, int64_t nsteps, int64_t save_every, double
     if ((u_frames || v_frames) && max_frames < need)
         return fail(c, NBX_ERR_CAPACITY, "nbx_run_vv: %lld frames needed, capacity %lld", (long long)need, (long long)max_frames);
     int64_t done = 0, k = 0;
-    while (done < nsteps) {
+    StepGraphKeep keep; // (single contexts; groups cache their graph themselves)
+    int rc = NBX_OK;
+    while (done < nsteps && rc == NBX_OK) {
         const int64_t chunk = std::min<int64_t>(save_every, nsteps - done);
-        NBX_TRY(nbx_step_vv(c, dt, chunk));
+        rc = step_vv_impl(c, dt, chunk, &keep);
         done += chunk;
-        if (u_frames || v_frames) {
+        if (rc == NBX_OK && (u_frames || v_frames)) {
             const size_t off = (size_t)k * 3 * (size_t)ncols;
-            NBX_TRY(nbx_download(c, u_frames ? u_frames + off : nullptr, v_frames ? v_frames + off : nullptr, nullptr));
+            rc = nbx_download(c, u_frames ? u_frames + off : nullptr, v_frames ? v_frames + off : nullptr, nullptr);
         }
         ++k;
     }
+    if (keep.exec) cudaGraphExecDestroy(keep.exec);
+    if (rc != NBX_OK) return rc;
     if (nframes) *nframes = k;
     return NBX_OK;
 }
