@@ -279,6 +279,42 @@ def test_water_three_molecules():
     assert s.temperature(v0, kb, N=9, Nc=6) == pytest.approx(T_exp, rel=1e-12)
 
 
+def test_water_sde_stepper_follows_the_reference_formulas():
+    """The oracle's Euler-Maruyama stepper for the SDEProblem of WaterSPCFw (src/nbody_to_ode.jl:600-680): without
+    friction and noise it is the plain Euler step of the water RHS; with friction the oxygen columns lose (gamma v) / mO more
+    than the hydrogens (:627-629, :664); the noise of one step has the amplitudes sqrt(2 gamma kb T dt) / mO and / mH
+    (:668-676)."""
+    T, kb = 298.16, 8.3144598e-3
+    mO, mH = 15.999, 1.00794
+    L = ((mO + 2 * mH) * 216 / (997 / 1.6747)) ** (1 / 3)
+    rOH, aHOH = 0.1012, 113.24 * math.pi / 180
+    rng = np.random.default_rng(5)
+    nm = 4
+    opos = rng.random((3, nm)) * L
+    u0 = np.zeros((3, 3 * nm), order="F")
+    u0[:, 0::3] = opos
+    u0[:, 1::3] = opos + np.array([[rOH], [0], [0]])
+    u0[:, 2::3] = opos + np.array([[math.cos(aHOH) * rOH], [0], [math.sin(aHOH) * rOH]])
+    v0 = np.asfortranarray(rng.standard_normal((3, 3 * nm)))
+    s = orc.System(np.tile([mO, mH, mH], nm), qs=np.tile([-0.82, 0.41, 0.41], nm), water=True, bc=("cubic", L),
+                   lj=dict(eps=0.1554253 * 4.184, sigma=0.3165492, R=0.9), coulomb=dict(k=138.935458, R=0.49 * L),
+                   spcfw=dict(rOH=rOH, aHOH=aHOH, kb=1059.162 * 4.184 * 1e2, ka=75.9 * 4.184))
+    dt = 1e-4
+    a0 = s.rhs(u0, v0)
+    u1, v1 = orc.euler_maruyama_water(s, u0, v0, dt, 1, 0.0, 0.0, mO, mH, np.random.default_rng(1))
+    assert np.array_equal(u1, u0 + dt * v0) and np.allclose(v1, v0 + dt * a0, rtol=0, atol=1e-13 * np.abs(a0).max() * dt)
+    gamma = 7.0
+    _, v2 = orc.euler_maruyama_water(s, u0, v0, dt, 1, gamma, 0.0, mO, mH, np.random.default_rng(1))
+    lost = (v1 - v2) / (dt * gamma)                    # = v for hydrogens, v (1 + 1 / mO) for oxygens
+    assert np.allclose(lost[:, 1::3], v0[:, 1::3], rtol=1e-9) and np.allclose(lost[:, 2::3], v0[:, 2::3], rtol=1e-9)
+    assert np.allclose(lost[:, 0::3], v0[:, 0::3] * (1.0 + 1.0 / mO), rtol=1e-9)
+    _, v3 = orc.euler_maruyama_water(s, u0, v0, dt, 1, gamma, kb * T, mO, mH, np.random.default_rng(2))
+    xi = np.random.default_rng(2).standard_normal(v0.shape)
+    kick = (v3 - v2) / (math.sqrt(2.0 * gamma * kb * T) * math.sqrt(dt))
+    assert np.allclose(kick[:, 0::3], xi[:, 0::3] / mO, rtol=1e-9, atol=1e-12)
+    assert np.allclose(kick[:, 1::3], xi[:, 1::3] / mH, rtol=1e-9, atol=1e-12)
+
+
 def test_berendsen_125_atoms():
     """test/thermostat_test.jl:39-56: |T2 - T0| / T0 < 0.1 after 200 steps (tau_B = 10 dt)"""
     T, T0, kb = 120.0, 90.0, 1.38e-23
