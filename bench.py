@@ -377,6 +377,34 @@ def other_configs(local, world, steps=5):
         return ctx.info("group_mode") if world > 1 else 0
 
     modes = {0: "1 GPU", 1: "pair sharding", 2: "target blocks", 3: "x-slabs"}
+
+    def parity_of(ctx, system, molecules=None, ntargets=96):
+        """One GPU: the accelerations left resident by the timed run against the CPU oracle at the resident positions, for a
+        subsample (whole molecules for water).  (Groups: the headline and the LJ run carry the multi-GPU parity figures.)"""
+        if world > 1:
+            return None
+        try:
+            from oracle import nbody_oracle as orc
+
+            u_now, _, a_now = ctx.download(want_v=False, want_dv=True)
+            rng = np.random.Generator(np.random.Philox(21))
+            if molecules is not None:
+                mols = np.sort(rng.choice(molecules, ntargets // 3, replace=False))
+                cols = (3 * mols[:, None] + np.arange(3)[None, :]).ravel()
+                ref = orc.System(**system).accel_molecules(u_now, mols, host_threads())
+            else:
+                cols = np.sort(rng.choice(u_now.shape[1], ntargets, replace=False))
+                ref = orc.System(**system).accel_targets(u_now, cols, host_threads())
+            norms = np.linalg.norm(ref, axis=0)
+            floor = 1e-3 * float(np.sqrt(np.mean(norms ** 2)))   # the tests' metric: bodies whose net acceleration cancels below
+            err = np.linalg.norm(a_now[:, cols] - ref, axis=0) / np.maximum(norms, max(floor, 1e-300))  # 1e-3 RMS are judged against it
+            return {"max_rel_err_per_body": float(err.max()), "median_rel_err_per_body": float(np.median(err)),
+                    "targets": int(len(cols)), "tolerance": 1e-12,
+                    "what": "resident accelerations after the timed steps vs the CPU oracle (fp64 restatement) at the resident "
+                            "positions; heavily cancelling sums are refereed in long double by tests/test_gpu_parity.py"}
+        except Exception as e:  # a diagnostic must not cost the line
+            return {"error": repr(e)}
+
     try:
         for tag, rel, what in (("config4_water_cutoff_0.9162nm", 0.9162, "cell lists for O-O Lennard-Jones and Coulomb"),
                                ("config4_water_cutoff_0.49L", None, "Coulomb cutoff 4.886 nm = 0.49 L (no cell list possible): every unordered pair "
@@ -393,7 +421,9 @@ def other_configs(local, world, steps=5):
             ms = timed(lambda k: ctx.step_vv(w["dt"], k), steps if rel is None else 10 * steps)
             out[tag] = {"metric": "SPC/Fw water molecule-steps/s (32,768 molecules, LJ + Coulomb cutoff + bonds/angles, velocity Verlet)",
                         "value": w["nmol"] / (ms * 1e-3), "unit": "molecule-steps/s", "ms_per_step": ms, "n_atoms": 3 * w["nmol"],
-                        "coulomb_cutoff_nm": w["coulomb"]["R"], "path": what, "n_gpus": world, "decomposition": modes[mode]}
+                        "coulomb_cutoff_nm": w["coulomb"]["R"], "path": what, "n_gpus": world, "decomposition": modes[mode],
+                        "parity": parity_of(ctx, dict(ms=w["ms"], qs=w["qs"], water=True, bc=("cubic", w["L"]), lj=w["lj"],
+                                                      coulomb=w["coulomb"], spcfw=w["spcfw"]), molecules=w["nmol"])}
             ctx.close()
         # config 2 at its largest size (the 8-GPU target of the north star): 1.1e12 pairs per evaluation
         n1 = 1048576
@@ -422,9 +452,15 @@ def other_configs(local, world, steps=5):
             mode = grouped(ctx, w["u"], w["v"])
             dt = 1e-9
             ms = timed(lambda k: ctx.step_em(dt, k), steps)
+            osys = dict(ms=w["ms"], qs=w.get("qs"), mm=w.get("mm"))
+            if "coulomb" in w:
+                osys["coulomb"] = dict(k=w["coulomb"]["k"], R=float("inf"))
+            else:
+                osys["dipole"] = w["dipole"]
             out[tag] = {"metric": "pair-interactions/s (65,536 bodies, all-pairs, Langevin thermostat, Euler-Maruyama steps)",
                         "value": float(n) * float(n - 1) / (ms * 1e-3), "unit": "pair-interactions/s", "ms_per_step": ms,
-                        "n_bodies": n, "n_gpus": world, "decomposition": modes[mode]}
+                        "n_bodies": n, "n_gpus": world, "decomposition": modes[mode],
+                        "parity": parity_of(ctx, osys)}   # (a(x_end) is left resident by nbx_step_em)
             ctx.close()
         if world == 1:
             # config 1, the reference's own CPU-runnable case (examples/liquid_argon.jl as shipped: 216 atoms, R = L/2, velocity
