@@ -121,3 +121,56 @@ def test_dipoles_against_exact_arithmetic():
     mm = np.asfortranarray(rng.standard_normal((3, 14)))
     s = orc.System(ms, mm=mm, dipole=dict(mu_4pi=1e-2))
     _close(s.rhs(u, np.zeros_like(u)), _exact(u, ms, "dipole", 1e-2, mm=mm))
+
+
+def _cross(a, b):
+    return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+
+def _unit(a):
+    n = mp.sqrt(sum(c * c for c in a))
+    return [c / n for c in a]
+
+
+def test_spcfw_bonds_and_angle_against_exact_arithmetic():
+    """harmonic_bond_potential_acceleration! (:367-393, every bond seen from both ends) and
+    valence_angle_potential_acceleration! (:395-433, called with a = H1, b = O, c = H2: src/nbody_to_ode.jl:255-260)."""
+    rng = np.random.default_rng(6)
+    nm = 5
+    mO, mH = 15.999, 1.00794
+    rOH, aHOH, kb, ka = 0.1012, 113.24 * np.pi / 180, 1059.162 * 4.184 * 1e2, 75.9 * 4.184
+    o = rng.random((3, nm)) * 2.0
+    u = np.zeros((3, 3 * nm), order="F")
+    u[:, 0::3] = o
+    u[:, 1::3] = o + np.array([[rOH], [0.0], [0.0]]) + 0.01 * rng.standard_normal((3, nm))
+    u[:, 2::3] = o + np.array([[np.cos(aHOH) * rOH], [0.0], [np.sin(aHOH) * rOH]]) + 0.01 * rng.standard_normal((3, nm))
+    ms = np.tile([mO, mH, mH], nm)
+    s = orc.System(ms, qs=np.zeros(3 * nm), water=True, spcfw=dict(rOH=rOH, aHOH=aHOH, kb=kb, ka=ka))
+    got = s.rhs(u, np.zeros_like(u))
+    exact = np.zeros_like(u)
+    M = [mp.mpf(float(m)) for m in ms]
+    for m in range(nm):
+        O, H1, H2 = 3 * m, 3 * m + 1, 3 * m + 2
+        X = {k: [mp.mpf(float(u[d, k])) for d in range(3)] for k in (O, H1, H2)}
+        acc = {k: [mp.mpf(0)] * 3 for k in (O, H1, H2)}
+        for i, j in ((O, H1), (O, H2), (H1, O), (H2, O)):
+            rij = [X[i][d] - X[j][d] for d in range(3)]
+            r = mp.sqrt(sum(c * c for c in rij))
+            fac = -(r - mp.mpf(rOH)) * mp.mpf(kb) / r
+            acc[i] = [acc[i][d] + fac * rij[d] / M[i] for d in range(3)]
+        rba = [X[H1][d] - X[O][d] for d in range(3)]
+        rbc = [X[H2][d] - X[O][d] for d in range(3)]
+        rcb = [-c for c in rbc]
+        x = _cross(rba, rbc)
+        pa, pc = _unit(_cross(rba, x)), _unit(_cross(rcb, x))
+        nba, nbc = mp.sqrt(sum(c * c for c in rba)), mp.sqrt(sum(c * c for c in rbc))
+        ang = mp.acos(sum(a * b for a, b in zip(rba, rbc)) / (nba * nbc))
+        force = -mp.mpf(ka) * (ang - mp.mpf(aHOH))
+        fa = [c * force / nba for c in pa]
+        fc = [c * force / nbc for c in pc]
+        fb = [-(a + c) for a, c in zip(fa, fc)]
+        for k, f in ((H1, fa), (O, fb), (H2, fc)):
+            acc[k] = [acc[k][d] + f[d] / M[k] for d in range(3)]
+        for k in (O, H1, H2):
+            exact[:, k] = [float(c) for c in acc[k]]
+    _close(got, exact, tol=1e-12)   # (acos near 113 degrees and the stiff bond constant amplify the last bits)
